@@ -1,0 +1,136 @@
+"""ctypes binding of libb200dm.so (include/b200dm.h).  PyTorch tensors are only the device-memory
+container: every call passes raw device pointers and the current CUDA stream.
+
+There is no CPU fallback: importing works anywhere (so host logic can be unit-tested), but any
+compute call without the library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb200dm.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
+CONV_DIRECT, CONV_PARITY, CONV_BATCHED_GEMM = 0, 1, 2
+ACT = {None: ACT_NONE, "none": ACT_NONE, "silu": ACT_SILU, "swish": ACT_SILU, "relu": ACT_RELU}
+
+
+class B200dmError(RuntimeError):
+    pass
+
+
+class UpdateDesc(C.Structure):
+    _fields_ = [("n_per_sample", C.c_int64), ("batch", C.c_int32), ("sampler", C.c_int32),
+                ("beta", C.c_void_p), ("sqrt_alpha", C.c_void_p), ("alpha_bar", C.c_void_p),
+                ("alpha_bar_prev", C.c_void_p), ("sqrt_alpha_bar", C.c_void_p), ("sqrt_alpha_bar_prev", C.c_void_p),
+                ("sqrt_one_minus_alpha_bar", C.c_void_p), ("t_dev", C.c_void_p), ("t", C.c_int32), ("t_prev", C.c_int32),
+                ("seed", C.c_uint64), ("sample_id0", C.c_int64), ("eps_dtype", C.c_int32), ("reserved", C.c_int32)]
+
+
+class NormDesc(C.Structure):
+    _fields_ = [("voxels", C.c_int64), ("batch", C.c_int32), ("c0", C.c_int32), ("c1", C.c_int32), ("kind", C.c_int32),
+                ("groups", C.c_int32), ("act", C.c_int32), ("x_dtype", C.c_int32), ("y_dtype", C.c_int32)]
+
+
+class VqDesc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("d", C.c_int32), ("k", C.c_int32), ("x_dtype", C.c_int32), ("q_dtype", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("batch", C.c_int32), ("in_d", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
+                ("c0", C.c_int32), ("c1", C.c_int32), ("c_out", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
+                ("act", C.c_int32), ("y_dtype", C.c_int32), ("chan_bias_rows", C.c_int32), ("use_halo", C.c_int32),
+                ("reserved", C.c_int32 * 4)]  # reserved[0] = post_act, reserved[1] = transposed store
+
+
+_SIGS = {
+    "b200dm_version": (C.c_int, []),
+    "b200dm_last_error": (C.c_char_p, []),
+    "b200dm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200dm_ddpm_update": (C.c_int, [C.POINTER(UpdateDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200dm_philox_normal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200dm_step_advance": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "b200dm_bn_fold": (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200dm_gn_stats": (C.c_int, [C.POINTER(NormDesc), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200dm_gn_stats_workspace": (C.c_size_t, [C.POINTER(NormDesc)]),
+    "b200dm_norm_act_fwd": (C.c_int, [C.POINTER(NormDesc)] + [C.c_void_p] * 7),
+    "b200dm_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    "b200dm_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "b200dm_vq_argmin_gather": (C.c_int, [C.POINTER(VqDesc)] + [C.c_void_p] * 7),
+    "b200dm_vq_prepare": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200dm_dense_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200dm_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "b200dm_conv_packed_weight_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "b200dm_conv_pack_weights": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int32, C.c_void_p]),
+    "b200dm_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc)] + [C.c_void_p] * 9 + [C.POINTER(C.c_void_p)]),
+    "b200dm_conv_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200dm_conv_plan_destroy": (None, [C.c_void_p]),
+    "b200dm_conv_plan_flops": (C.c_double, [C.c_void_p]),
+    "b200dm_debug_flag_read_reset": (C.c_int, [C.POINTER(C.c_int32)]),
+    "b200dm_program_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "b200dm_program_destroy": (None, [C.c_void_p]),
+    "b200dm_program_add_conv": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200dm_program_add_norm_act": (C.c_int, [C.c_void_p, C.POINTER(NormDesc)] + [C.c_void_p] * 6),
+    "b200dm_program_add_gn_stats": (C.c_int, [C.c_void_p, C.POINTER(NormDesc), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200dm_program_add_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "b200dm_program_add_softmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float]),
+    "b200dm_program_add_update": (C.c_int, [C.c_void_p, C.POINTER(UpdateDesc)] + [C.c_void_p] * 5),
+    "b200dm_program_add_step_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "b200dm_program_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200dm_program_num_launches": (C.c_int, [C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise B200dmError(f"{_LIB_PATH} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                              "There is no CPU fallback.")
+        l = C.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B200dmError(f"libb200dm error {rc}: {lib().b200dm_last_error().decode()}")
+
+
+def require_gpu():
+    if not torch.cuda.is_available():
+        raise B200dmError("libb200dm needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise B200dmError(f"unsupported dtype {t.dtype}")
+
+
+def debug_flag() -> int:
+    f = C.c_int32(0)
+    check(lib().b200dm_debug_flag_read_reset(C.byref(f)))
+    return f.value

@@ -1,0 +1,570 @@
+// K1-K5 (+ the attention matmuls): Conv3D as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   GEMM view   M = output voxels (tile = a 128-voxel box bw x bh x bd x bn of the NDHWC tensor)
+//               N = C_out (BLOCK_N columns of TMEM, fp32 accumulators)
+//               K = taps x C_in, walked as k-blocks of (tap, 64-channel chunk)
+//   A operand   TMA (cp.async.bulk.tensor.5d, SWIZZLE_128B) loads the box shifted by the tap offset straight
+//               from the bf16 NDHWC activation: out-of-bounds voxels / channels are zero-filled by the TMA
+//               unit, which IS TF 'same' padding (incl. the asymmetric (0,1) of stride-2) -- no im2col
+//               buffer, no padded copy.  Two K-segments (two tensor maps) read [x, skip] without ever
+//               materialising layers.Concatenate.
+//   B operand   packed bf16 weights [group][n_pad][chunk][tap][64], one 2-D TMA per k-block.
+//   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16 x4 per k-block, issued by one
+//               thread; accumulators live in TMEM; tcgen05.commit releases smem stages / signals the epilogue.
+//   Epilogue    4 warps: tcgen05.ld -> +bias +temb[t][n] -> PReLU/act -> +residual -> act -> bf16|fp32 NDHWC
+//               (optionally transposed per sample, for V^T of the attention blocks).
+//   PARITY mode nearest-upsample(2)+Conv3 and ConvTranspose(k4,s2) both become 8 output-parity
+//               sub-convolutions of 2^3 taps on the low-res input (blockIdx.z = parity): 27 -> 8 taps.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+#include <cuda.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include <vector>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct ConvParams {
+  int mode, batch;
+  int in_d, in_h, in_w;
+  int out_d, out_h, out_w;
+  int m_d, m_h, m_w;                 // M-space extent (== out for DIRECT / GEMM, == in for PARITY)
+  int box_w, box_h, box_d, box_n;    // product == 128
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  int nch0, nch1, ntaps, ksize, stride, pad;
+  int c_out, n_pad;
+  int act, post_act, y_f32, transposed_store;
+  int chan_bias_rows;
+  const float* bias;
+  const float* chan_bias;
+  const int* t_dev;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* prelu_alpha;  // (d,h,w,c) bf16, no batch dim
+  void* y;
+  int* dbg;
+};
+
+__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <int BLOCK_N, int NSTAGE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                  const __grid_constant__ CUtensorMap mapB, const ConvParams p) {
+  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * kStageBytes);
+  // bars[0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2NSTAGE] tmem_full; then tmem ptr
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t bar_base = ptx::smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * NSTAGE);
+
+  // tile decode
+  int bx = blockIdx.x;
+  const int tw = bx % p.tiles_w; bx /= p.tiles_w;
+  const int th = bx % p.tiles_h; bx /= p.tiles_h;
+  const int td = bx % p.tiles_d; bx /= p.tiles_d;
+  const int tn = bx;
+  const int w0 = tw * p.box_w, h0 = th * p.box_h, d0 = td * p.box_d, n0 = tn * p.box_n;
+  const int n_tile = blockIdx.y;
+  const int parity = blockIdx.z;
+  const int pw = parity & 1, ph = (parity >> 1) & 1, pd = (parity >> 2) & 1;
+  const int nkb = (p.nch0 + p.nch1) * p.ntaps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&mapA0);
+    ptx::prefetch_tmap(&mapB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int b_row = (p.mode == B200DM_CONV_PARITY ? parity : (p.mode == B200DM_CONV_BATCHED_GEMM ? n0 : 0)) * p.n_pad +
+                        n_tile * BLOCK_N;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NSTAGE;
+        const uint32_t phase = (kb / NSTAGE) & 1;
+        if (!ptx::mbar_wait(empty_bar(s), phase ^ 1, p.dbg, 1)) break;
+        const int chunk = kb / p.ntaps, tap = kb - chunk * p.ntaps;
+        int ow, oh, od;
+        if (p.mode == B200DM_CONV_PARITY) {
+          ow = (tap & 1) - 1 + pw; oh = ((tap >> 1) & 1) - 1 + ph; od = ((tap >> 2) & 1) - 1 + pd;
+        } else {
+          const int k = p.ksize;
+          ow = tap % k - p.pad; oh = (tap / k) % k - p.pad; od = tap / (k * k) - p.pad;
+        }
+        const uint32_t a_dst = smem_base + s * kStageBytes;
+        const uint32_t b_dst = a_dst + kABytes;
+        ptx::mbar_expect_tx(full_bar(s), kStageBytes);
+        if (chunk < p.nch0)
+          ptx::tma_load_5d(a_dst, &mapA0, full_bar(s), chunk * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
+        else
+          ptx::tma_load_5d(a_dst, &mapA1, full_bar(s), (chunk - p.nch0) * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
+        ptx::tma_load_2d(b_dst, &mapB, full_bar(s), kb * 64, b_row);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
+      bool ok = true;
+      for (int kb = 0; kb < nkb && ok; ++kb) {
+        const int s = kb % NSTAGE;
+        const uint32_t phase = (kb / NSTAGE) & 1;
+        ok = ptx::mbar_wait(full_bar(s), phase, p.dbg, 2);
+        if (!ok) break;
+        ptx::tc_fence_after();
+        const uint32_t a_addr = smem_base + s * kStageBytes;
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t da = ptx::make_smem_desc(a_addr + ks * 32, 16, 1024, ptx::kLayoutSw128);
+          const uint64_t db = ptx::make_smem_desc(b_addr + ks * 32, 16, 1024, ptx::kLayoutSw128);
+          ptx::tc_mma_f16(tmem_base, da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(empty_bar(s));
+      }
+      ptx::tc_commit(tmem_full_bar);
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int t = r;
+    const int iw = t % p.box_w; t /= p.box_w;
+    const int ih = t % p.box_h; t /= p.box_h;
+    const int id = t % p.box_d; t /= p.box_d;
+    const int in_ = t;
+    const int mw = w0 + iw, mh = h0 + ih, md = d0 + id, n = n0 + in_;
+    const bool valid = (mw < p.m_w) && (mh < p.m_h) && (md < p.m_d) && (n < p.batch);
+    int ow = mw, oh = mh, od = md;
+    if (p.mode == B200DM_CONV_PARITY) { ow = 2 * mw + pw; oh = 2 * mh + ph; od = 2 * md + pd; }
+    const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;           // voxel index within the sample
+    const int64_t vox_per = (int64_t)p.out_d * p.out_h * p.out_w;
+    const int64_t row_off = ((int64_t)n * vox_per + vox) * p.c_out;             // NDHWC element offset of channel 0
+    const float* cb = nullptr;
+    if (p.chan_bias && valid) {
+      const int tt = p.t_dev ? p.t_dev[0] : 0;
+      cb = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + n) * p.c_out;
+    }
+    const bool ok = ptx::mbar_wait(tmem_full_bar, 0, p.dbg, 3);
+    ptx::tc_fence_after();
+    if (ok) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        const int col0 = n_tile * BLOCK_N + c0;
+        if (col0 >= p.c_out) break;  // warp-uniform
+        uint32_t rr[16];
+        ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
+        ptx::tc_wait_ld();
+        if (!valid) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+        const int ncol = (p.c_out - col0) < 16 ? (p.c_out - col0) : 16;
+        if (ncol == 16 && !p.transposed_store) {
+          // vector path: 16 channels = 32 B bf16 / 64 B fp32 per thread
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (cb) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (p.prelu_alpha) {
+            float a[16];
+            const __nv_bfloat16* ap = p.prelu_alpha + vox * p.c_out + col0;
+            unpack8(*reinterpret_cast<const bf16x8*>(ap), *reinterpret_cast<float(*)[8]>(&a[0]));
+            unpack8(*reinterpret_cast<const bf16x8*>(ap + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) + a[j] * fminf(v[j], 0.f);
+          }
+          if (p.act != B200DM_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.residual) {
+            float a[16];
+            const __nv_bfloat16* rp = p.residual + row_off + col0;
+            unpack8(*reinterpret_cast<const bf16x8*>(rp), *reinterpret_cast<float(*)[8]>(&a[0]));
+            unpack8(*reinterpret_cast<const bf16x8*>(rp + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += a[j];
+          }
+          if (p.post_act != B200DM_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+          }
+          if (p.y_f32) {
+            float* yo = reinterpret_cast<float*>(p.y) + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + row_off + col0;
+            *reinterpret_cast<bf16x8*>(yo) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
+            *reinterpret_cast<bf16x8*>(yo + 8) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
+          }
+        } else {
+          // scalar path: ragged channel tail (e.g. C_out = 1) or per-sample transposed store
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < ncol) {
+              const int col = col0 + j;
+              float x = v[j];
+              if (p.bias) x += __ldg(p.bias + col);
+              if (cb) x += __ldg(cb + col);
+              if (p.prelu_alpha) { const float a = bf(p.prelu_alpha[vox * p.c_out + col]); x = fmaxf(x, 0.f) + a * fminf(x, 0.f); }
+              x = apply_act(x, p.act);
+              if (p.residual) x += bf(p.residual[row_off + col]);
+              x = apply_act(x, p.post_act);
+              const int64_t o = p.transposed_store ? ((int64_t)n * p.c_out + col) * vox_per + vox : row_off + col;
+              if (p.y_f32) reinterpret_cast<float*>(p.y)[o] = x;
+              else reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+struct Geometry {
+  int ntaps, pad, groups, nch0, nch1, n_pad, block_n;
+  int out_d, out_h, out_w, m_d, m_h, m_w;
+  int box_w, box_h, box_d, box_n;
+  size_t ktot;
+};
+
+int compute_geometry(const b200dm_conv_desc* d, Geometry* g) {
+  B2_CHECK_ARG(d, "conv: null desc");
+  B2_CHECK_ARG(d->mode >= 0 && d->mode <= 2, "conv: bad mode %d", d->mode);
+  B2_CHECK_ARG(d->batch > 0 && d->in_d > 0 && d->in_h > 0 && d->in_w > 0, "conv: empty input");
+  B2_CHECK_ARG(d->c0 > 0 && d->c0 % 8 == 0 && d->c1 >= 0 && d->c1 % 8 == 0, "conv: C_in segments must be multiples of 8 (got %d,%d)", d->c0, d->c1);
+  B2_CHECK_ARG(d->c_out > 0, "conv: c_out must be > 0");
+  g->nch0 = (d->c0 + 63) / 64;
+  g->nch1 = (d->c1 + 63) / 64;
+  if (d->mode == B200DM_CONV_DIRECT) {
+    B2_CHECK_ARG(d->ksize == 1 || d->ksize == 3 || d->ksize == 4, "conv: ksize %d unsupported", d->ksize);
+    B2_CHECK_ARG(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
+    g->ntaps = d->ksize * d->ksize * d->ksize;
+    g->groups = 1;
+    g->out_d = (d->in_d + d->stride - 1) / d->stride;
+    g->out_h = (d->in_h + d->stride - 1) / d->stride;
+    g->out_w = (d->in_w + d->stride - 1) / d->stride;
+    // TF 'same': total = max((out-1)*s + k - in, 0), before = total/2.  Cubic volumes: same pad on all axes.
+    B2_CHECK_ARG(d->in_d == d->in_h || d->stride == 1, "conv: strided conv needs equal D,H,W");
+    int total = (g->out_w - 1) * d->stride + d->ksize - d->in_w;
+    if (total < 0) total = 0;
+    g->pad = total / 2;
+    if (d->stride == 2) {
+      int td = (g->out_d - 1) * 2 + d->ksize - d->in_d, th = (g->out_h - 1) * 2 + d->ksize - d->in_h;
+      B2_CHECK_ARG((td < 0 ? 0 : td) / 2 == g->pad && (th < 0 ? 0 : th) / 2 == g->pad, "conv: strided conv needs the same 'same' padding on all axes");
+    }
+    g->m_d = g->out_d; g->m_h = g->out_h; g->m_w = g->out_w;
+  } else if (d->mode == B200DM_CONV_PARITY) {
+    B2_CHECK_ARG(d->ksize == 3 || d->ksize == 4, "conv: parity mode needs ksize 3 (upsample fold) or 4 (transposed conv)");
+    g->ntaps = 8; g->groups = 8; g->pad = 0;
+    g->out_d = 2 * d->in_d; g->out_h = 2 * d->in_h; g->out_w = 2 * d->in_w;
+    g->m_d = d->in_d; g->m_h = d->in_h; g->m_w = d->in_w;
+  } else {
+    B2_CHECK_ARG(d->in_d == 1 && d->in_h == 1, "conv: batched GEMM uses in_d = in_h = 1, in_w = rows");
+    B2_CHECK_ARG(d->c1 == 0, "conv: batched GEMM takes one K segment");
+    g->ntaps = 1; g->groups = d->batch; g->pad = 0;
+    g->out_d = 1; g->out_h = 1; g->out_w = d->in_w;
+    g->m_d = 1; g->m_h = 1; g->m_w = d->in_w;
+  }
+  if (d->c_out <= 16) g->n_pad = 16;
+  else if (d->c_out <= 32) g->n_pad = 32;
+  else if (d->c_out <= 64) g->n_pad = 64;
+  else g->n_pad = ((d->c_out + 127) / 128) * 128;
+  g->block_n = g->n_pad < 128 ? g->n_pad : 128;
+  g->ktot = (size_t)(g->nch0 + g->nch1) * g->ntaps * 64;
+  // M tile box, product 128
+  if (d->mode == B200DM_CONV_BATCHED_GEMM) {
+    g->box_w = 128; g->box_h = 1; g->box_d = 1; g->box_n = 1;
+  } else {
+    int bw = pow2_ceil(g->m_w); if (bw > 8) bw = 8;
+    int bh = pow2_ceil(g->m_h); if (bh > 128 / bw) bh = 128 / bw; if (bh > 16) bh = 16;
+    int bd = pow2_ceil(g->m_d); if (bd > 128 / (bw * bh)) bd = 128 / (bw * bh);
+    int bn = 128 / (bw * bh * bd);
+    g->box_w = bw; g->box_h = bh; g->box_d = bd; g->box_n = bn;
+  }
+  return B200DM_OK;
+}
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+struct b200dm_conv_plan {
+  b200dm_conv_desc desc;
+  Geometry g;
+  ConvParams p;
+  CUtensorMap mapA0, mapA1, mapB;
+  dim3 grid;
+  size_t smem;
+  int nstage;
+  double flops;
+};
+
+static int* g_dbg_flag = nullptr;
+static int ensure_dbg_flag() {
+  if (!g_dbg_flag) {
+    B2_CHECK_CUDA(cudaMalloc(&g_dbg_flag, sizeof(int)));
+    B2_CHECK_CUDA(cudaMemset(g_dbg_flag, 0, sizeof(int)));
+  }
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_debug_flag_read_reset(int32_t* flag_out) {
+  B2_CHECK_ARG(flag_out, "debug_flag: null");
+  *flag_out = 0;
+  if (!g_dbg_flag) return B200DM_OK;
+  B2_CHECK_CUDA(cudaMemcpy(flag_out, g_dbg_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  B2_CHECK_CUDA(cudaMemset(g_dbg_flag, 0, sizeof(int)));
+  return B200DM_OK;
+}
+
+extern "C" size_t b200dm_conv_packed_weight_bytes(const b200dm_conv_desc* d) {
+  Geometry g;
+  if (compute_geometry(d, &g) != B200DM_OK) return 0;
+  if (d->mode == B200DM_CONV_BATCHED_GEMM) return 0;
+  return (size_t)g.groups * g.n_pad * g.ktot * 2;
+}
+
+extern "C" int b200dm_conv_pack_weights(const b200dm_conv_desc* d, const float* w, int32_t transposed, void* packed) {
+  Geometry g;
+  int rc = compute_geometry(d, &g);
+  if (rc) return rc;
+  B2_CHECK_ARG(w && packed, "conv_pack_weights: null pointer");
+  B2_CHECK_ARG(d->mode != B200DM_CONV_BATCHED_GEMM, "conv_pack_weights: batched GEMM has no packed weights");
+  const int k = d->ksize, cin = d->c0 + d->c1, cout = d->c_out;
+  uint16_t* out = reinterpret_cast<uint16_t*>(packed);
+  memset(out, 0, (size_t)g.groups * g.n_pad * g.ktot * 2);
+  // Keras kernel index: ((kd*k + kh)*k + kw) * cin*cout + (transposed ? co*cin + ci : ci*cout + co)
+  auto W = [&](int kd, int kh, int kw, int ci, int co) -> float {
+    const size_t base = ((size_t)(kd * k + kh) * k + kw) * (size_t)cin * cout;
+    return transposed ? w[base + (size_t)co * cin + ci] : w[base + (size_t)ci * cout + co];
+  };
+  const int nch = g.nch0 + g.nch1;
+  for (int grp = 0; grp < g.groups; ++grp) {
+    const int pw = grp & 1, ph = (grp >> 1) & 1, pd = (grp >> 2) & 1;
+    for (int co = 0; co < cout; ++co) {
+      uint16_t* row = out + ((size_t)grp * g.n_pad + co) * g.ktot;
+      for (int ch = 0; ch < nch; ++ch) {
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+          for (int c = 0; c < 64; ++c) {
+            int ci;
+            if (ch < g.nch0) { ci = ch * 64 + c; if (ci >= d->c0) continue; }
+            else { ci = (ch - g.nch0) * 64 + c; if (ci >= d->c1) continue; ci += d->c0; }
+            float v = 0.f;
+            if (d->mode == B200DM_CONV_DIRECT) {
+              v = W(tap / (k * k), (tap / k) % k, tap % k, ci, co);
+            } else {
+              const int tw = tap & 1, th = (tap >> 1) & 1, tdp = (tap >> 2) & 1;
+              if (k == 3) {
+                // nearest-upsample fold: parity 0: slot0 (offset -1) <- {k0}, slot1 (offset 0) <- {k1,k2};
+                //                        parity 1: slot0 (offset 0) <- {k0,k1}, slot1 (offset +1) <- {k2}
+                auto lo = [](int par, int slot) { return par == 0 ? (slot == 0 ? 0 : 1) : (slot == 0 ? 0 : 2); };
+                auto hi = [](int par, int slot) { return par == 0 ? (slot == 0 ? 0 : 2) : (slot == 0 ? 1 : 2); };
+                double acc = 0.0;
+                for (int kd = lo(pd, tdp); kd <= hi(pd, tdp); ++kd)
+                  for (int kh = lo(ph, th); kh <= hi(ph, th); ++kh)
+                    for (int kw = lo(pw, tw); kw <= hi(pw, tw); ++kw) acc += (double)W(kd, kh, kw, ci, co);
+                v = (float)acc;
+              } else {
+                // transposed conv k4 s2 'same': out[2m+p] = sum_off in[m+off] * w[p + 1 - 2*off], off = slot - 1 + p
+                auto kk = [](int par, int slot) { return par + 1 - 2 * (slot - 1 + par); };
+                v = W(kk(pd, tdp), kk(ph, th), kk(pw, tw), ci, co);
+              }
+            }
+            row[((size_t)ch * g.ntaps + tap) * 64 + c] = f32_to_bf16_rne(v);
+          }
+        }
+      }
+    }
+  }
+  return B200DM_OK;
+}
+
+template <int BLOCK_N, int NSTAGE>
+static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
+  auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    attr_set = true;
+  }
+  kern<<<pl->grid, kThreads, pl->smem, s>>>(pl->mapA0, pl->mapA1, pl->mapB, pl->p);
+  B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}
+
+static size_t conv_smem_bytes(int block_n, int nstage) {
+  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (2 * nstage + 1) * 8 + 16;
+}
+
+extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const void* x1, const void* w_packed,
+                                       const float* bias, const float* chan_bias, const int32_t* t_dev,
+                                       const void* residual, const void* prelu_alpha, void* y,
+                                       b200dm_conv_plan** out) {
+  B2_CHECK_ARG(out, "conv_plan_create: null out");
+  *out = nullptr;
+  Geometry g;
+  int rc = compute_geometry(d, &g);
+  if (rc) return rc;
+  B2_CHECK_ARG(x0 && w_packed && y, "conv_plan_create: null tensor pointer");
+  B2_CHECK_ARG((d->c1 > 0) == (x1 != nullptr), "conv_plan_create: x1 must be given iff c1 > 0");
+  B2_CHECK_ARG(d->y_dtype == B200DM_BF16 || d->y_dtype == B200DM_F32, "conv_plan_create: bad y dtype");
+  B2_CHECK_ARG(((uintptr_t)x0 & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv_plan_create: pointers must be 16-byte aligned");
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { b200dm_set_error("conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return B200DM_ERR_CUDA; }
+  rc = ensure_dbg_flag();
+  if (rc) return rc;
+
+  b200dm_conv_plan* pl = new (std::nothrow) b200dm_conv_plan();
+  B2_CHECK_ARG(pl, "conv_plan_create: out of memory");
+  pl->desc = *d;
+  pl->g = g;
+  const int st = d->mode == B200DM_CONV_DIRECT ? d->stride : 1;
+  auto encodeA = [&](CUtensorMap* m, const void* ptr, int C) -> int {
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->in_d, (cuuint64_t)d->batch};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)d->in_w * C * 2, (cuuint64_t)d->in_h * d->in_w * C * 2,
+                             (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)(g.box_w * st), (cuuint32_t)(g.box_h * st), (cuuint32_t)(g.box_d * st), (cuuint32_t)g.box_n};
+    cuuint32_t es[5] = {1, (cuuint32_t)st, (cuuint32_t)st, (cuuint32_t)st, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200dm_set_error("cuTensorMapEncodeTiled(A) failed: %d (C=%d dims %d,%d,%d,%d box %d,%d,%d,%d stride %d)", (int)r, C, d->in_w, d->in_h, d->in_d, d->batch, g.box_w, g.box_h, g.box_d, g.box_n, st); return B200DM_ERR_CUDA; }
+    return B200DM_OK;
+  };
+  rc = encodeA(&pl->mapA0, x0, d->c0);
+  if (rc) { delete pl; return rc; }
+  rc = encodeA(&pl->mapA1, d->c1 > 0 ? x1 : x0, d->c1 > 0 ? d->c1 : d->c0);
+  if (rc) { delete pl; return rc; }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)g.ktot, (cuuint64_t)g.groups * g.n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)g.ktot * 2};
+    if (d->mode == B200DM_CONV_BATCHED_GEMM) {
+      // B is a raw activation tensor [batch][c_out rows][K = c0]; rows beyond c_out of a sample alias the next sample
+      // (masked by the epilogue's col < c_out), K beyond c0 is zero-filled by TMA.
+      dims[0] = (cuuint64_t)d->c0; dims[1] = (cuuint64_t)d->batch * d->c_out; strides[0] = (cuuint64_t)d->c0 * 2;
+    }
+    cuuint32_t box[2] = {64, (cuuint32_t)g.block_n};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200dm_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete pl; return B200DM_ERR_CUDA; }
+  }
+  ConvParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.mode = d->mode; p.batch = d->batch;
+  p.in_d = d->in_d; p.in_h = d->in_h; p.in_w = d->in_w;
+  p.out_d = g.out_d; p.out_h = g.out_h; p.out_w = g.out_w;
+  p.m_d = g.m_d; p.m_h = g.m_h; p.m_w = g.m_w;
+  p.box_w = g.box_w; p.box_h = g.box_h; p.box_d = g.box_d; p.box_n = g.box_n;
+  p.tiles_w = (g.m_w + g.box_w - 1) / g.box_w; p.tiles_h = (g.m_h + g.box_h - 1) / g.box_h;
+  p.tiles_d = (g.m_d + g.box_d - 1) / g.box_d; p.tiles_n = (d->batch + g.box_n - 1) / g.box_n;
+  p.nch0 = g.nch0; p.nch1 = g.nch1; p.ntaps = g.ntaps; p.ksize = d->ksize; p.stride = st; p.pad = g.pad;
+  p.c_out = d->c_out; p.n_pad = d->mode == B200DM_CONV_BATCHED_GEMM ? d->c_out : g.n_pad;
+  p.act = d->act; p.post_act = d->reserved[0]; p.y_f32 = d->y_dtype == B200DM_F32; p.transposed_store = d->reserved[1];
+  p.chan_bias_rows = d->chan_bias_rows;
+  p.bias = bias; p.chan_bias = chan_bias; p.t_dev = t_dev;
+  p.residual = (const __nv_bfloat16*)residual; p.prelu_alpha = (const __nv_bfloat16*)prelu_alpha;
+  p.y = y; p.dbg = g_dbg_flag;
+  const long long mtiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  if (mtiles > 0x7fffffffLL) { delete pl; b200dm_set_error("conv_plan_create: too many tiles"); return B200DM_ERR_INVALID; }
+  const int ntiles = d->mode == B200DM_CONV_BATCHED_GEMM ? (d->c_out + g.block_n - 1) / g.block_n : g.n_pad / g.block_n;
+  pl->grid = dim3((unsigned)mtiles, (unsigned)ntiles, d->mode == B200DM_CONV_PARITY ? 8 : 1);
+  pl->nstage = 4;
+  pl->smem = conv_smem_bytes(g.block_n, pl->nstage);
+  // algorithmic FLOPs: 2*k^3*Cin*Cout*B*out_voxels; convT: 2*64*Cin*Cout*B*in_voxels; GEMM: 2*M*N*K
+  if (d->mode == B200DM_CONV_PARITY)
+    pl->flops = d->ksize == 3 ? 2.0 * 27 * (d->c0 + d->c1) * d->c_out * (double)d->batch * g.out_d * g.out_h * g.out_w
+                              : 2.0 * 64 * (d->c0 + d->c1) * d->c_out * (double)d->batch * d->in_d * d->in_h * d->in_w;
+  else
+    pl->flops = 2.0 * g.ntaps * (d->c0 + d->c1) * d->c_out * (double)d->batch * g.out_d * g.out_h * g.out_w;
+  *out = pl;
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
+  B2_CHECK_ARG(pl, "conv_plan_run: null plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (pl->g.block_n) {
+    case 16: return launch_conv<16, 4>(pl, s);
+    case 32: return launch_conv<32, 4>(pl, s);
+    case 64: return launch_conv<64, 4>(pl, s);
+    case 128: return launch_conv<128, 4>(pl, s);
+  }
+  b200dm_set_error("conv_plan_run: unsupported BLOCK_N %d", pl->g.block_n);
+  return B200DM_ERR_UNSUPPORTED;
+}
+
+extern "C" void b200dm_conv_plan_destroy(b200dm_conv_plan* p) { delete p; }
+
+extern "C" double b200dm_conv_plan_flops(const b200dm_conv_plan* p) { return p ? p->flops : 0.0; }

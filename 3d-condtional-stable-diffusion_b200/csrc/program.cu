@@ -1,0 +1,130 @@
+// Step program: an ordered list of kernel invocations over fixed buffers, replayed natively with one
+// call per U-Net forward / decode (the reference drives one eager TF op at a time from Python,
+// networks/dm3d.py:516-530).  Every launch goes to the caller's stream, so the whole program is
+// CUDA-graph capturable; timestep-dependent inputs are read through device pointers (t_dev).
+#include <vector>
+#include <new>
+#include "common.cuh"
+
+namespace {
+enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE };
+struct Op {
+  OpKind kind;
+  b200dm_conv_plan* conv = nullptr;
+  b200dm_norm_desc nd{};
+  b200dm_update_desc ud{};
+  const void* p0 = nullptr; const void* p1 = nullptr; const void* p2 = nullptr; const void* p3 = nullptr; const void* p4 = nullptr;
+  void* out = nullptr; void* out2 = nullptr;
+  float f0 = 0.f;
+  int64_t i0 = 0; int32_t i1 = 0, i2 = 0;
+  size_t ws = 0;
+  const float* gam[3] = {nullptr, nullptr, nullptr};
+  const float* bet[3] = {nullptr, nullptr, nullptr};
+  void* ys[3] = {nullptr, nullptr, nullptr};
+  int launches = 1;
+};
+}  // namespace
+
+struct b200dm_program {
+  std::vector<Op> ops;
+};
+
+extern "C" int b200dm_program_create(b200dm_program** out) {
+  B2_CHECK_ARG(out, "program_create: null out");
+  *out = new (std::nothrow) b200dm_program();
+  B2_CHECK_ARG(*out, "program_create: out of memory");
+  return B200DM_OK;
+}
+
+extern "C" void b200dm_program_destroy(b200dm_program* p) {
+  if (!p) return;
+  for (auto& op : p->ops)
+    if (op.kind == OP_CONV) b200dm_conv_plan_destroy(op.conv);
+  delete p;
+}
+
+extern "C" int b200dm_program_add_conv(b200dm_program* p, b200dm_conv_plan* plan) {
+  B2_CHECK_ARG(p && plan, "program_add_conv: null argument");
+  Op op; op.kind = OP_CONV; op.conv = plan;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_norm_act(b200dm_program* p, const b200dm_norm_desc* d, const void* x0, const void* x1,
+                                           const float* a, const float* b, const float* mean_rstd, void* y) {
+  B2_CHECK_ARG(p && d && x0 && a && b && y, "program_add_norm_act: null argument");
+  Op op; op.kind = OP_NORM; op.nd = *d; op.p0 = x0; op.p1 = x1; op.p2 = a; op.p3 = b; op.p4 = mean_rstd; op.out = y;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_gn_stats(b200dm_program* p, const b200dm_norm_desc* d, const void* x, float eps,
+                                           float* mean_rstd, float* workspace, size_t ws_bytes) {
+  B2_CHECK_ARG(p && d && x && mean_rstd && workspace, "program_add_gn_stats: null argument");
+  Op op; op.kind = OP_GNSTATS; op.nd = *d; op.p0 = x; op.f0 = eps; op.out = mean_rstd; op.out2 = workspace; op.ws = ws_bytes;
+  op.launches = 2;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_layernorm(b200dm_program* p, const void* x, int64_t rows, int32_t c, float eps,
+                                            int32_t n_out, const float* const* gammas, const float* const* betas,
+                                            void* const* ys) {
+  B2_CHECK_ARG(p && x && gammas && betas && ys && n_out >= 1 && n_out <= 3, "program_add_layernorm: bad argument");
+  Op op; op.kind = OP_LN; op.p0 = x; op.i0 = rows; op.i1 = c; op.f0 = eps; op.i2 = n_out;
+  for (int i = 0; i < n_out; ++i) { op.gam[i] = gammas[i]; op.bet[i] = betas[i]; op.ys[i] = ys[i]; }
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_softmax(b200dm_program* p, const float* s, void* p_bf16, int64_t rows, int32_t cols,
+                                          float scale) {
+  B2_CHECK_ARG(p && s && p_bf16, "program_add_softmax: null argument");
+  Op op; op.kind = OP_SOFTMAX; op.p0 = s; op.out = p_bf16; op.i0 = rows; op.i1 = cols; op.f0 = scale;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_update(b200dm_program* p, const b200dm_update_desc* d, const float* x_t, const void* eps,
+                                         const float* noise, float* x_prev, void* x_prev_bf16) {
+  B2_CHECK_ARG(p && d && x_t && eps && x_prev, "program_add_update: null argument");
+  Op op; op.kind = OP_UPDATE; op.ud = *d; op.p0 = x_t; op.p1 = eps; op.p2 = noise; op.out = x_prev; op.out2 = x_prev_bf16;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_step_advance(b200dm_program* p, int32_t* t_dev, int32_t delta) {
+  B2_CHECK_ARG(p && t_dev, "program_add_step_advance: null argument");
+  Op op; op.kind = OP_ADVANCE; op.out = t_dev; op.i1 = delta;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_num_launches(const b200dm_program* p) {
+  if (!p) return 0;
+  int n = 0;
+  for (const auto& op : p->ops) n += op.launches;
+  return n;
+}
+
+extern "C" int b200dm_program_run(b200dm_program* p, void* stream) {
+  B2_CHECK_ARG(p, "program_run: null program");
+  int rc = B200DM_OK;
+  for (auto& op : p->ops) {
+    switch (op.kind) {
+      case OP_CONV: rc = b200dm_conv_plan_run(op.conv, stream); break;
+      case OP_NORM:
+        rc = b200dm_norm_act_fwd(&op.nd, op.p0, op.p1, (const float*)op.p2, (const float*)op.p3, (const float*)op.p4, op.out, stream);
+        break;
+      case OP_GNSTATS: rc = b200dm_gn_stats(&op.nd, op.p0, op.f0, (float*)op.out, (float*)op.out2, op.ws, stream); break;
+      case OP_LN: rc = b200dm_layernorm_fwd(op.p0, op.i0, op.i1, op.f0, op.i2, op.gam, op.bet, op.ys, stream); break;
+      case OP_SOFTMAX: rc = b200dm_softmax_rows((const float*)op.p0, op.out, op.i0, op.i1, op.f0, stream); break;
+      case OP_UPDATE:
+        rc = b200dm_ddpm_update(&op.ud, (const float*)op.p0, op.p1, (const float*)op.p2, (float*)op.out, op.out2, stream);
+        break;
+      case OP_ADVANCE: rc = b200dm_step_advance((int32_t*)op.out, op.i1, stream); break;
+    }
+    if (rc != B200DM_OK) return rc;
+  }
+  return B200DM_OK;
+}

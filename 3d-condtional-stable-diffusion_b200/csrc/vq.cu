@@ -1,0 +1,186 @@
+// K11: VQ nearest-code search + embedding gather (+ usage histogram) as a shared-memory-tiled
+// distance kernel.  d = (||x||^2 + ||e||^2) - 2 x.e in fp32 exactly as VectorQuantizer.get_code_indices
+// writes it (networks/vqvae3d_monai.py:165-177), argmin with the lowest index on ties, then the
+// gather q = E[idx] (the one_hot @ E^T / embedding_lookup of :139-144, vqgan_attn_cp.py:215).
+// fp32 SIMT on purpose: the ranking must be reproducible to the last bit (bf16/TF32 tensor-core
+// products flip near-ties); 128x128 block tile, 8x8 register tile, the (N,K) distance matrix
+// never leaves the SM.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+__global__ void sqnorm_kernel(const float* __restrict__ e, int K, int D, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s = __fadd_rn(s, __fmul_rn(e[(int64_t)k * D + d], e[(int64_t)k * D + d]));
+  out[k] = s;
+}
+
+template <bool kBf16>
+__device__ __forceinline__ float4 load_x4(const void* x, int64_t row, int D, int d, int64_t N) {
+  if (row >= N || d >= D) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kBf16) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * D + d);
+    const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row * D + d));
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256) vq_kernel(b200dm_vq_desc dsc, const void* __restrict__ x,
+                                                 const float* __restrict__ cb, const float* __restrict__ esq,
+                                                 int64_t* __restrict__ idx_out, void* __restrict__ q_out,
+                                                 int32_t* __restrict__ hist) {
+  __shared__ float Xs[BK][BM + PAD];
+  __shared__ float Es[BK][BN + PAD];
+  __shared__ float xsq_s[BM];
+  __shared__ float rbest[BM][17];
+  __shared__ int ribest[BM][17];
+  __shared__ int final_idx[BM];
+
+  const int D = dsc.d, K = dsc.k;
+  const int64_t N = dsc.n;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+
+  // ||x||^2 per row, sequential fp32 (2 threads per row would reorder the sum: keep one thread per row)
+  if (tid < BM) {
+    const int64_t r = row0 + tid;
+    float s = 0.f;
+    if (r < N) {
+      for (int d = 0; d < D; d += 4) {
+        const float4 v = load_x4<kBf16>(x, r, D, d, N);
+        s = __fadd_rn(s, __fmul_rn(v.x, v.x)); s = __fadd_rn(s, __fmul_rn(v.y, v.y));
+        s = __fadd_rn(s, __fmul_rn(v.z, v.z)); s = __fadd_rn(s, __fmul_rn(v.w, v.w));
+      }
+    }
+    xsq_s[tid] = s;
+  }
+
+  float best[8];
+  int besti[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = INFINITY; besti[i] = 0x7fffffff; }
+
+  const int lrow = tid >> 2, ld = (tid & 3) << 2;  // loader: rows lrow, lrow+64; 4 consecutive d
+  for (int n0 = 0; n0 < K; n0 += BN) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int d0 = 0; d0 < D; d0 += BK) {
+      float4 xa = load_x4<kBf16>(x, row0 + lrow, D, d0 + ld, N);
+      float4 xb = load_x4<kBf16>(x, row0 + lrow + 64, D, d0 + ld, N);
+      float4 ea = (n0 + lrow < K && d0 + ld < D) ? __ldg(reinterpret_cast<const float4*>(cb + (int64_t)(n0 + lrow) * D + d0 + ld)) : make_float4(0, 0, 0, 0);
+      float4 eb = (n0 + lrow + 64 < K && d0 + ld < D) ? __ldg(reinterpret_cast<const float4*>(cb + (int64_t)(n0 + lrow + 64) * D + d0 + ld)) : make_float4(0, 0, 0, 0);
+      __syncthreads();
+      Xs[ld + 0][lrow] = xa.x; Xs[ld + 1][lrow] = xa.y; Xs[ld + 2][lrow] = xa.z; Xs[ld + 3][lrow] = xa.w;
+      Xs[ld + 0][lrow + 64] = xb.x; Xs[ld + 1][lrow + 64] = xb.y; Xs[ld + 2][lrow + 64] = xb.z; Xs[ld + 3][lrow + 64] = xb.w;
+      Es[ld + 0][lrow] = ea.x; Es[ld + 1][lrow] = ea.y; Es[ld + 2][lrow] = ea.z; Es[ld + 3][lrow] = ea.w;
+      Es[ld + 0][lrow + 64] = eb.x; Es[ld + 1][lrow + 64] = eb.y; Es[ld + 2][lrow + 64] = eb.z; Es[ld + 3][lrow + 64] = eb.w;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[8], b[8];
+        *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+        *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&Xs[k][64 + ty * 4]);
+        *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Es[k][tx * 4]);
+        *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Es[k][64 + tx * 4]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+    // distances for this code tile; running first-min per row
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int code = n0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (code < K) {
+        const float e2 = __ldg(esq + code);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+          const float dist = __fsub_rn(__fadd_rn(xsq_s[r], e2), __fmul_rn(2.0f, acc[i][j]));
+          if (dist < best[i] || (dist == best[i] && code < besti[i])) { best[i] = dist; besti[i] = code; }
+        }
+      }
+    }
+  }
+  // cross-thread (16 threads share a row) reduction
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+    rbest[r][tx] = best[i];
+    ribest[r][tx] = besti[i];
+  }
+  __syncthreads();
+  if (tid < BM) {
+    float b = rbest[tid][0];
+    int bi = ribest[tid][0];
+    for (int t = 1; t < 16; ++t) {
+      const float v = rbest[tid][t];
+      const int vi = ribest[tid][t];
+      if (v < b || (v == b && vi < bi)) { b = v; bi = vi; }
+    }
+    final_idx[tid] = bi;
+    const int64_t r = row0 + tid;
+    if (r < N) {
+      idx_out[r] = (int64_t)bi;
+      if (hist) atomicAdd(hist + bi, 1);
+    }
+  }
+  __syncthreads();
+  if (q_out) {
+    // gather: 128 rows x D, 16-byte vectors, one warp streams one row at a time
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < BM; r += 8) {
+      const int64_t gr = row0 + r;
+      if (gr >= N) break;
+      const float* src = cb + (int64_t)final_idx[r] * D;
+      for (int d = lane * 4; d < D; d += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+        if (dsc.q_dtype == B200DM_F32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(q_out) + gr * D + d) = v;
+        } else {
+          __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(q_out) + gr * D + d);
+          o[0] = __floats2bfloat162_rn(v.x, v.y);
+          o[1] = __floats2bfloat162_rn(v.z, v.w);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int b200dm_vq_prepare(const float* codebook_kd, int32_t k, int32_t d, float* code_sqnorm, void* stream) {
+  B2_CHECK_ARG(codebook_kd && code_sqnorm && k > 0 && d > 0, "vq_prepare: bad arguments");
+  sqnorm_kernel<<<(k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(codebook_kd, k, d, code_sqnorm);
+  B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_vq_argmin_gather(const b200dm_vq_desc* d, const void* x, const float* codebook_kd,
+                                       const float* code_sqnorm, int64_t* idx, void* q, int32_t* hist, void* stream) {
+  B2_CHECK_ARG(d && x && codebook_kd && code_sqnorm && idx, "vq_argmin_gather: null argument");
+  B2_CHECK_ARG(d->n >= 0 && d->k > 0 && d->d > 0 && d->d % 4 == 0 && d->d <= 4096, "vq_argmin_gather: need d %% 4 == 0, 0 < d <= 4096, k > 0");
+  B2_CHECK_ARG(d->x_dtype == B200DM_F32 || d->x_dtype == B200DM_BF16, "vq_argmin_gather: bad x dtype");
+  B2_CHECK_ARG(d->q_dtype == B200DM_F32 || d->q_dtype == B200DM_BF16, "vq_argmin_gather: bad q dtype");
+  if (d->n == 0) return B200DM_OK;  // empty input: nothing to do (tf.argmin on (0,K) returns (0,))
+  const int64_t blocks = (d->n + BM - 1) / BM;
+  B2_CHECK_ARG(blocks <= 0x7fffffff, "vq_argmin_gather: too many rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d->x_dtype == B200DM_BF16)
+    vq_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(*d, x, codebook_kd, code_sqnorm, idx, q, hist);
+  else
+    vq_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(*d, x, codebook_kd, code_sqnorm, idx, q, hist);
+  B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}

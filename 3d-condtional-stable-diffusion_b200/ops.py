@@ -1,0 +1,270 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/b200dm.h).
+
+Layout: activations are channels-last (N, D, H, W, C) like the reference's; bf16 on the hot path,
+fp32 for x_t / eps_hat / decoded volumes.  All functions enqueue on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import lib, check, ptr, stream, dt
+
+
+def _dev():
+    L.require_gpu()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------ K10 update
+class ScheduleTables:
+    """Device copies of the reference's ``Betas`` tables (networks/dm3d.py:194-214): float64 numpy -> float32."""
+
+    NAMES = ("beta", "sqrt_alpha", "alpha_bar", "alpha_bar_prev", "sqrt_alpha_bar", "sqrt_alpha_bar_prev",
+             "sqrt_one_minus_alpha_bar")
+
+    def __init__(self, timesteps: int, device=None):
+        beta = np.linspace(0.0001, 0.02, timesteps)
+        alpha = 1 - beta
+        alpha_bar = np.cumprod(alpha, 0)
+        alpha_bar_prev = np.append(1.0, alpha_bar[:-1])
+        host = dict(beta=beta, alpha=alpha, sqrt_alpha=np.sqrt(alpha), alpha_bar=alpha_bar,
+                    alpha_bar_prev=alpha_bar_prev, sqrt_alpha_bar=np.sqrt(alpha_bar),
+                    sqrt_alpha_bar_prev=np.sqrt(alpha_bar_prev), sqrt_one_minus_alpha_bar=np.sqrt(1 - alpha_bar))
+        self.timesteps = timesteps
+        self.host = {k: np.asarray(v, dtype=np.float32) for k, v in host.items()}
+        self.dev = None
+        if device is not None:
+            self.to(device)
+
+    def to(self, device):
+        self.dev = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+        return self
+
+    def fill(self, d: L.UpdateDesc):
+        for n in self.NAMES:
+            setattr(d, n, self.dev[n].data_ptr())
+
+
+def make_update_desc(tables: ScheduleTables, n_per_sample, batch, t=0, t_prev=-1, sampler=0, seed=0, sample_id0=0,
+                     eps_dtype=L.F32, t_dev=None) -> L.UpdateDesc:
+    d = L.UpdateDesc()
+    d.n_per_sample, d.batch, d.sampler = n_per_sample, batch, sampler
+    tables.fill(d)
+    d.t_dev = t_dev.data_ptr() if t_dev is not None else None
+    d.t, d.t_prev, d.seed, d.sample_id0, d.eps_dtype = t, t_prev, seed, sample_id0, eps_dtype
+    return d
+
+
+def ddpm_update(tables, x_t, eps, t, noise=None, seed=0, sample_id0=0, sampler=0, t_prev=-1, want_bf16=False):
+    """One reverse step: DiffusionModel.sample + clip + noise add (dm3d.py:477-508, 528-530)."""
+    _dev()
+    assert x_t.dtype == torch.float32 and x_t.is_contiguous() and eps.is_contiguous()
+    B = x_t.shape[0]
+    n = x_t[0].numel()
+    d = make_update_desc(tables, n, B, t, t_prev, sampler, seed, sample_id0, dt(eps))
+    out = torch.empty_like(x_t)
+    out_b = torch.empty(x_t.shape, dtype=torch.bfloat16, device=x_t.device) if want_bf16 else None
+    check(lib().b200dm_ddpm_update(C.byref(d), ptr(x_t), ptr(eps), ptr(noise), ptr(out), ptr(out_b), stream()))
+    return (out, out_b) if want_bf16 else out
+
+
+def philox_normal(shape, seed, sample_id0=0, step=0, stream_id=1, want_bf16=False):
+    dev = _dev()
+    x = torch.empty(shape, dtype=torch.float32, device=dev)
+    xb = torch.empty(shape, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    check(lib().b200dm_philox_normal(ptr(x), ptr(xb), x[0].numel(), shape[0], seed, sample_id0, step, stream_id, stream()))
+    return (x, xb) if want_bf16 else x
+
+
+# ------------------------------------------------------------------ K6/K7 norms
+def bn_fold(gamma, beta, mean, var, eps=1e-3):
+    _dev()
+    scale, shift = torch.empty_like(gamma), torch.empty_like(gamma)
+    check(lib().b200dm_bn_fold(ptr(gamma), ptr(beta), ptr(mean), ptr(var), eps, gamma.numel(), ptr(scale), ptr(shift), stream()))
+    return scale, shift
+
+
+def make_norm_desc(x0, x1=None, kind=0, groups=1, act=None) -> L.NormDesc:
+    d = L.NormDesc()
+    d.voxels = int(np.prod(x0.shape[1:-1]))
+    d.batch, d.c0, d.c1 = x0.shape[0], x0.shape[-1], (x1.shape[-1] if x1 is not None else 0)
+    d.kind, d.groups, d.act, d.x_dtype, d.y_dtype = kind, groups, L.ACT[act], L.BF16, L.BF16
+    return d
+
+
+def gn_stats(x, groups, eps):
+    _dev()
+    d = make_norm_desc(x, None, 1, groups)
+    ws = torch.empty(lib().b200dm_gn_stats_workspace(C.byref(d)) // 4, dtype=torch.float32, device=x.device)
+    mr = torch.empty(x.shape[0], groups, 2, dtype=torch.float32, device=x.device)
+    check(lib().b200dm_gn_stats(C.byref(d), ptr(x), eps, ptr(mr), ptr(ws), ws.numel() * 4, stream()))
+    return mr
+
+
+def norm_act(x0, a, b, act=None, x1=None, kind=0, groups=1, mean_rstd=None, out=None):
+    """y = act(affine(x)) over [x0, x1] concatenated on channels (bf16 in, bf16 out)."""
+    _dev()
+    d = make_norm_desc(x0, x1, kind, groups, act)
+    if out is None:
+        out = torch.empty(*x0.shape[:-1], d.c0 + d.c1, dtype=torch.bfloat16, device=x0.device)
+    check(lib().b200dm_norm_act_fwd(C.byref(d), ptr(x0), ptr(x1), ptr(a), ptr(b), ptr(mean_rstd), ptr(out), stream()))
+    return out
+
+
+def _ptr_array(ts):
+    arr = (C.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def layernorm(x, gammas, betas, eps=1e-3):
+    _dev()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    ys = [torch.empty_like(x) for _ in gammas]
+    check(lib().b200dm_layernorm_fwd(ptr(x), rows, c, eps, len(gammas), _ptr_array(gammas), _ptr_array(betas), _ptr_array(ys), stream()))
+    return ys
+
+
+def cast(x, dtype):
+    _dev()
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(lib().b200dm_cast(ptr(x), dt(x), ptr(y), dt(y), x.numel(), stream()))
+    return y
+
+
+# ------------------------------------------------------------------ K11 VQ
+def vq_prepare(codebook_kd):
+    _dev()
+    sq = torch.empty(codebook_kd.shape[0], dtype=torch.float32, device=codebook_kd.device)
+    check(lib().b200dm_vq_prepare(ptr(codebook_kd), codebook_kd.shape[0], codebook_kd.shape[1], ptr(sq), stream()))
+    return sq
+
+
+def vq_argmin_gather(x, codebook_kd, code_sqnorm=None, want_q=True, q_dtype=torch.float32, hist=None):
+    """x (..., D) fp32|bf16; codebook (K, D) fp32 -> (idx int64 (N,), q (..., D) | None)."""
+    _dev()
+    D = x.shape[-1]
+    n = x.numel() // D
+    if code_sqnorm is None:
+        code_sqnorm = vq_prepare(codebook_kd)
+    d = L.VqDesc()
+    d.n, d.d, d.k, d.x_dtype, d.q_dtype = n, D, codebook_kd.shape[0], dt(x), (L.F32 if q_dtype == torch.float32 else L.BF16)
+    idx = torch.empty(n, dtype=torch.int64, device=x.device)
+    q = torch.empty(x.shape, dtype=q_dtype, device=x.device) if want_q else None
+    check(lib().b200dm_vq_argmin_gather(C.byref(d), ptr(x), ptr(codebook_kd), ptr(code_sqnorm), ptr(idx), ptr(q), ptr(hist), stream()))
+    return idx, q
+
+
+# ------------------------------------------------------------------ K12 dense / softmax
+def dense_f32(x, w, b=None, act_in=None, act_out=None):
+    _dev()
+    m, k = x.shape
+    n = w.shape[1]
+    y = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    check(lib().b200dm_dense_f32(ptr(x), ptr(w), ptr(b), ptr(y), m, k, n, L.ACT[act_in], L.ACT[act_out], stream()))
+    return y
+
+
+def softmax_rows(s, scale=1.0):
+    _dev()
+    cols = s.shape[-1]
+    p = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
+    check(lib().b200dm_softmax_rows(ptr(s), ptr(p), s.numel() // cols, cols, scale, stream()))
+    return p
+
+
+# ------------------------------------------------------------------ K1-K5 conv
+def make_conv_desc(mode, batch, in_dhw, c0, c1, c_out, ksize=3, stride=1, act=None, post_act=None, y_dtype=torch.bfloat16,
+                   chan_bias_rows=0, transposed_store=False, use_halo=False) -> L.ConvDesc:
+    d = L.ConvDesc()
+    d.mode, d.batch = mode, batch
+    d.in_d, d.in_h, d.in_w = in_dhw
+    d.c0, d.c1, d.c_out, d.ksize, d.stride = c0, c1, c_out, ksize, stride
+    d.act, d.y_dtype = L.ACT[act], (L.F32 if y_dtype == torch.float32 else L.BF16)
+    d.chan_bias_rows, d.use_halo = chan_bias_rows, int(use_halo)
+    d.reserved[0], d.reserved[1] = L.ACT[post_act], int(transposed_store)
+    return d
+
+
+def pack_conv_weights(desc: L.ConvDesc, keras_kernel: torch.Tensor, transposed=False) -> torch.Tensor:
+    """Keras kernel fp32 (k,k,k,Cin,Cout) [(k,k,k,Cout,Cin) if transposed] -> packed bf16 bytes (host)."""
+    nbytes = lib().b200dm_conv_packed_weight_bytes(C.byref(desc))
+    if nbytes == 0:
+        raise L.B200dmError("pack_conv_weights: " + lib().b200dm_last_error().decode())
+    w = keras_kernel.detach().to("cpu", torch.float32).contiguous()
+    out = torch.empty(nbytes // 2, dtype=torch.bfloat16)
+    check(lib().b200dm_conv_pack_weights(C.byref(desc), C.c_void_p(w.data_ptr()), int(transposed), C.c_void_p(out.data_ptr())))
+    return out
+
+
+class ConvPlan:
+    """One conv / GEMM invocation with fixed buffers (owns the TMA descriptors)."""
+
+    def __init__(self, desc, x0, w_packed, y, x1=None, bias=None, chan_bias=None, t_dev=None, residual=None, prelu_alpha=None):
+        _dev()
+        self.keep = (x0, x1, w_packed, bias, chan_bias, t_dev, residual, prelu_alpha, y)  # keep buffers alive
+        self.desc = desc
+        h = C.c_void_p()
+        check(lib().b200dm_conv_plan_create(C.byref(desc), ptr(x0), ptr(x1), ptr(w_packed), ptr(bias), ptr(chan_bias),
+                                            ptr(t_dev), ptr(residual), ptr(prelu_alpha), ptr(y), C.byref(h)))
+        self.h = h
+        self.y = y
+        self.owned = True
+
+    @property
+    def flops(self):
+        return lib().b200dm_conv_plan_flops(self.h)
+
+    def run(self):
+        check(lib().b200dm_conv_plan_run(self.h, stream()))
+        return self.y
+
+    def release(self):  # ownership moved into a program
+        self.owned = False
+
+    def __del__(self):
+        if getattr(self, "owned", False) and self.h:
+            lib().b200dm_conv_plan_destroy(self.h)
+            self.h = None
+
+
+def conv_out_shape(mode, in_dhw, stride):
+    if mode == L.CONV_PARITY:
+        return tuple(2 * s for s in in_dhw)
+    return tuple(-(-s // stride) for s in in_dhw)
+
+
+def conv3d(x0, keras_kernel, bias=None, x1=None, mode=L.CONV_DIRECT, stride=1, act=None, post_act=None, residual=None,
+           chan_bias=None, prelu_alpha=None, y_dtype=torch.bfloat16, transposed=False):
+    """Convenience one-shot conv (tests): packs, plans, runs.  x bf16 NDHWC; returns y NDHWC."""
+    dev = _dev()
+    B, D, H, W, c0 = x0.shape
+    c1 = x1.shape[-1] if x1 is not None else 0
+    k = keras_kernel.shape[0]
+    c_out = keras_kernel.shape[3] if transposed else keras_kernel.shape[4]
+    desc = make_conv_desc(mode, B, (D, H, W), c0, c1, c_out, k, stride, act, post_act, y_dtype,
+                          chan_bias_rows=B if chan_bias is not None else 0)
+    wp = pack_conv_weights(desc, keras_kernel, transposed).to(dev)
+    od, oh, ow = conv_out_shape(mode, (D, H, W), stride)
+    y = torch.empty(B, od, oh, ow, c_out, dtype=y_dtype, device=dev)
+    plan = ConvPlan(desc, x0, wp, y, x1=x1, bias=bias, chan_bias=chan_bias, residual=residual, prelu_alpha=prelu_alpha)
+    plan.run()
+    return y
+
+
+def batched_gemm(a, b, y_dtype=torch.float32, residual=None):
+    """y[n] = a[n] (M,K) @ b[n] (N,K)^T, bf16 operands, fp32 accumulate (attention matmuls)."""
+    dev = _dev()
+    B, M, K = a.shape
+    N = b.shape[1]
+    desc = make_conv_desc(L.CONV_BATCHED_GEMM, B, (1, 1, M), K, 0, N, 1, 1, None, None, y_dtype)
+    y = torch.empty(B, M, N, dtype=y_dtype, device=dev)
+    plan = ConvPlan(desc, a, b, y, residual=residual)
+    plan.run()
+    return y

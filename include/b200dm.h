@@ -1,0 +1,236 @@
+/*
+ * b200dm.h -- C ABI of libb200dm.so: the sm_100a kernels behind the reference's sampling path.
+ *
+ * The reference (aayush9400/3D-Condtional-Stable-Diffusion) has no FFI/plugin boundary of its own: the
+ * path sits behind Keras layer calls that TensorFlow lowers to cuDNN/cuBLAS/Eigen ops.  Each entry
+ * point below replaces the TF op call site(s) it cites (file:line in the reference tree) and is what
+ * a binding for this path would bind (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - return 0 on success, negative B200DM_ERR_* otherwise; b200dm_last_error() gives the text
+ *     (thread-local).
+ *   - every data pointer is a DEVICE pointer owned by the caller (16-byte aligned, contiguous,
+ *     channels-last N,D,H,W,C).  The library never allocates or frees caller-visible device memory,
+ *     never synchronises, and enqueues on the caller's cudaStream_t (passed as void*).
+ *   - dtype enums: B200DM_F32 / B200DM_BF16.
+ *   - there is NO CPU fallback: on a machine without a B200-class GPU the compute calls fail.
+ */
+#ifndef B200DM_H
+#define B200DM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DM_VERSION 100
+
+#define B200DM_OK 0
+#define B200DM_ERR_INVALID (-1)
+#define B200DM_ERR_CUDA (-2)
+#define B200DM_ERR_UNSUPPORTED (-3)
+#define B200DM_ERR_KERNEL_TIMEOUT (-4)
+
+#define B200DM_F32 0
+#define B200DM_BF16 1
+
+#define B200DM_ACT_NONE 0
+#define B200DM_ACT_SILU 1
+#define B200DM_ACT_RELU 2
+
+int b200dm_version(void);
+const char* b200dm_last_error(void);
+/* number of SMs / compute capability of the current device (major*10+minor); <0 on error */
+int b200dm_device_info(int* sm_count, int* cc);
+
+/* ---------------------------------------------------------------------------------------------
+ * K10  fused reverse-diffusion update.  Replaces DiffusionModel.sample + the loop body of
+ * DiffusionModel.generate (networks/dm3d.py:477-508, 516-530; conditional_dm3d.py:517-548, 559-573):
+ * seven table gathers, x0, posterior mean, variance, clip(mean,-1,1), mean + sqrt(max(var,1e-20))*noise,
+ * and the tf.random.normal op, as ONE elementwise pass.  Noise is read from `noise` when given,
+ * else generated in-register from Philox4x32-10 (key=seed, counter=(elem/4, t, sample_id0+b, 0)).
+ * sampler 1 = deterministic DDIM (extension).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_per_sample;            /* S^3 * C */
+  int32_t batch;
+  int32_t sampler;                 /* 0 = DDPM ancestral (reference), 1 = DDIM eta=0 (extension) */
+  const float* beta;               /* device fp32[T] tables == reference Betas (dm3d.py:194-214) */
+  const float* sqrt_alpha;
+  const float* alpha_bar;
+  const float* alpha_bar_prev;
+  const float* sqrt_alpha_bar;
+  const float* sqrt_alpha_bar_prev;
+  const float* sqrt_one_minus_alpha_bar;
+  const int32_t* t_dev;            /* device int32[2] = {t, t_prev}; if NULL use t / t_prev below */
+  int32_t t;
+  int32_t t_prev;                  /* DDIM only: next (smaller) timestep, -1 for the last step */
+  uint64_t seed;
+  int64_t sample_id0;              /* global index of sample 0 of this batch (multi-GPU sharding) */
+  int32_t eps_dtype;               /* dtype of eps */
+  int32_t reserved;
+} b200dm_update_desc;
+
+int b200dm_ddpm_update(const b200dm_update_desc* d, const float* x_t, const void* eps,
+                       const float* noise_or_null, float* x_prev, void* x_prev_bf16_or_null,
+                       void* stream);
+/* x ~ N(0,1) from the same Philox stream family (stream id 1): replaces tf.random.normal(shape)
+ * for x_T (dm3d.py:513). */
+int b200dm_philox_normal(float* x, void* x_bf16_or_null, int64_t n_per_sample, int32_t batch,
+                         uint64_t seed, int64_t sample_id0, int32_t step, int32_t stream_id,
+                         void* stream);
+/* t_dev[0] += delta (and t_dev[1] += delta): lets a captured CUDA graph walk the schedule. */
+int b200dm_step_advance(int32_t* t_dev, int32_t delta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6/K7  fused normalisation + activation (+ channel concat, + per-voxel PReLU) in one HBM pass.
+ * Replaces BatchNormalization(inference)+swish (dm3d.py:235-236, 243-244, 371-372), the BN of the
+ * attention blocks (dm3d.py:46; conditional_dm3d.py:188), GroupNormalization+SiLU
+ * (vqgan_attn_cp.py:258,262,269-274,382-383; vqgan_gnorm.py:268-271) and layers.Concatenate
+ * (dm3d.py:359) when two sources are given.
+ *   kind 0: y = act(x * scale[c] + shift[c])             scale/shift fp32[C]   (BN folded by caller
+ *           from gamma,beta,moving_mean,moving_var, eps=1e-3 -- b200dm_bn_fold)
+ *   kind 1: y = act((x - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c])   stats from b200dm_gn_stats
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t voxels;                  /* D*H*W per sample */
+  int32_t batch;
+  int32_t c0, c1;                  /* channels of source 0 and (optional) source 1; C = c0+c1 */
+  int32_t kind;                    /* 0 affine (BN inference), 1 group norm */
+  int32_t groups;                  /* kind 1 */
+  int32_t act;                     /* B200DM_ACT_* */
+  int32_t x_dtype, y_dtype;
+} b200dm_norm_desc;
+
+int b200dm_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                   float eps, int32_t c, float* scale, float* shift, void* stream);
+int b200dm_gn_stats(const b200dm_norm_desc* d, const void* x, float eps, float* mean_rstd /* [B][G][2] */,
+                    float* workspace, size_t ws_bytes, void* stream);
+size_t b200dm_gn_stats_workspace(const b200dm_norm_desc* d);
+int b200dm_norm_act_fwd(const b200dm_norm_desc* d, const void* x0, const void* x1_or_null,
+                        const float* scale_or_gamma, const float* shift_or_beta,
+                        const float* mean_rstd_or_null, void* y, void* stream);
+/* LayerNormalization(axis=-1, eps) with up to 3 (gamma,beta) sets applied to ONE read of x:
+ * CrossAttentionBlock.norm1/2/3 (conditional_dm3d.py:125-127,191-193).  x,y bf16 (rows, C). */
+int b200dm_layernorm_fwd(const void* x, int64_t rows, int32_t c, float eps, int32_t n_out,
+                         const float* const* gammas, const float* const* betas, void* const* ys,
+                         void* stream);
+/* dtype conversion fp32 <-> bf16 (n elements) */
+int b200dm_cast(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K11  VQ nearest-code search + gather.  Replaces VectorQuantizer.get_code_indices + the lookup
+ * in VectorQuantizer.call (networks/vqvae3d_monai.py:165-177,139-144; vqgan_attn_cp.py:189-201,215).
+ * d = ||x||^2 + ||e||^2 - 2 x.e, argmin with lowest index on ties; codebook (K,D) row-major
+ * ("KD" layout; the caller transposes a (D,K) reference codebook once at load).
+ * idx int64[N]; q (N,D) fp32 or bf16 (optional); hist int32[K] += bincount (optional;
+ * == codebooks_used.assign_add, vqvae3d_monai.py:161).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n;                       /* rows */
+  int32_t d;                       /* embedding dim (multiple of 4, <= 1024) */
+  int32_t k;                       /* codes */
+  int32_t x_dtype;                 /* B200DM_F32 or B200DM_BF16 */
+  int32_t q_dtype;
+} b200dm_vq_desc;
+int b200dm_vq_argmin_gather(const b200dm_vq_desc* d, const void* x, const float* codebook_kd,
+                            const float* code_sqnorm /* fp32[K] from b200dm_vq_prepare */,
+                            int64_t* idx, void* q_or_null, int32_t* hist_or_null, void* stream);
+int b200dm_vq_prepare(const float* codebook_kd, int32_t k, int32_t d, float* code_sqnorm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K12  small fp32 dense: Y = act(X W + b), X (M,K), W (K,N) Keras layout.  Replaces the Dense layers on the
+ * time / context embeddings (dm3d.py:229-232, 280-288; conditional_dm3d.py:310-318): step-invariant,
+ * evaluated once per schedule (all T rows) or per generate() call, never per step.
+ * --------------------------------------------------------------------------------------------- */
+int b200dm_dense_f32(const float* x, const float* w, const float* b_or_null, float* y,
+                     int32_t m, int32_t k, int64_t n, int32_t act_in, int32_t act_out, void* stream);
+
+/* row softmax over fp32 scores -> bf16 probabilities (tf.nn.softmax(attn_score,-1), dm3d.py:56;
+ * conditional_dm3d.py:178).  scores (rows, cols) fp32, scale applied before the softmax. */
+int b200dm_softmax_rows(const float* s, void* p_bf16, int64_t rows, int32_t cols, float scale,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1-K5, K8/K9 GEMMs  Conv3D as an implicit GEMM on tcgen05/TMEM with TMA-staged NDHWC bf16 tiles.
+ * Replaces layers.Conv3D k=3 'same' (dm3d.py:237-239,246-248,318-323,373-375), stride-2 DownSample
+ * (dm3d.py:257-263; TF 'same' pad (0,1)), UpSampling3D(2)+Conv3D (dm3d.py:271-274; folded into 8
+ * parity sub-convolutions of 2^3 taps), Conv3D k=1 / Dense-on-voxels (dm3d.py:225-227,47-49,62;
+ * conditional_dm3d.py:129-138), Conv3DTranspose k=4 s=2 'same' (vqvae3d_monai.py:372-377;
+ * vqgan_attn_cp.py:398-403; the same 8-parity form) and, with a per-sample B operand, the two
+ * attention matmuls (tf.einsum dm3d.py:51,61).
+ *
+ *   y[n, o, co] = epilogue( sum_{seg, tap, ci} x_seg[n, in(o,tap), ci] * W[parity(o)][co][seg,tap,ci] )
+ *   epilogue: + bias[co] + chan_bias[t][n][co]; * PReLU/act; + residual[n,o,co]
+ *
+ * A plan owns the TMA descriptors for one fixed set of buffers; create once, run every step.
+ * --------------------------------------------------------------------------------------------- */
+#define B200DM_CONV_DIRECT 0   /* k^3 taps, stride 1 or 2, TF 'same' padding */
+#define B200DM_CONV_PARITY 1   /* out = 2*in: 8 output parities x 2^3 taps (upsample+conv3 / convT k4 s2) */
+#define B200DM_CONV_BATCHED_GEMM 2 /* per-sample B operand: y[n] = x[n] (rows,K) . w[n] (N,K)^T */
+
+typedef struct {
+  int32_t mode;
+  int32_t batch, in_d, in_h, in_w;  /* input spatial size (GEMM mode: in_w = rows per sample, d=h=1) */
+  int32_t c0, c1;                   /* channels of the two K-segments (c1 = 0: one source) */
+  int32_t c_out;
+  int32_t ksize;                    /* DIRECT: 1, 3 or 4 */
+  int32_t stride;                   /* DIRECT: 1 or 2 */
+  int32_t act;                      /* B200DM_ACT_* applied after bias adds, before the residual add */
+  int32_t y_dtype;                  /* B200DM_BF16 or B200DM_F32 */
+  int32_t chan_bias_rows;           /* rows in chan_bias per timestep (= batch) */
+  int32_t use_halo;                 /* 1: stage one halo tile per K-chunk and shift the A descriptor per tap */
+  int32_t reserved[4];
+} b200dm_conv_desc;
+
+typedef struct b200dm_conv_plan b200dm_conv_plan;
+
+/* packed weight size (bytes) for a desc: bf16 [parities][n_pad][chunks*taps*64] */
+size_t b200dm_conv_packed_weight_bytes(const b200dm_conv_desc* d);
+/* host-side packer: Keras kernel fp32 (k,k,k,Cin,Cout) [or (k,k,k,Cout,Cin) when transposed!=0] ->
+ * packed bf16 image (host pointers).  For PARITY mode with ksize 3 the 27 taps are pre-summed into
+ * 8x8 (nearest-upsample fold); with ksize 4 (transposed conv) they are re-indexed. */
+int b200dm_conv_pack_weights(const b200dm_conv_desc* d, const float* keras_kernel_host,
+                             int32_t transposed, void* packed_host);
+int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const void* x1_or_null,
+                            const void* w_packed, const float* bias_or_null,
+                            const float* chan_bias_or_null, const int32_t* t_dev_or_null,
+                            const void* residual_or_null, const void* prelu_alpha_or_null,
+                            void* y, b200dm_conv_plan** out);
+int b200dm_conv_plan_run(b200dm_conv_plan* p, void* stream);
+void b200dm_conv_plan_destroy(b200dm_conv_plan* p);
+double b200dm_conv_plan_flops(const b200dm_conv_plan* p);
+/* device-side watchdog flag: non-zero if any tcgen05/TMA pipeline wait timed out since last reset */
+int b200dm_debug_flag_read_reset(int32_t* flag_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Step program: an ordered list of the above ops with fixed buffers, launched natively in one
+ * call (one ctypes crossing per U-Net forward instead of ~250), CUDA-graph capturable.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct b200dm_program b200dm_program;
+int b200dm_program_create(b200dm_program** out);
+void b200dm_program_destroy(b200dm_program* p);
+int b200dm_program_add_conv(b200dm_program* p, b200dm_conv_plan* plan /* ownership moves */);
+int b200dm_program_add_norm_act(b200dm_program* p, const b200dm_norm_desc* d, const void* x0,
+                                const void* x1_or_null, const float* a, const float* b,
+                                const float* mean_rstd_or_null, void* y);
+int b200dm_program_add_gn_stats(b200dm_program* p, const b200dm_norm_desc* d, const void* x, float eps,
+                                float* mean_rstd, float* workspace, size_t ws_bytes);
+int b200dm_program_add_layernorm(b200dm_program* p, const void* x, int64_t rows, int32_t c, float eps,
+                                 int32_t n_out, const float* const* gammas, const float* const* betas,
+                                 void* const* ys);
+int b200dm_program_add_softmax(b200dm_program* p, const float* s, void* p_bf16, int64_t rows,
+                               int32_t cols, float scale);
+int b200dm_program_add_update(b200dm_program* p, const b200dm_update_desc* d, const float* x_t,
+                              const void* eps, const float* noise_or_null, float* x_prev,
+                              void* x_prev_bf16_or_null);
+int b200dm_program_add_step_advance(b200dm_program* p, int32_t* t_dev, int32_t delta);
+int b200dm_program_run(b200dm_program* p, void* stream);
+int b200dm_program_num_launches(const b200dm_program* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DM_H */

@@ -1,0 +1,176 @@
+"""First-stage quantizer and 3D decoders (oracle; test infrastructure only).
+
+Restates
+  VectorQuantizer.get_code_indices / call   networks/vqvae3d_monai.py:165-177,133-163
+      (variants vqgan.py:204-216, vqgan_gnorm.py:203-215, vqgan_stride.py:204-216,
+       vqgan_attn_cp.py:189-201,203-247); codebook stored (D,K) or (K,D) per variant
+  D1  vqvae3d_monai.Decoder :309-391 + VQVAEResidualUnit :218-234
+  D5  vqgan_attn_cp.Decoder :339-427 + VQVAEResidualUnit :250-276
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import Emu, EXACT
+
+
+# ------------------------------------------------------------------ quantizer
+def code_distances(flat: torch.Tensor, codebook: torch.Tensor, layout: str = "DK"):
+    """||x||^2 + ||e||^2 - 2 x.e  (N,K); codebook (D,K) for layout 'DK', (K,D) for 'KD'."""
+    E = codebook if layout == "DK" else codebook.t()
+    sim = flat @ E
+    return (flat ** 2).sum(1, keepdim=True) + (E ** 2).sum(0) - 2 * sim
+
+
+def get_code_indices(flat, codebook, layout="DK"):
+    """argmin over codes, lowest index on ties (tf.argmin)."""
+    d = code_distances(flat, codebook, layout)
+    # torch.argmin does not promise first-min on ties: make it explicit
+    m = d.min(dim=1, keepdim=True).values
+    K = d.shape[1]
+    idx = torch.where(d == m, torch.arange(K)[None, :], torch.full((1, 1), K)).min(dim=1).values
+    return idx.to(torch.int64)
+
+
+def get_code_indices_exact(flat, codebook, layout="DK"):
+    """Same argmin evaluated in float64 on the float32 inputs (rounding-free ranking) and the
+    float64 margin between best and second-best distance, to classify near-ties."""
+    d = code_distances(flat.double(), codebook.double(), layout)
+    top2 = torch.topk(d, 2, dim=1, largest=False).values
+    m = top2[:, :1]
+    K = d.shape[1]
+    idx = torch.where(d == m, torch.arange(K)[None, :], torch.full((1, 1), K)).min(dim=1).values
+    return idx.to(torch.int64), (top2[:, 1] - top2[:, 0])
+
+
+def quantize(x, codebook, layout="DK"):
+    """VectorQuantizer.call at inference: -> (quantized (same shape), indices, perplexity, counts).
+    Returns the gathered code rows q (the reference's STE form x+(q-x) equals q to 1 ulp)."""
+    D = x.shape[-1]
+    flat = x.reshape(-1, D)
+    idx = get_code_indices(flat, codebook, layout)
+    E = codebook.t() if layout == "DK" else codebook  # (K,D)
+    q = E[idx].reshape(x.shape)
+    K = E.shape[0]
+    counts = torch.bincount(idx, minlength=K)
+    p = counts.double() / flat.shape[0]
+    perplexity = torch.exp(-(p * torch.log(p + 1e-10)).sum()).float()
+    return q, idx, perplexity, counts
+
+
+# ------------------------------------------------------------------ decoder D1 (monai)
+class MonaiDecoder:
+    """vqvae3d_monai.Decoder: Conv3(D->c_top) PReLU; per level R x ResUnit, ConvT(k4,s2) (+ReLU if not last)."""
+
+    def __init__(self, in_channels, out_channels, num_channels, num_res_layers, num_res_channels, in_size):
+        self.cin, self.cout = in_channels, out_channels
+        self.ch = list(reversed(num_channels))
+        self.rch = list(reversed(num_res_channels))
+        self.R, self.s0 = num_res_layers, in_size
+
+    def spec(self):
+        sp, s = [], self.s0
+        c = self.ch[0]
+        sp += [("stem.kernel", (3, 3, 3, self.cin, c), "glorot"), ("stem.bias", (c,), "zeros"),
+               ("stem.prelu.alpha", (s, s, s, c), "zeros")]
+        for i, c in enumerate(self.ch):
+            for j in range(self.R):
+                n = f"level.{i}.res.{j}"
+                rc = self.rch[i]
+                sp += [(f"{n}.conv1.kernel", (3, 3, 3, c, rc), "glorot"), (f"{n}.conv1.bias", (rc,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, rc, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros"),
+                       (f"{n}.norm.gamma", (c,), "ones"), (f"{n}.norm.beta", (c,), "zeros"),
+                       (f"{n}.norm.mean", (c,), "zeros"), (f"{n}.norm.var", (c,), "ones"),
+                       (f"{n}.prelu.alpha", (s, s, s, c), "zeros")]
+            out = self.cout if i == len(self.ch) - 1 else self.ch[i + 1]
+            sp += [(f"level.{i}.up.kernel", (4, 4, 4, out, c), "glorot"), (f"level.{i}.up.bias", (out,), "zeros")]
+            s *= 2
+        return sp
+
+    def forward(self, P, z, emu: Emu = EXACT):
+        x = emu.a(ops.prelu(ops.conv3d(emu.a(z), emu.w(P["stem.kernel"]), P["stem.bias"]), P["stem.prelu.alpha"]))
+        for i in range(len(self.ch)):
+            for j in range(self.R):
+                n = f"level.{i}.res.{j}"
+                h = emu.a(torch.relu(ops.conv3d(x, emu.w(P[f"{n}.conv1.kernel"]), P[f"{n}.conv1.bias"])))
+                h = ops.conv3d(h, emu.w(P[f"{n}.conv2.kernel"]), P[f"{n}.conv2.bias"])
+                h = ops.batchnorm_infer(h, P[f"{n}.norm.gamma"], P[f"{n}.norm.beta"], P[f"{n}.norm.mean"], P[f"{n}.norm.var"])
+                x = emu.a(torch.relu(x + ops.prelu(h, P[f"{n}.prelu.alpha"])))
+            x = ops.conv3d_transpose(x, emu.w(P[f"level.{i}.up.kernel"]), P[f"level.{i}.up.bias"])
+            if i != len(self.ch) - 1:
+                x = emu.a(torch.relu(x))
+        return x
+
+
+# ------------------------------------------------------------------ decoder D5 (vqgan_attn_cp)
+class AttnCpDecoder:
+    """vqgan_attn_cp.Decoder: Conv1(D->c_top) GN(min(D,32)) SiLU; [ConvT(k4,s2,c_i) 2xResUnit]x(L-1); Conv3(->out).
+    ResUnit: GN(min(C,32),eps 1e-6) SiLU Conv3 GN SiLU Conv3 + x."""
+
+    def __init__(self, in_channels, out_channels, num_channels):
+        self.cin, self.cout = in_channels, out_channels
+        self.ch = list(reversed(num_channels))
+
+    def spec(self):
+        c0 = self.ch[0]
+        sp = [("stem.kernel", (1, 1, 1, self.cin, c0), "glorot"), ("stem.bias", (c0,), "zeros"),
+              ("stem.norm.gamma", (c0,), "ones"), ("stem.norm.beta", (c0,), "zeros")]
+        for i in range(1, len(self.ch)):
+            c = self.ch[i]
+            sp += [(f"level.{i}.up.kernel", (4, 4, 4, c, self.ch[i - 1]), "glorot"), (f"level.{i}.up.bias", (c,), "zeros")]
+            for j in range(2):
+                n = f"level.{i}.res.{j}"
+                sp += [(f"{n}.norm1.gamma", (c,), "ones"), (f"{n}.norm1.beta", (c,), "zeros"),
+                       (f"{n}.conv1.kernel", (3, 3, 3, c, c), "glorot"), (f"{n}.conv1.bias", (c,), "zeros"),
+                       (f"{n}.norm2.gamma", (c,), "ones"), (f"{n}.norm2.beta", (c,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, c, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros")]
+        sp += [("head.kernel", (3, 3, 3, self.ch[-1], self.cout), "glorot"), ("head.bias", (self.cout,), "zeros")]
+        return sp
+
+    def stem_groups(self):
+        # GroupNormalization(groups=min(self.in_channels, 32)) applied to the c_top-channel tensor
+        return min(self.cin, 32)
+
+    def forward(self, P, z, emu: Emu = EXACT):
+        x = emu.a(ops.conv3d(emu.a(z), emu.w(P["stem.kernel"]), P["stem.bias"]))
+        x = emu.a(ops.swish(ops.groupnorm(x, P["stem.norm.gamma"], P["stem.norm.beta"], self.stem_groups(), 1e-6)))
+        for i in range(1, len(self.ch)):
+            c = self.ch[i]
+            g = min(c, 32)
+            x = emu.a(ops.conv3d_transpose(x, emu.w(P[f"level.{i}.up.kernel"]), P[f"level.{i}.up.bias"]))
+            for j in range(2):
+                n = f"level.{i}.res.{j}"
+                h = emu.a(ops.swish(ops.groupnorm(x, P[f"{n}.norm1.gamma"], P[f"{n}.norm1.beta"], g, 1e-6)))
+                h = emu.a(ops.conv3d(h, emu.w(P[f"{n}.conv1.kernel"]), P[f"{n}.conv1.bias"]))
+                h = emu.a(ops.swish(ops.groupnorm(h, P[f"{n}.norm2.gamma"], P[f"{n}.norm2.beta"], g, 1e-6)))
+                x = emu.a(ops.conv3d(h, emu.w(P[f"{n}.conv2.kernel"]), P[f"{n}.conv2.bias"]) + x)
+        return ops.conv3d(x, emu.w(P["head.kernel"]), P["head.bias"])
+
+
+# ------------------------------------------------------------------ parameter counting (known-answer pin)
+def monai_vqvae_param_count(in_channels, out_channels, num_channels, num_res_layers, num_res_channels,
+                            num_embeddings, embedding_dim, img_size=128):
+    """(trainable, bn_moving_stats) of vqvae3d_monai.VQVAE (encoder :237-306, decoder :309-391, quantizer
+    :112-131) with down/upsample parameters (2,4,1,'same'); per-voxel PReLU alphas; biases everywhere."""
+    tr, nt = 0, 0
+    s, c_prev = img_size, in_channels
+    for i, c in enumerate(num_channels):  # encoder
+        tr += 4 ** 3 * c_prev * c + c
+        s //= 2
+        for _ in range(num_res_layers):
+            rc = num_res_channels[i]
+            tr += 27 * c * rc + rc + 27 * rc * c + c + 2 * c + s ** 3 * c
+            nt += 2 * c
+        c_prev = c
+    tr += 27 * c_prev * embedding_dim + embedding_dim + s ** 3 * embedding_dim
+    dec = MonaiDecoder(embedding_dim, out_channels, num_channels, num_res_layers, num_res_channels, s)
+    for name, shp, _ in dec.spec():
+        n = int(np.prod(shp))
+        if name.endswith(".mean") or name.endswith(".var"):
+            nt += n
+        else:
+            tr += n
+    tr += embedding_dim * num_embeddings
+    return tr, nt

@@ -1,0 +1,184 @@
+"""GPU parity: tcgen05 implicit-GEMM conv (all variants) vs the oracle's Keras-semantics conv.
+
+Inputs and weights are bf16-representable, accumulation is fp32 on both sides, so the only
+difference is summation order: tolerance 2e-3 * max|y| absolute on fp32 outputs (stated), and one
+bf16 ulp (2^-8 relative) on bf16 outputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _r(t):  # bf16-representable fp32
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return _r(torch.randn(shape, generator=g) * scale)
+
+
+def _close(y, ref, tol=2e-3, what=""):
+    y = y.float().cpu()
+    err = (y - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-12
+    assert err <= tol * den, f"{what}: max abs err {err:.4e} vs max|ref| {den:.4e} (rel {err/den:.3e})"
+
+
+def _check_flag():
+    from b200dm import _lib
+    torch.cuda.synchronize()
+    assert _lib.debug_flag() == 0, "tcgen05/TMA pipeline watchdog fired"
+
+
+CASES = [
+    # B, S, cin, cout
+    (2, 8, 64, 64),
+    (1, 16, 8, 64),
+    (2, 4, 128, 256),
+    (1, 16, 32, 32),
+    (1, 8, 192, 64),
+    (3, 8, 64, 16),
+    (1, 32, 64, 64),
+]
+
+
+@pytest.mark.parametrize("B,S,cin,cout", CASES)
+def test_conv3_same(cuda, B, S, cin, cout):
+    from b200dm import ops
+    x = _rand((B, S, S, S, cin), 1)
+    w = _rand((3, 3, 3, cin, cout), 2, 1.0 / np.sqrt(27 * cin))
+    b = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+    ref = O.conv3d(x, w, b)
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, bias=b.to(cuda), y_dtype=torch.float32)
+    _check_flag()
+    _close(y, ref, what=f"conv3 B{B} S{S} {cin}->{cout}")
+
+
+def test_conv3_bf16_out_and_epilogue(cuda):
+    from b200dm import ops
+    B, S, cin, cout = 2, 8, 64, 128
+    x = _rand((B, S, S, S, cin), 1)
+    w = _rand((3, 3, 3, cin, cout), 2, 1.0 / np.sqrt(27 * cin))
+    b = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+    cbias = torch.randn(B, cout, generator=torch.Generator().manual_seed(4))
+    res = _rand((B, S, S, S, cout), 5)
+    ref = O.swish(O.conv3d(x, w, b) + cbias[:, None, None, None, :]) + res
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, bias=b.to(cuda), chan_bias=cbias.to(cuda), act="silu",
+                   residual=res.to(cuda, torch.bfloat16))
+    _check_flag()
+    assert y.dtype == torch.bfloat16
+    _close(y, ref, tol=6e-3, what="conv3 + bias + temb + silu + residual (bf16 out)")
+
+
+def test_conv3_two_segments(cuda):
+    from b200dm import ops
+    B, S, c0, c1, cout = 2, 8, 64, 32, 64
+    x0, x1 = _rand((B, S, S, S, c0), 1), _rand((B, S, S, S, c1), 6)
+    w = _rand((3, 3, 3, c0 + c1, cout), 2, 1.0 / np.sqrt(27 * (c0 + c1)))
+    ref = O.conv3d(torch.cat([x0, x1], -1), w)
+    y = ops.conv3d(x0.to(cuda, torch.bfloat16), w, x1=x1.to(cuda, torch.bfloat16), y_dtype=torch.float32)
+    _check_flag()
+    _close(y, ref, what="conv3 over [x, skip] K-segments")
+
+
+def test_conv1(cuda):
+    from b200dm import ops
+    B, S, cin, cout = 2, 8, 96, 64
+    x = _rand((B, S, S, S, cin), 1)
+    w = _rand((1, 1, 1, cin, cout), 2, 1.0 / np.sqrt(cin))
+    ref = torch.relu(O.conv3d(x, w))
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, act="relu", y_dtype=torch.float32)
+    _check_flag()
+    _close(y, ref, what="conv1 + relu")
+
+
+def test_conv_head_cout1(cuda):
+    from b200dm import ops
+    B, S, cin = 1, 16, 32
+    x = _rand((B, S, S, S, cin), 1)
+    w = _rand((3, 3, 3, cin, 1), 2, 1.0 / np.sqrt(27 * cin))
+    b = torch.tensor([0.25])
+    ref = O.conv3d(x, w, b)
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, bias=b.to(cuda), y_dtype=torch.float32)
+    _check_flag()
+    _close(y, ref, what="conv3 32->1 head")
+
+
+@pytest.mark.parametrize("S,c", [(8, 64), (16, 128)])
+def test_conv3_stride2_tf_same(cuda, S, c):
+    """TF 'same' for even input, k=3, s=2 pads (0,1): NOT torch padding=1."""
+    from b200dm import ops
+    x = _rand((2, S, S, S, c), 1)
+    w = _rand((3, 3, 3, c, c), 2, 1.0 / np.sqrt(27 * c))
+    ref = O.conv3d(x, w, stride=2)
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, stride=2, y_dtype=torch.float32)
+    _check_flag()
+    assert tuple(y.shape) == tuple(ref.shape)
+    _close(y, ref, what="conv3 stride 2")
+
+
+@pytest.mark.parametrize("S,c", [(4, 64), (8, 128)])
+def test_upsample_conv_parity_fold(cuda, S, c):
+    from b200dm import ops, _lib
+    x = _rand((2, S, S, S, c), 1)
+    w = _rand((3, 3, 3, c, c), 2, 1.0 / np.sqrt(27 * c))
+    b = torch.randn(c, generator=torch.Generator().manual_seed(3))
+    ref = O.conv3d(O.upsample_nearest2(x), w, b)
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, bias=b.to(cuda), mode=_lib.CONV_PARITY, y_dtype=torch.float32)
+    _check_flag()
+    # folded taps are summed in fp32 then rounded to bf16 once: error bound is one bf16 ulp of a weight
+    _close(y, ref, tol=8e-3, what="UpSampling3D(2)+Conv3 as 8 parity sub-convs")
+
+
+@pytest.mark.parametrize("S,cin,cout", [(4, 128, 64), (8, 64, 32)])
+def test_conv_transpose_k4s2(cuda, S, cin, cout):
+    from b200dm import ops, _lib
+    x = _rand((2, S, S, S, cin), 1)
+    w = _rand((4, 4, 4, cout, cin), 2, 1.0 / np.sqrt(8 * cin))
+    b = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+    ref = O.conv3d_transpose(x, w, b)
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, bias=b.to(cuda), mode=_lib.CONV_PARITY, transposed=True, y_dtype=torch.float32)
+    _check_flag()
+    _close(y, ref, what="Conv3DTranspose k4 s2")
+
+
+def test_prelu_postact_epilogue(cuda):
+    """monai ResUnit tail: relu(x + PReLU(conv(h)))  (vqvae3d_monai.py:233-234), BN folded by the host."""
+    from b200dm import ops
+    B, S, c = 2, 8, 64
+    h, x = _rand((B, S, S, S, c), 1), _rand((B, S, S, S, c), 7)
+    w = _rand((3, 3, 3, c, c), 2, 1.0 / np.sqrt(27 * c))
+    alpha = _r(torch.rand(S, S, S, c, generator=torch.Generator().manual_seed(8)) * 0.3)
+    ref = torch.relu(x + O.prelu(O.conv3d(h, w), alpha))
+    y = ops.conv3d(h.to(cuda, torch.bfloat16), w, prelu_alpha=alpha.to(cuda, torch.bfloat16),
+                   residual=x.to(cuda, torch.bfloat16), post_act="relu", y_dtype=torch.float32)
+    _check_flag()
+    _close(y, ref, what="PReLU + residual + ReLU epilogue")
+
+
+def test_batched_gemm_and_transposed_store(cuda):
+    from b200dm import ops, _lib
+    B, L, Cc = 2, 512, 256
+    q, k = _rand((B, L, Cc), 1), _rand((B, L, Cc), 2)
+    s = ops.batched_gemm(q.to(cuda, torch.bfloat16), k.to(cuda, torch.bfloat16))
+    _check_flag()
+    _close(s, torch.einsum("blc,bLc->blL", q, k), what="Q K^T")
+    # V^T via a transposed-store 1^3 conv
+    x = _rand((B, 8, 8, 8, Cc), 3)
+    w = _rand((1, 1, 1, Cc, Cc), 4, 1.0 / 16)
+    desc = ops.make_conv_desc(_lib.CONV_DIRECT, B, (8, 8, 8), Cc, 0, Cc, 1, 1, y_dtype=torch.bfloat16, transposed_store=True)
+    wp = ops.pack_conv_weights(desc, w).to(cuda)
+    vt = torch.empty(B, Cc, L, dtype=torch.bfloat16, device=cuda)
+    ops.ConvPlan(desc, x.to(cuda, torch.bfloat16), wp, vt).run()
+    _check_flag()
+    ref = O.conv3d(x, w).reshape(B, L, Cc).transpose(1, 2)
+    _close(vt, ref, tol=6e-3, what="transposed store")
+    p = _r(torch.softmax(torch.randn(B, L, L, generator=torch.Generator().manual_seed(5)), -1))
+    o = ops.batched_gemm(p.to(cuda, torch.bfloat16), vt)
+    _check_flag()
+    _close(o, torch.einsum("blL,bcL->blc", p, vt.float().cpu()), what="P V")
