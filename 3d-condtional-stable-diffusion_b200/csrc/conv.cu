@@ -169,7 +169,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const float* cb = nullptr;
     if (p.chan_bias && valid) {
       const int tt = p.t_dev ? p.t_dev[0] : 0;
-      cb = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + n) * p.c_out;
+      cb = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? n : 0)) * p.c_out;
     }
     const bool ok = ptx::mbar_wait(tmem_full_bar, 0, p.dbg, 3);
     ptx::tc_fence_after();

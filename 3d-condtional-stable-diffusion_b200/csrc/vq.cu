@@ -169,11 +169,12 @@ extern "C" int b200dm_vq_prepare(const float* codebook_kd, int32_t k, int32_t d,
 
 extern "C" int b200dm_vq_argmin_gather(const b200dm_vq_desc* d, const void* x, const float* codebook_kd,
                                        const float* code_sqnorm, int64_t* idx, void* q, int32_t* hist, void* stream) {
-  B2_CHECK_ARG(d && x && codebook_kd && code_sqnorm && idx, "vq_argmin_gather: null argument");
-  B2_CHECK_ARG(d->n >= 0 && d->k > 0 && d->d > 0 && d->d % 4 == 0 && d->d <= 4096, "vq_argmin_gather: need d %% 4 == 0, 0 < d <= 4096, k > 0");
+  B2_CHECK_ARG(d, "vq_argmin_gather: null desc");
+  if (d->n == 0) return B200DM_OK;  // empty input: nothing to do (tf.argmin on (0,K) returns (0,))
+  B2_CHECK_ARG(x && codebook_kd && code_sqnorm && idx, "vq_argmin_gather: null argument");
+  B2_CHECK_ARG(d->n > 0 && d->k > 0 && d->d > 0 && d->d % 4 == 0 && d->d <= 4096, "vq_argmin_gather: need d %% 4 == 0, 0 < d <= 4096, k > 0");
   B2_CHECK_ARG(d->x_dtype == B200DM_F32 || d->x_dtype == B200DM_BF16, "vq_argmin_gather: bad x dtype");
   B2_CHECK_ARG(d->q_dtype == B200DM_F32 || d->q_dtype == B200DM_BF16, "vq_argmin_gather: bad q dtype");
-  if (d->n == 0) return B200DM_OK;  // empty input: nothing to do (tf.argmin on (0,K) returns (0,))
   const int64_t blocks = (d->n + BM - 1) / BM;
   B2_CHECK_ARG(blocks <= 0x7fffffff, "vq_argmin_gather: too many rows");
   cudaStream_t s = (cudaStream_t)stream;

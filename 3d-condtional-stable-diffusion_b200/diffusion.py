@@ -1,0 +1,213 @@
+"""Latent diffusion wrapper: the host-side mirror of the reference's ``DiffusionModel``.
+
+    unconditional  networks/dm3d.py:379-545          (generate :510-532, sample :477-508, test :534-545)
+    conditional    networks/conditional_dm3d.py:418-594 (generate :550-575, test :577-593)
+
+Same constructor ``DiffusionModel(latent_size, num_embed, latent_channels, vqvae_load_ckpt, args)`` (``args`` carries
+timesteps / num_gpus / kernel_resize / bs), same attributes (.timesteps .b .network .encoder .quantizer .decoder
+.vqvae_trainer) and the same ``sample(x_t, pred_noise, t, shape) -> (mean, var)`` and
+``generate(shape, last_step[, context_value]) -> latents`` contracts.  Build additions (explicit extensions,
+SURVEY 8b): ``x_T=``, ``noise=`` (inject), ``seed=``, ``sample_id0=`` (multi-GPU sharding), ``sampler="ddim"``,
+``steps=``, per-sample ``context=`` ids, and ``decode(latents, quantize=False)``.
+
+The reverse loop is one captured CUDA graph per step: U-Net program + fused posterior update + a device-side
+timestep decrement, replayed T times with zero host work in between.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .first_stage import VQVAE
+from .program import Program
+from .unet import build_model
+
+
+class Betas(ops.ScheduleTables):
+    """reference ``Betas`` (dm3d.py:194-214): attribute access to the fp32 tables."""
+
+    def __getattr__(self, k):
+        host = self.__dict__.get("host", {})
+        if k in host:
+            return host[k]
+        raise AttributeError(k)
+
+
+class DiffusionModel:
+    conditional = False
+    first_conv_channels = 64
+
+    def __init__(self, latent_size, num_embed, latent_channels, vqvae_load_ckpt, args, first_stage=None):
+        self.timesteps = args.timesteps
+        self.b = Betas(args.timesteps)
+        self.lc = latent_channels
+        self.latent_size = latent_size
+        self.num_gpus, self.global_bs = getattr(args, "num_gpus", 1), getattr(args, "bs", 1)
+        # The unconditional file hard-codes K=1024, D=256 (dm3d.py:405-406); the conditional one uses the arguments
+        # (conditional_dm3d.py:444-445).  ``first_stage`` lets a caller plug any object with .encoder/.quantizer/.decoder.
+        if first_stage is None:
+            K, D = (num_embed, latent_channels) if self.conditional else (1024, 256)
+            first_stage = VQVAE(in_channels=1, out_channels=1, num_channels=(32, 64, 128, 256),
+                                num_res_channels=(32, 64, 128, 256), num_res_layers=5,
+                                downsample_parameters=((2, 4, 1, "same"),) * 4, upsample_parameters=((2, 4, 1, "same", 0),) * 4,
+                                num_embeddings=K, embedding_dim=D, dropout=None,
+                                num_gpus=self.num_gpus, kernel_resize=getattr(args, "kernel_resize", False),
+                                latent_size=latent_size)
+        self.vqvae_trainer = first_stage
+        self.vqvae_load_ckpt = vqvae_load_ckpt
+        if vqvae_load_ckpt is not None:
+            print("Loading VQVAE weights")
+            self.vqvae_trainer.load_weights(vqvae_load_ckpt)
+        self.encoder, self.quantizer, self.decoder = first_stage.encoder, first_stage.quantizer, first_stage.decoder
+        self.network = build_model(latent_size, latent_channels, widths=[64, 128, 256],
+                                   has_attention=[False, False, True, True],
+                                   context_dim=1 if self.conditional else None,
+                                   first_conv_channels=self.first_conv_channels, conditional=self.conditional)
+        self._step = None
+
+    # ------------------------------------------------------------------ reference API
+    def load_weights(self, path):
+        self.network.load_weights(path)
+        self._step = None
+
+    def sample(self, x_t, pred_noise, curr_time_step, shape=None):
+        """-> (posterior_mean, variance); the reference returns the variance under the name log-variance
+        (dm3d.py:506-508).  Standalone diagnostic form with the reference's fp32 op order; inside generate() the same
+        arithmetic runs fused with the clip and the noise add in the update kernel (csrc/update.cu)."""
+        t = int(torch.as_tensor(curr_time_step).reshape(-1)[0])
+        h = self.b.host
+        f = lambda n: torch.tensor(h[n][t], dtype=torch.float32, device=x_t.device)  # noqa: E731
+        x_0 = (x_t - f("sqrt_one_minus_alpha_bar") * pred_noise) / f("sqrt_alpha_bar")
+        mean = (f("beta") * f("sqrt_alpha_bar_prev") / (1 - f("alpha_bar"))) * x_0 + \
+               ((1 - f("alpha_bar_prev")) * f("sqrt_alpha") / (1 - f("alpha_bar"))) * x_t
+        var = (1 - f("alpha_bar_prev")) * f("beta") / (1 - f("alpha_bar"))
+        return mean, var.reshape(1, 1, 1, 1, 1).expand(x_t.shape[0], 1, 1, 1, 1)
+
+    # ------------------------------------------------------------------ compiled step
+    def _compile(self, batch, sampler, inject_noise, seed, sample_id0):
+        key = (batch, sampler, inject_noise)
+        if self._step is not None and self._step["key"] == key:
+            st = self._step
+            if (st["desc"].seed, st["desc"].sample_id0) != (seed, sample_id0):
+                st["desc"].seed, st["desc"].sample_id0 = seed, sample_id0
+                st["graph"] = None  # kernel arguments are baked into a captured graph
+            return st
+        L.require_gpu()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.b.to(dev)
+        t_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+        net = self.network.compile(batch, self.timesteps, dev, t_dev=t_dev)
+        S, Cl = self.latent_size, self.lc
+        x = torch.zeros(batch, S, S, S, Cl, dtype=torch.float32, device=dev)
+        noise = torch.zeros_like(x) if inject_noise else None
+        desc = ops.make_update_desc(self.b, x[0].numel(), batch, 0, -1, 1 if sampler == "ddim" else 0, seed, sample_id0,
+                                    L.F32, t_dev=t_dev)
+        self._step = dict(key=key, net=net, x=x, noise=noise, desc=desc, t_dev=t_dev, graph=None, dev=dev, delta=-1)
+        return self._step
+
+    def _run_step_eager(self, st):
+        """U-Net forward -> fused update (x in place, bf16 copy into the U-Net input) -> t -= delta."""
+        st["net"].prog.run()
+        d = st["desc"]
+        L.check(L.lib().b200dm_ddpm_update(ctypes.byref(d), L.ptr(st["x"]), L.ptr(st["net"].eps), L.ptr(st["noise"]),
+                                           L.ptr(st["x"]), L.ptr(st["net"].x_in), L.stream()))
+        L.check(L.lib().b200dm_step_advance(L.ptr(st["t_dev"]), st["delta"], L.stream()))
+
+    def _capture(self, st):
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._run_step_eager(st)  # warm-up (sets kernel attributes outside capture)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            self._run_step_eager(st)
+        st["graph"] = g
+        return g
+
+    def generate(self, shape=(1, 16, 16, 16, 16), last_step=0, context_value=None, *, x_T=None, noise=None, seed=1234,
+                 sample_id0=0, sampler="ddpm", steps=None, context=None, use_graph=True, on_step=None):
+        """Reverse diffusion from t=T-1 down to ``last_step`` (dm3d.py:510-532).  ``noise``: callable i -> tensor or
+        dict/sequence indexed by timestep, injected instead of the Philox stream (parity tests).  Returns fp32 latents."""
+        shape = tuple(shape)
+        B = shape[0]
+        assert shape[1] == self.latent_size and shape[-1] == self.lc, "shape must match the compiled latent geometry"
+        st = self._compile(B, sampler, noise is not None, seed, sample_id0)
+        dev, net = st["dev"], st["net"]
+        if self.conditional:
+            ctx = context if context is not None else (0 if context_value is None else context_value)
+            net.set_context(torch.as_tensor(ctx).reshape(-1))
+        if x_T is None:  # samples = tf.random.normal(shape) (dm3d.py:513): Philox stream 1
+            x0, xb = ops.philox_normal(shape, seed, sample_id0, 0, 1, want_bf16=True)
+        else:
+            x0 = x_T.to(dev, torch.float32).contiguous()
+            xb = ops.cast(x0, torch.bfloat16)
+        st["x"].copy_(x0)
+        net.x_in.copy_(xb)
+        T = self.timesteps
+        if sampler == "ddim":
+            n = steps or T
+            seq = sorted({int(round(v)) for v in np.linspace(last_step, T - 1, n)}, reverse=True)
+        else:
+            seq = list(range(T - 1, last_step - 1, -1))
+        uniform = all(seq[i] - seq[i + 1] == seq[0] - seq[1] for i in range(len(seq) - 1)) if len(seq) > 1 else True
+        delta = (seq[1] - seq[0]) if len(seq) > 1 else -1
+        graph_ok = use_graph and noise is None and on_step is None and uniform and sampler == "ddpm"
+        if graph_ok:
+            if st["graph"] is None or st["delta"] != delta:
+                st["delta"] = delta
+                st["t_dev"].copy_(torch.tensor([seq[0], seq[0] + delta], dtype=torch.int32))
+                # capture runs one warm-up step + records one: restore state afterwards
+                self._capture(st)
+                st["x"].copy_(x0)
+                net.x_in.copy_(xb)
+            st["t_dev"].copy_(torch.tensor([seq[0], seq[0] + delta], dtype=torch.int32))
+            for _ in seq:
+                st["graph"].replay()
+        else:
+            for j, i in enumerate(seq):
+                nxt = seq[j + 1] if j + 1 < len(seq) else -1
+                st["t_dev"].copy_(torch.tensor([i, nxt], dtype=torch.int32))
+                if noise is not None and i > 0:
+                    z = noise(i) if callable(noise) else noise[i]
+                    st["noise"].copy_(z.to(dev, torch.float32))
+                st["delta"] = 0
+                self._run_step_eager(st)
+                if on_step is not None:
+                    on_step(i, st["x"], net.eps)
+            st["delta"] = -1 if st["graph"] is None else st["delta"]
+        return st["x"].clone()
+
+    def decode(self, latents, quantize=False):
+        """latents -> volumes through the first-stage decoder; ``quantize=True`` snaps latents to the codebook first
+        (extension: the reference's test() decodes un-quantized latents, dm3d.py:541)."""
+        if quantize:
+            latents, _, _ = self.quantizer.quantize(latents)
+        return self.decoder(latents)
+
+    def test(self, test_prefix, context=None, shape=None, out_dir="./generated_images_dm3d"):
+        """reference test(): generate (10,16,16,16,64) latents, decode, save .npy (dm3d.py:534-545).  The literal shape
+        is a default; pass ``shape`` to override (the reference's literals are mutually inconsistent)."""
+        i = self.timesteps
+        print(f"Generating for {i} rsteps")
+        if self.vqvae_load_ckpt is not None:
+            self.vqvae_trainer.load_weights(self.vqvae_load_ckpt)
+        shape = shape or (10, self.latent_size, self.latent_size, self.latent_size, self.lc)
+        kw = dict(context_value=context) if self.conditional and context is not None else {}
+        lat = self.generate(shape, last_step=self.timesteps - i, **kw)
+        images = self.decoder(lat)
+        os.makedirs(out_dir, exist_ok=True)
+        np.save(os.path.join(out_dir, f"{test_prefix}-{i}rsteps.npy"), images.cpu().numpy())
+        return images
+
+
+class ConditionalDiffusionModel(DiffusionModel):
+    """networks/conditional_dm3d.DiffusionModel: first_conv_channels=32, class-id context -> cross-attention."""
+    conditional = True
+    first_conv_channels = 32

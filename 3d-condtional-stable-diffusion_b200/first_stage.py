@@ -1,0 +1,267 @@
+"""First stage on the sm_100a kernels: VQ codebook quantizer + 3D decoders (latents -> MRI volumes).
+
+Mirrors the attribute surface the reference's DiffusionModel uses (``.encoder / .quantizer / .decoder``):
+    VectorQuantizer            networks/vqvae3d_monai.py:112-177 (codebook (D,K)); vqgan_attn_cp.py:140-247 ((K,D))
+    MonaiDecoder  (family D1)  networks/vqvae3d_monai.py:309-391 + VQVAEResidualUnit :218-234
+    AttnCpDecoder (family D5)  networks/vqgan_attn_cp.py:339-427 + VQVAEResidualUnit :250-276
+    VQVAE / VQGAN              networks/vqvae3d_monai.py:394-457 / vqgan_attn_cp.py:569-590 (constructor surface)
+The encoder is not on the sampling path and is not built: ``.encoder`` raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .program import Program
+from . import weights as Wt
+
+
+# ================================================================== quantizer
+class VectorQuantizer:
+    """``layout`` 'DK': embeddings stored (embedding_dim, num_embeddings) like vqvae3d_monai/vqgan;
+    'KD': (num_embeddings, embedding_dim) like vqgan_gnorm/stride/attn_cp."""
+
+    def __init__(self, num_embeddings, embedding_dim, beta=0.25, layout="DK", seed=3):
+        self.num_embeddings, self.embedding_dim, self.beta, self.layout = num_embeddings, embedding_dim, beta, layout
+        rng = np.random.default_rng(seed)
+        if layout == "DK":   # HeUniform on (D,K): limit sqrt(6/fan_in), fan_in = D (vqvae3d_monai.py:123-127)
+            lim = np.sqrt(6.0 / embedding_dim)
+            e = rng.uniform(-lim, lim, size=(embedding_dim, num_embeddings))
+        else:                # tf.random_uniform_initializer() = U(-0.05, 0.05) (vqgan_attn_cp.py:154-158)
+            e = rng.uniform(-0.05, 0.05, size=(num_embeddings, embedding_dim))
+        self.embeddings = torch.from_numpy(e.astype(np.float32))
+        self.codebooks_used = torch.zeros(num_embeddings, dtype=torch.int32)
+        self._dev = None
+
+    def set_embeddings(self, e):
+        e = torch.as_tensor(e).float().cpu()
+        want = (self.embedding_dim, self.num_embeddings) if self.layout == "DK" else (self.num_embeddings, self.embedding_dim)
+        if tuple(e.shape) != want:
+            raise ValueError(f"codebook: expected {want} ({self.layout} layout), got {tuple(e.shape)}")
+        self.embeddings, self._dev = e, None
+
+    def _device_state(self):
+        if self._dev is None:
+            L.require_gpu()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            kd = (self.embeddings.t() if self.layout == "DK" else self.embeddings).contiguous().to(dev)
+            self._dev = dict(kd=kd, sq=ops.vq_prepare(kd), hist=torch.zeros(self.num_embeddings, dtype=torch.int32, device=dev))
+        return self._dev
+
+    def get_code_indices(self, flattened_inputs, distribution=False):
+        """(N, D) -> (N,) int64; lowest index on ties.  ``distribution=True`` (the (N,K) distance matrix) is a
+        training-time diagnostic of the reference and is not part of this path."""
+        if distribution:
+            raise NotImplementedError("distribution=True is not on the sampling/decode path")
+        st = self._device_state()
+        idx, _ = ops.vq_argmin_gather(flattened_inputs.contiguous(), st["kd"], st["sq"], want_q=False)
+        return idx
+
+    def quantize(self, x, q_dtype=torch.float32):
+        """-> (quantized like x, indices (N,), perplexity).  Returns the gathered code rows q; the reference's
+        straight-through form x + (q - x) equals q up to 1 ulp."""
+        st = self._device_state()
+        st["hist"].zero_()
+        idx, q = ops.vq_argmin_gather(x.contiguous(), st["kd"], st["sq"], want_q=True, q_dtype=q_dtype, hist=st["hist"])
+        counts = st["hist"].cpu()
+        self.codebooks_used += counts                       # codebooks_used.assign_add (vqvae3d_monai.py:161)
+        p = counts.double() / max(1, idx.numel())
+        perplexity = float(torch.exp(-(p * torch.log(p + 1e-10)).sum()))
+        return q, idx, perplexity
+
+    def __call__(self, x):
+        q, _, perplexity = self.quantize(x)
+        return q, perplexity
+
+
+# ================================================================== decoders
+class _DecoderBase:
+    spec: list
+    out_channels: int
+
+    def __init__(self):
+        self.params = Wt.init_params(self.spec, seed=1, mode="keras")
+        self.prog = None
+
+    def set_weights(self, params):
+        Wt.check_against_spec(params, self.spec)
+        self.params = {k: torch.as_tensor(v).float().cpu() for k, v in params.items()}
+        self.prog = None
+
+    def count_params(self):
+        return sum(int(np.prod(s)) for _, s, _ in self.spec)
+
+    def _conv(self, pr, x0, kernel, bias, cout, k=3, mode=L.CONV_DIRECT, act=None, post_act=None, residual=None,
+              prelu_alpha=None, y_dtype=torch.bfloat16, transposed=False, note=""):
+        B, D, H, W, c0 = x0.shape
+        desc = ops.make_conv_desc(mode, B, (D, H, W), c0, 0, cout, k, 1, act, post_act, y_dtype)
+        wp = ops.pack_conv_weights(desc, kernel, transposed).to(self.device)
+        od, oh, ow = ops.conv_out_shape(mode, (D, H, W), 1)
+        y = pr.buf((B, od, oh, ow, cout), y_dtype)
+        return pr.conv(desc, x0, wp, y, bias=bias.to(self.device).contiguous(), residual=residual,
+                       prelu_alpha=prelu_alpha, note=note)
+
+    def __call__(self, latents):
+        """decoder(latents (B,s,s,s,D) fp32|bf16) -> volumes (B,S,S,S,out) fp32."""
+        if self.prog is None or tuple(latents.shape) != tuple(self.z_in.shape):
+            self.compile(latents.shape[0], latents.shape[1])
+        z = latents.to(self.device)
+        self.z_in.copy_(z if z.dtype == torch.bfloat16 else ops.cast(z.contiguous().float(), torch.bfloat16))
+        self.prog.run()
+        return self.out.clone()
+
+
+class MonaiDecoder(_DecoderBase):
+    """Conv3(D->c_top) PReLU; per level: R x [relu(x + PReLU(BN(Conv3(relu(Conv3(x))))))], ConvT(k4,s2) (+ReLU)."""
+
+    def __init__(self, in_channels, out_channels, num_channels, num_res_layers, num_res_channels, in_size,
+                 upsample_parameters=None, dropout=None, output_act=None, kernel_resize=False):
+        self.cin, self.out_channels, self.R, self.in_size = in_channels, out_channels, num_res_layers, in_size
+        self.ch, self.rch = list(reversed(num_channels)), list(reversed(num_res_channels))
+        self.output_act = output_act
+        sp, s = [], in_size
+        c = self.ch[0]
+        sp += [("stem.kernel", (3, 3, 3, in_channels, c), "glorot"), ("stem.bias", (c,), "zeros"), ("stem.prelu.alpha", (s, s, s, c), "zeros")]
+        for i, c in enumerate(self.ch):
+            for j in range(self.R):
+                n, rc = f"level.{i}.res.{j}", self.rch[i]
+                sp += [(f"{n}.conv1.kernel", (3, 3, 3, c, rc), "glorot"), (f"{n}.conv1.bias", (rc,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, rc, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros"),
+                       (f"{n}.norm.gamma", (c,), "ones"), (f"{n}.norm.beta", (c,), "zeros"),
+                       (f"{n}.norm.mean", (c,), "zeros"), (f"{n}.norm.var", (c,), "ones"),
+                       (f"{n}.prelu.alpha", (s, s, s, c), "zeros")]
+            out = out_channels if i == len(self.ch) - 1 else self.ch[i + 1]
+            sp += [(f"level.{i}.up.kernel", (4, 4, 4, out, c), "glorot"), (f"level.{i}.up.bias", (out,), "zeros")]
+            s *= 2
+        self.spec = sp
+        super().__init__()
+
+    def compile(self, batch, in_size=None):
+        L.require_gpu()
+        assert in_size in (None, self.in_size), "per-voxel PReLU alphas lock the decoder to its build resolution"
+        P = self.params
+        self.device = dev = torch.device("cuda", torch.cuda.current_device())
+        pr = self.prog = Program(dev)
+        s = self.in_size
+        self.z_in = pr.buf((batch, s, s, s, self.cin))
+        alpha = lambda n: P[n].to(dev, torch.bfloat16).contiguous()  # noqa: E731
+        x = self._conv(pr, self.z_in, P["stem.kernel"], P["stem.bias"], self.ch[0], prelu_alpha=alpha("stem.prelu.alpha"), note="stem")
+        for i, c in enumerate(self.ch):
+            for j in range(self.R):
+                n = f"level.{i}.res.{j}"
+                h = self._conv(pr, x, P[f"{n}.conv1.kernel"], P[f"{n}.conv1.bias"], self.rch[i], act="relu", note=f"{n}.conv1")
+                # BN (inference, eps 1e-3) folded into conv2: w' = w*scale[co], b' = b*scale + shift
+                scale = P[f"{n}.norm.gamma"] * torch.rsqrt(P[f"{n}.norm.var"] + 1e-3)
+                shift = P[f"{n}.norm.beta"] - P[f"{n}.norm.mean"] * scale
+                x = self._conv(pr, h, P[f"{n}.conv2.kernel"] * scale, P[f"{n}.conv2.bias"] * scale + shift, c,
+                               prelu_alpha=alpha(f"{n}.prelu.alpha"), residual=x, post_act="relu", note=f"{n}.conv2")
+            last = i == len(self.ch) - 1
+            out = self.out_channels if last else self.ch[i + 1]
+            act = "relu" if (not last or self.output_act) else None
+            x = self._conv(pr, x, P[f"level.{i}.up.kernel"], P[f"level.{i}.up.bias"], out, k=4, mode=L.CONV_PARITY, act=act,
+                           y_dtype=torch.float32 if last else torch.bfloat16, transposed=True, note=f"level.{i}.up")
+        self.out = x
+        torch.cuda.synchronize(dev)
+        return self
+
+
+class AttnCpDecoder(_DecoderBase):
+    """Conv1(D->c_top) GN(min(D,32)) SiLU; [ConvT(k4,s2,c_i), 2 x (GN SiLU Conv3 GN SiLU Conv3 + x)] x (L-1); Conv3(->out)."""
+
+    def __init__(self, in_channels, out_channels, num_channels, **_unused):
+        self.cin, self.out_channels = in_channels, out_channels
+        self.ch = list(reversed(num_channels))
+        c0 = self.ch[0]
+        sp = [("stem.kernel", (1, 1, 1, in_channels, c0), "glorot"), ("stem.bias", (c0,), "zeros"),
+              ("stem.norm.gamma", (c0,), "ones"), ("stem.norm.beta", (c0,), "zeros")]
+        for i in range(1, len(self.ch)):
+            c = self.ch[i]
+            sp += [(f"level.{i}.up.kernel", (4, 4, 4, c, self.ch[i - 1]), "glorot"), (f"level.{i}.up.bias", (c,), "zeros")]
+            for j in range(2):
+                n = f"level.{i}.res.{j}"
+                sp += [(f"{n}.norm1.gamma", (c,), "ones"), (f"{n}.norm1.beta", (c,), "zeros"),
+                       (f"{n}.conv1.kernel", (3, 3, 3, c, c), "glorot"), (f"{n}.conv1.bias", (c,), "zeros"),
+                       (f"{n}.norm2.gamma", (c,), "ones"), (f"{n}.norm2.beta", (c,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, c, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros")]
+        sp += [("head.kernel", (3, 3, 3, self.ch[-1], out_channels), "glorot"), ("head.bias", (out_channels,), "zeros")]
+        self.spec = sp
+        super().__init__()
+
+    def compile(self, batch, in_size):
+        L.require_gpu()
+        P = self.params
+        self.device = dev = torch.device("cuda", torch.cuda.current_device())
+        pr = self.prog = Program(dev)
+        s = in_size
+        self.z_in = pr.buf((batch, s, s, s, self.cin))
+        g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
+
+        def gn_silu(x, name, groups):
+            mr = pr.gn_stats(x, groups, 1e-6, note=f"{name}.stats")
+            return pr.norm_act(x, g(f"{name}.gamma"), g(f"{name}.beta"), pr.buf(x.shape), act="silu", kind=1, groups=groups,
+                               mean_rstd=mr, note=name)
+
+        x = self._conv(pr, self.z_in, P["stem.kernel"], P["stem.bias"], self.ch[0], k=1, note="stem")
+        x = gn_silu(x, "stem.norm", min(self.cin, 32))
+        for i in range(1, len(self.ch)):
+            c = self.ch[i]
+            grp = min(c, 32)
+            x = self._conv(pr, x, P[f"level.{i}.up.kernel"], P[f"level.{i}.up.bias"], c, k=4, mode=L.CONV_PARITY, transposed=True,
+                           note=f"level.{i}.up")
+            for j in range(2):
+                n = f"level.{i}.res.{j}"
+                h = gn_silu(x, f"{n}.norm1", grp)
+                h = self._conv(pr, h, P[f"{n}.conv1.kernel"], P[f"{n}.conv1.bias"], c, note=f"{n}.conv1")
+                h = gn_silu(h, f"{n}.norm2", grp)
+                x = self._conv(pr, h, P[f"{n}.conv2.kernel"], P[f"{n}.conv2.bias"], c, residual=x, note=f"{n}.conv2")
+        self.out = self._conv(pr, x, P["head.kernel"], P["head.bias"], self.out_channels, y_dtype=torch.float32, note="head")
+        torch.cuda.synchronize(dev)
+        return self
+
+
+# ================================================================== model wrappers (constructor surface)
+class _NoEncoder:
+    def __call__(self, *a, **k):
+        raise NotImplementedError("the encoder is not on the sampling/decode hot path (SURVEY section 8f.2); not built")
+
+
+class VQVAE:
+    """networks/vqvae3d_monai.VQVAE constructor surface; ``latent_size`` (build addition) sizes the per-voxel PReLUs
+    (Keras infers it from the fixed 128^3 input: 128 / 2^levels)."""
+
+    def __init__(self, in_channels, out_channels, num_channels, num_res_layers, num_res_channels,
+                 downsample_parameters=((2, 4, 1, 1),) * 3, upsample_parameters=((2, 4, 1, 1, 0),) * 3,
+                 num_embeddings=128, embedding_dim=64, dropout=0.1, act="relu", output_act=None, num_gpus=2,
+                 kernel_resize=False, latent_size=None):
+        self.in_channels, self.out_channels, self.num_channels = in_channels, out_channels, tuple(num_channels)
+        self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
+        self.num_res_layers, self.num_res_channels, self.num_gpus = num_res_layers, tuple(num_res_channels), num_gpus
+        if latent_size is None:
+            latent_size = 128 // (2 ** len(num_channels))
+        self.encoder = _NoEncoder()
+        self.decoder = MonaiDecoder(embedding_dim, out_channels, num_channels, num_res_layers, num_res_channels, latent_size,
+                                    upsample_parameters, dropout, output_act, kernel_resize)
+        self.quantizer = VectorQuantizer(num_embeddings, embedding_dim, layout="DK")
+
+    def load_weights(self, path):
+        p = Wt.load_npz(path)
+        self.decoder.set_weights({k[len("decoder."):]: v for k, v in p.items() if k.startswith("decoder.")})
+        self.quantizer.set_embeddings(p["quantizer.embeddings"])
+
+
+class VQGAN:
+    """networks/vqgan_attn_cp.VQGAN surface for the path: 32^3 <-> 128^3 first stage with a 3-entry channel list."""
+
+    def __init__(self, in_channels=1, out_channels=1, num_channels=(32, 64, 128), num_res_layers=2, num_res_channels=None,
+                 num_embeddings=1024, embedding_dim=256, **_training_only):
+        self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
+        self.encoder = _NoEncoder()
+        self.decoder = AttnCpDecoder(embedding_dim, out_channels, num_channels)
+        self.quantizer = VectorQuantizer(num_embeddings, embedding_dim, layout="KD")
+
+    def load_weights(self, path):
+        p = Wt.load_npz(path)
+        self.decoder.set_weights({k[len("decoder."):]: v for k, v in p.items() if k.startswith("decoder.")})
+        self.quantizer.set_embeddings(p["quantizer.embeddings"])

@@ -229,9 +229,12 @@ class ConvPlan:
         self.owned = False
 
     def __del__(self):
-        if getattr(self, "owned", False) and self.h:
-            lib().b200dm_conv_plan_destroy(self.h)
-            self.h = None
+        try:
+            if getattr(self, "owned", False) and self.h:
+                lib().b200dm_conv_plan_destroy(self.h)
+                self.h = None
+        except Exception:  # interpreter shutdown
+            pass
 
 
 def conv_out_shape(mode, in_dhw, stride):

@@ -1,0 +1,115 @@
+"""Python handle on a native step program (csrc/program.cu): an ordered list of kernel invocations over
+fixed buffers.  Building happens once; ``run()`` is one ctypes call and is CUDA-graph capturable."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import ops
+from ._lib import lib, check, ptr, stream
+
+
+class Program:
+    def __init__(self, device):
+        L.require_gpu()
+        self.device = device
+        h = C.c_void_p()
+        check(lib().b200dm_program_create(C.byref(h)))
+        self.h = h
+        self.keep = []       # every tensor the program points at
+        self.flops = 0.0     # algorithmic tensor-core FLOPs per run
+        self.bytes = 0.0     # algorithmic HBM bytes of the elementwise ops per run
+        self.log = []        # (kind, note) per op, for profiles / debugging
+        self.outputs = {}    # note -> output tensor (layer-by-layer parity debugging)
+
+    # -- allocation helper
+    def buf(self, shape, dtype=torch.bfloat16):
+        t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def hold(self, *ts):
+        for t in ts:
+            if t is not None:
+                self.keep.append(t)
+        return ts[0] if len(ts) == 1 else ts
+
+    # -- ops
+    def conv(self, desc, x0, w_packed, y, x1=None, bias=None, chan_bias=None, t_dev=None, residual=None,
+             prelu_alpha=None, note=""):
+        plan = ops.ConvPlan(desc, x0, w_packed, y, x1=x1, bias=bias, chan_bias=chan_bias, t_dev=t_dev,
+                            residual=residual, prelu_alpha=prelu_alpha)
+        self.flops += plan.flops
+        check(lib().b200dm_program_add_conv(self.h, plan.h))
+        plan.release()
+        self.keep.extend(t for t in plan.keep if t is not None)
+        self.log.append(("conv", note, plan.flops))
+        self.outputs[note] = y
+        return y
+
+    def norm_act(self, x0, a, b, y, act=None, x1=None, kind=0, groups=1, mean_rstd=None, note=""):
+        d = ops.make_norm_desc(x0, x1, kind, groups, act)
+        check(lib().b200dm_program_add_norm_act(self.h, C.byref(d), ptr(x0), ptr(x1), ptr(a), ptr(b), ptr(mean_rstd), ptr(y)))
+        self.hold(x0, x1, a, b, mean_rstd, y)
+        nbytes = 2.0 * y.numel() * 2
+        self.bytes += nbytes
+        self.log.append(("norm_act", note, nbytes))
+        self.outputs[note] = y
+        return y
+
+    def gn_stats(self, x, groups, eps, note=""):
+        d = ops.make_norm_desc(x, None, 1, groups)
+        ws_bytes = lib().b200dm_gn_stats_workspace(C.byref(d))
+        ws = self.buf((ws_bytes // 4,), torch.float32)
+        mr = self.buf((x.shape[0], groups, 2), torch.float32)
+        check(lib().b200dm_program_add_gn_stats(self.h, C.byref(d), ptr(x), eps, ptr(mr), ptr(ws), ws_bytes))
+        self.hold(x)
+        self.bytes += x.numel() * 2.0
+        self.log.append(("gn_stats", note, x.numel() * 2.0))
+        return mr
+
+    def layernorm(self, x, gammas, betas, ys, eps=1e-3, note=""):
+        c = x.shape[-1]
+        check(lib().b200dm_program_add_layernorm(self.h, ptr(x), x.numel() // c, c, eps, len(gammas), ops._ptr_array(gammas),
+                                                 ops._ptr_array(betas), ops._ptr_array(ys)))
+        self.hold(x, *gammas, *betas, *ys)
+        self.bytes += x.numel() * 2.0 * (1 + len(ys))
+        self.log.append(("layernorm", note, x.numel() * 2.0 * (1 + len(ys))))
+        return ys
+
+    def softmax(self, s, p, scale, note=""):
+        cols = s.shape[-1]
+        check(lib().b200dm_program_add_softmax(self.h, ptr(s), ptr(p), s.numel() // cols, cols, scale))
+        self.hold(s, p)
+        self.bytes += s.numel() * 6.0
+        self.log.append(("softmax", note, s.numel() * 6.0))
+        return p
+
+    def update(self, desc, x_t, eps, x_prev, x_prev_bf16=None, noise=None, note=""):
+        check(lib().b200dm_program_add_update(self.h, C.byref(desc), ptr(x_t), ptr(eps), ptr(noise), ptr(x_prev), ptr(x_prev_bf16)))
+        self.hold(x_t, eps, x_prev, x_prev_bf16, noise)
+        nbytes = x_t.numel() * (4.0 + eps.element_size() + 4.0 + (2.0 if x_prev_bf16 is not None else 0.0))
+        self.bytes += nbytes
+        self.log.append(("update", note, nbytes))
+
+    def advance(self, t_dev, delta):
+        check(lib().b200dm_program_add_step_advance(self.h, ptr(t_dev), delta))
+        self.hold(t_dev)
+        self.log.append(("advance", "", 0))
+
+    @property
+    def num_launches(self):
+        return lib().b200dm_program_num_launches(self.h)
+
+    def run(self):
+        check(lib().b200dm_program_run(self.h, stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().b200dm_program_destroy(self.h)
+                self.h = None
+        except Exception:  # interpreter shutdown
+            pass

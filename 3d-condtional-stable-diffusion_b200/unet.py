@@ -1,0 +1,309 @@
+"""3D latent U-Net on the sm_100a kernels: the host-side mirror of ``build_model``.
+
+    unconditional  reference networks/dm3d.py:294-376
+    conditional    reference networks/conditional_dm3d.py:324-415
+
+``build_model(img_size, img_channels, widths, has_attention, ...)`` keeps the reference's signature and
+returns a ``UNet``: parameters in the reference's Keras layouts under canonical names (weights.py),
+and -- once ``compile(batch, timesteps)`` is called -- a native step program of fixed-buffer kernel
+launches (conv plans, fused norm+act passes, attention) that evaluates eps_hat = network([x, t(, ctx)]).
+
+What is hoisted out of the per-step path: the time-embedding MLP and every
+ResidualBlock's Dense(swish(temb)) depend only on t -> tables over all T, read by the conv epilogue
+through a device-side timestep; ContextMLP + key(ctx)/value(ctx) depend only on the class ids ->
+computed once per generate() call.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .program import Program
+from . import weights as Wt
+
+
+def build_model(img_size, img_channels, widths, has_attention, has_cross_attention=None, num_res_blocks=2,
+                norm_groups=8, interpolation="nearest", activation_fn="swish", context_dim=None,
+                first_conv_channels=None, conditional=None):
+    """Same call surface as the reference's ``build_model``.  ``conditional`` defaults to the reference file
+    it mirrors: dm3d.build_model (context_dim=None) is unconditional with first_conv_channels=64;
+    conditional_dm3d.build_model (context_dim=1) is conditional with first_conv_channels=32.
+    ``norm_groups``, ``has_cross_attention``, ``interpolation`` are accepted and unused, as in the reference."""
+    if has_cross_attention and not context_dim:
+        raise ValueError("Context dim can not be None if has_cross_attention is not None")
+    if conditional is None:
+        conditional = context_dim is not None
+    if first_conv_channels is None:
+        first_conv_channels = 32 if conditional else 64
+    cfg = SimpleNamespace(img_size=img_size, img_channels=img_channels, widths=list(widths),
+                          has_attention=list(has_attention), num_res_blocks=num_res_blocks,
+                          first_conv_channels=first_conv_channels, conditional=bool(conditional),
+                          context_dim=context_dim if context_dim else 1)
+    return UNet(cfg)
+
+
+def _walk(cfg):
+    """The layer-construction order of build_model as a flat list of block records."""
+    F, W, R = cfg.first_conv_channels, cfg.widths, cfg.num_res_blocks
+    blocks = [dict(kind="in", name="in", cin=cfg.img_channels, cout=F, s=cfg.img_size)]
+    c, s = F, cfg.img_size
+    skips = [c]
+    for i, w in enumerate(W):
+        for j in range(R):
+            blocks.append(dict(kind="res", name=f"down.{i}.res.{j}", cin=c, cskip=0, cout=w, s=s)); c = w
+            if cfg.has_attention[i]:
+                blocks.append(dict(kind="attn", name=f"down.{i}.attn.{j}", c=c, s=s))
+            blocks.append(dict(kind="push")); skips.append(c)
+        if w != W[-1]:  # the reference compares widths by VALUE (dm3d.py:343)
+            blocks.append(dict(kind="down", name=f"down.{i}.downsample", c=c, s=s)); s //= 2
+            blocks.append(dict(kind="push")); skips.append(c)
+    blocks.append(dict(kind="res", name="mid.res.0", cin=c, cskip=0, cout=W[-1], s=s)); c = W[-1]
+    blocks.append(dict(kind="attn", name="mid.attn", c=c, s=s))
+    blocks.append(dict(kind="res", name="mid.res.1", cin=c, cskip=0, cout=c, s=s))
+    for i in reversed(range(len(W))):
+        w = W[i]
+        for j in range(R + 1):
+            cs = skips.pop()
+            blocks.append(dict(kind="res", name=f"up.{i}.res.{j}", cin=c, cskip=cs, cout=w, s=s, pop=True)); c = w
+            if cfg.has_attention[i]:
+                blocks.append(dict(kind="attn", name=f"up.{i}.attn.{j}", c=c, s=s))
+        if i != 0:
+            blocks.append(dict(kind="up", name=f"up.{i}.upsample", c=c, s=s)); s *= 2
+    blocks.append(dict(kind="out", name="out", cin=c, cout=cfg.img_channels, s=s))
+    return blocks
+
+
+def param_spec(cfg):
+    """[(canonical name, Keras-layout shape, initialiser)] in the reference's construction order."""
+    F = cfg.first_conv_channels
+    sp = []
+    bn = lambda n, c: [(f"{n}.gamma", (c,), "ones"), (f"{n}.beta", (c,), "zeros"), (f"{n}.mean", (c,), "zeros"), (f"{n}.var", (c,), "ones")]  # noqa: E731
+    dn = lambda n, i, o, k="vs1": [(f"{n}.kernel", (i, o), k), (f"{n}.bias", (o,), "zeros")]  # noqa: E731
+    cv = lambda n, k, i, o, kk="vs1": [(f"{n}.kernel", (k, k, k, i, o), kk), (f"{n}.bias", (o,), "zeros")]  # noqa: E731
+    for b in _walk(cfg):
+        k, n = b["kind"], b.get("name")
+        if k == "in":
+            sp += cv("in", 3, b["cin"], b["cout"]) + dn("time.dense0", 4 * F, 4 * F) + dn("time.dense1", 4 * F, 4 * F)
+            if cfg.conditional:
+                sp += [("ctx.embedding", (cfg.context_dim + 1, 4 * F), "embed")]
+        elif k == "res":
+            cin, w = b["cin"] + b["cskip"], b["cout"]
+            if cin != w:
+                sp += cv(f"{n}.shortcut", 1, cin, w)
+            sp += dn(f"{n}.temb", 4 * F, w) + bn(f"{n}.norm1", cin) + cv(f"{n}.conv1", 3, cin, w) + bn(f"{n}.norm2", w) + cv(f"{n}.conv2", 3, w, w, "vs0")
+        elif k == "attn":
+            c, s = b["c"], b["s"]
+            if not cfg.conditional:
+                sp += bn(f"{n}.norm", c) + dn(f"{n}.query", c, c) + dn(f"{n}.key", c, c) + dn(f"{n}.value", c, c) + dn(f"{n}.proj", c, c, "vs0")
+            else:
+                sp += dn(f"{n}.ctxmlp", 4 * F, s ** 3 * c, "glorot") + bn(f"{n}.norm", c) + cv(f"{n}.proj_in", 1, c, c, "glorot")
+                for q in ("norm1", "norm2", "norm3"):
+                    sp += [(f"{n}.{q}.gamma", (c,), "ones"), (f"{n}.{q}.beta", (c,), "zeros")]
+                sp += dn(f"{n}.query", c, c, "glorot") + dn(f"{n}.key", c, c, "glorot") + dn(f"{n}.value", c, c, "glorot")
+                sp += dn(f"{n}.mlp0", c, 4 * c, "glorot") + dn(f"{n}.mlp1", 4 * c, c, "glorot") + cv(f"{n}.proj_out", 1, c, c, "glorot")
+        elif k in ("down", "up"):
+            sp += cv(n, 3, b["c"], b["c"])
+        elif k == "out":
+            sp += bn("out.norm", b["cin"]) + cv("out.conv", 3, b["cin"], b["cout"], "vs0")
+    return sp
+
+
+class UNet:
+    """keras.Model([image_input, time_input(, context_input)]) -> eps_hat, as a compiled kernel program."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.blocks = _walk(cfg)
+        self.spec = param_spec(cfg)
+        self.params = Wt.init_params(self.spec, seed=0, mode="keras")  # {name: fp32 CPU tensor, Keras layout}
+        self.prog = None
+
+    # ---- weights ----------------------------------------------------------------------------
+    def set_weights(self, params: dict):
+        Wt.check_against_spec(params, self.spec)
+        self.params = {k: torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).float().cpu() for k, v in params.items()}
+        self.prog = None
+
+    def load_weights(self, path):
+        self.set_weights(Wt.load_npz(path))
+
+    def count_params(self):
+        return sum(int(np.prod(s)) for _, s, _ in self.spec)
+
+    # ---- compilation ------------------------------------------------------------------------
+    def compile(self, batch: int, timesteps: int, device=None, t_dev=None):
+        """Pack weights, precompute the t-only tables, allocate every activation buffer and record the launches."""
+        L.require_gpu()
+        cfg, P = self.cfg, self.params
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.device, self.batch, self.timesteps = dev, batch, timesteps
+        F, B, S = cfg.first_conv_channels, batch, cfg.img_size
+        pr = Program(dev)
+        self.prog = pr
+        self.t_dev = t_dev if t_dev is not None else torch.zeros(2, dtype=torch.int32, device=dev)
+        g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
+
+        # --- K12: time embedding MLP for every t, then per-ResidualBlock Dense(swish(temb)) tables (T, w)
+        half = 2 * F
+        freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+        e = torch.arange(timesteps, dtype=torch.float32)[:, None] * freqs[None, :]
+        sinus = torch.cat([torch.sin(e), torch.cos(e)], dim=-1).to(dev)          # TimeEmbedding (dm3d.py:177-191)
+        temb = ops.dense_f32(ops.dense_f32(sinus, g("time.dense0.kernel"), g("time.dense0.bias"), act_out="silu"),
+                             g("time.dense1.kernel"), g("time.dense1.bias"))      # TimeMLP (dm3d.py:280-288)
+        self.temb_table = temb
+
+        def conv(x0, kname, cout, y=None, x1=None, k=3, stride=1, mode=L.CONV_DIRECT, act=None, bias=True, chan_bias=None,
+                 residual=None, y_dtype=torch.bfloat16, transposed_store=False, dense=False, note=""):
+            Bx, D, H, Wd, c0 = x0.shape
+            c1 = x1.shape[-1] if x1 is not None else 0
+            desc = ops.make_conv_desc(mode, Bx, (D, H, Wd), c0, c1, cout, k, stride, act, None, y_dtype,
+                                      chan_bias_rows=1 if chan_bias is not None else 0, transposed_store=transposed_store)
+            kern = P[f"{kname}.kernel"]
+            if dense:  # Dense on voxels == 1^3 conv: (in,out) -> (1,1,1,in,out)
+                kern = kern.reshape(1, 1, 1, *kern.shape)
+            wp = ops.pack_conv_weights(desc, kern).to(dev)
+            if y is None:
+                od, oh, ow = ops.conv_out_shape(mode, (D, H, Wd), stride)
+                y = pr.buf((Bx, cout, od * oh * ow) if transposed_store else (Bx, od, oh, ow, cout), y_dtype)
+            return pr.conv(desc, x0, wp, y, x1=x1, bias=g(f"{kname}.bias") if bias else None, chan_bias=chan_bias,
+                           t_dev=self.t_dev if chan_bias is not None else None, residual=residual, note=note or kname)
+
+        def bgemm(a, b, y_dtype, residual=None, note=""):
+            Bx, M, K = a.shape
+            N = b.shape[1]
+            desc = ops.make_conv_desc(L.CONV_BATCHED_GEMM, Bx, (1, 1, M), K, 0, N, 1, 1, None, None, y_dtype)
+            y = pr.buf((Bx, M, N), y_dtype)
+            return pr.conv(desc, a, b, y, residual=residual, note=note)
+
+        def bn_act(x0, name, act, x1=None, note=""):
+            sc, sh = ops.bn_fold(g(f"{name}.gamma"), g(f"{name}.beta"), g(f"{name}.mean"), g(f"{name}.var"), 1e-3)
+            C = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+            y = pr.buf((*x0.shape[:-1], C))
+            return pr.norm_act(x0, sc, sh, y, act=act, x1=x1, note=note or name)
+
+        def resblock(b, x, skip):
+            n, w = b["name"], b["cout"]
+            cin = b["cin"] + b["cskip"]
+            if cin != w:
+                res = conv(x, f"{n}.shortcut", w, x1=skip, k=1)
+            elif skip is None:
+                res = x
+            else:  # concat whose width equals w: materialise it once (identity affine)
+                one, zero = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
+                res = pr.norm_act(x, one, zero, pr.buf((*x.shape[:-1], cin)), x1=skip, note=f"{n}.concat")
+            table = ops.dense_f32(temb, g(f"{n}.temb.kernel"), g(f"{n}.temb.bias"), act_in="silu")  # (T, w)
+            h = bn_act(x, f"{n}.norm1", "silu", x1=skip)
+            h = conv(h, f"{n}.conv1", w, chan_bias=pr.hold(table))
+            h = bn_act(h, f"{n}.norm2", "silu")
+            return conv(h, f"{n}.conv2", w, residual=res)
+
+        def attention_core(q, k, vT, scale, residual, note):
+            s = bgemm(q, k, torch.float32, note=f"{note}.qk")
+            p = pr.softmax(s, pr.buf(s.shape), scale, note=f"{note}.softmax")
+            return bgemm(p, vT, torch.bfloat16, residual=residual, note=f"{note}.pv")
+
+        def attn_block(b, x):  # AttentionBlock.call (dm3d.py:39-63)
+            n, c, s = b["name"], b["c"], b["s"]
+            Lq = s ** 3
+            nrm = bn_act(x, f"{n}.norm", None)
+            q = conv(nrm, f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
+            kk = conv(nrm, f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
+            vT = conv(nrm, f"{n}.value", c, k=1, dense=True, transposed_store=True)
+            o = attention_core(q, kk, vT, float(c) ** -0.5, None, n).view(B, s, s, s, c)
+            return conv(o, f"{n}.proj", c, k=1, dense=True, residual=nrm)   # returns BN(x) + proj (dm3d.py:63)
+
+        self.ctx_sites = []
+
+        def xattn_block(b, x):  # CrossAttentionBlock.call (conditional_dm3d.py:186-195)
+            n, c, s = b["name"], b["c"], b["s"]
+            Lq = s ** 3
+            scale = float(c) ** -0.5
+            nrm = bn_act(x, f"{n}.norm", None)
+            h = conv(nrm, f"{n}.proj_in", c, k=1, act="relu")
+            gam = [g(f"{n}.norm{i}.gamma") for i in (1, 2, 3)]
+            bet = [g(f"{n}.norm{i}.beta") for i in (1, 2, 3)]
+            ln = pr.layernorm(h, gam, bet, [pr.buf(h.shape) for _ in range(3)], 1e-3, note=f"{n}.ln")
+            hf = h.view(B, Lq, c)
+            q1 = conv(ln[0], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
+            k1 = conv(ln[0], f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
+            v1T = conv(ln[0], f"{n}.value", c, k=1, dense=True, transposed_store=True)
+            t1 = attention_core(q1, k1, v1T, scale, hf, f"{n}.self")
+            q2 = conv(ln[1], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
+            kc, vcT = pr.buf((B, Lq, c)), pr.buf((B, c, Lq))          # filled by set_context()
+            self.ctx_sites.append(dict(name=n, c=c, s=s, kc=kc, vcT=vcT))
+            t2 = attention_core(q2, kc, vcT, scale, t1, f"{n}.cross")
+            m = conv(ln[2], f"{n}.mlp0", 4 * c, k=1, dense=True, act="relu")
+            xs = conv(m, f"{n}.mlp1", c, k=1, dense=True, residual=t2.view(B, s, s, s, c))
+            # relu(proj_out(x)) + residual: act before the residual add
+            return conv(xs, f"{n}.proj_out", c, k=1, act="relu", residual=x)
+
+        self.x_in = pr.buf((B, S, S, S, cfg.img_channels))
+        self.eps = pr.buf((B, S, S, S, cfg.img_channels), torch.float32)
+        x, skips = None, []
+        for b in self.blocks:
+            k = b["kind"]
+            if k == "in":
+                x = conv(self.x_in, "in", b["cout"])
+                skips.append(x)
+            elif k == "res":
+                x = resblock(b, x, skips.pop() if b.get("pop") else None)
+            elif k == "attn":
+                x = xattn_block(b, x) if cfg.conditional else attn_block(b, x)
+            elif k == "push":
+                skips.append(x)
+            elif k == "down":
+                x = conv(x, b["name"], b["c"], stride=2)
+            elif k == "up":
+                x = conv(x, b["name"], b["c"], mode=L.CONV_PARITY)
+            elif k == "out":
+                h = bn_act(x, "out.norm", "silu")
+                conv(h, "out.conv", b["cout"], y=self.eps, y_dtype=torch.float32)
+        torch.cuda.synchronize(dev)
+        return self
+
+    # ---- per-generate() context (conditional): ContextMLP + key(ctx) / value(ctx) --------------------------
+    def set_context(self, ctx_ids):
+        """ctx_ids: (B,) int class ids (0 healthy / 1 BraTS, dataset_utils.py:143,160)."""
+        if not self.cfg.conditional:
+            return
+        P, dev, B = self.params, self.device, self.batch
+        ids = torch.as_tensor(ctx_ids).long().reshape(-1).cpu()
+        if ids.numel() == 1:
+            ids = ids.expand(B)  # the reference feeds a batch-1 context (conditional_dm3d.py:552)
+        assert ids.numel() == B
+        cemb = P["ctx.embedding"][ids].to(dev).contiguous()          # Embedding (conditional_dm3d.py:358)
+        for site in self.ctx_sites:
+            n, c, s = site["name"], site["c"], site["s"]
+            ctx = ops.dense_f32(cemb, P[f"{n}.ctxmlp.kernel"].to(dev), P[f"{n}.ctxmlp.bias"].to(dev), act_out="silu")
+            ctx = ops.cast(ctx, torch.bfloat16).view(B, s, s, s, c)
+            for wname, out, tr in (("key", site["kc"], False), ("value", site["vcT"], True)):
+                desc = ops.make_conv_desc(L.CONV_DIRECT, B, (s, s, s), c, 0, c, 1, 1, transposed_store=tr)
+                wp = ops.pack_conv_weights(desc, P[f"{n}.{wname}.kernel"].reshape(1, 1, 1, c, c)).to(dev)
+                ops.ConvPlan(desc, ctx, wp, out, bias=P[f"{n}.{wname}.bias"].to(dev)).run()
+        torch.cuda.synchronize(dev)
+
+    # ---- call ---------------------------------------------------------------------------------------------
+    def forward_inplace(self):
+        """eps[...] = network(x_in, t_dev[0]) on the pre-bound buffers."""
+        self.prog.run()
+        return self.eps
+
+    def __call__(self, inputs):
+        """network([x (B,S,S,S,C) fp32|bf16, t (B,) int (, ctx (B,)|(B,1,1) int)]) -> eps_hat fp32 (new tensor)."""
+        x, t = inputs[0], inputs[1]
+        if self.prog is None or self.batch != x.shape[0]:
+            raise L.B200dmError("UNet: call compile(batch, timesteps) first (batch must match)")
+        tv = int(torch.as_tensor(t).reshape(-1)[0])
+        if not bool((torch.as_tensor(t).reshape(-1) == tv).all()):
+            raise L.B200dmError("UNet: the sampling path uses one timestep per batch, as generate() does")
+        if len(inputs) > 2 and self.cfg.conditional:
+            self.set_context(torch.as_tensor(inputs[2]).reshape(-1))
+        self.t_dev.copy_(torch.tensor([tv, tv - 1], dtype=torch.int32))
+        x = x.to(self.device)
+        self.x_in.copy_(x if x.dtype == torch.bfloat16 else ops.cast(x.contiguous().float(), torch.bfloat16))
+        return self.forward_inplace().clone()

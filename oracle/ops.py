@@ -17,11 +17,15 @@ class Emu:
     ``Emu(True)`` rounds to bf16 at the CUDA path's bf16 storage points (activations
     written to HBM, weights fed to the tensor cores)."""
 
-    def __init__(self, bf16: bool = False):
+    def __init__(self, bf16: bool = False, trace: dict | None = None):
         self.bf16 = bf16
+        self.trace = trace  # optional {tag: tensor} of every tagged storage point (layer-by-layer debugging)
 
-    def a(self, x: torch.Tensor) -> torch.Tensor:  # activation storage point
-        return x.to(torch.bfloat16).to(x.dtype) if self.bf16 else x
+    def a(self, x: torch.Tensor, tag: str | None = None) -> torch.Tensor:  # activation storage point
+        y = x.to(torch.bfloat16).to(x.dtype) if self.bf16 else x
+        if self.trace is not None and tag is not None:
+            self.trace[tag] = y
+        return y
 
     def w(self, x: torch.Tensor) -> torch.Tensor:  # tensor-core weight operand
         return x.to(torch.bfloat16).to(x.dtype) if self.bf16 else x

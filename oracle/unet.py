@@ -122,12 +122,12 @@ class UNet:
         if cin == w:
             res = x
         else:
-            res = emu.a(ops.conv3d(x, emu.w(P[f"{name}.shortcut.kernel"]), P[f"{name}.shortcut.bias"]))
+            res = emu.a(ops.conv3d(x, emu.w(P[f"{name}.shortcut.kernel"]), P[f"{name}.shortcut.bias"]), f"{name}.shortcut")
         e = ops.dense(ops.swish(temb), P[f"{name}.temb.kernel"], P[f"{name}.temb.bias"])[:, None, None, None, :]
-        h = emu.a(ops.swish(self._bn_apply(P, f"{name}.norm1", x)))
-        h = emu.a(ops.conv3d(h, emu.w(P[f"{name}.conv1.kernel"]), P[f"{name}.conv1.bias"]) + e)
-        h = emu.a(ops.swish(self._bn_apply(P, f"{name}.norm2", h)))
-        return emu.a(ops.conv3d(h, emu.w(P[f"{name}.conv2.kernel"]), P[f"{name}.conv2.bias"]) + res)
+        h = emu.a(ops.swish(self._bn_apply(P, f"{name}.norm1", x)), f"{name}.norm1")
+        h = emu.a(ops.conv3d(h, emu.w(P[f"{name}.conv1.kernel"]), P[f"{name}.conv1.bias"]) + e, f"{name}.conv1")
+        h = emu.a(ops.swish(self._bn_apply(P, f"{name}.norm2", h)), f"{name}.norm2")
+        return emu.a(ops.conv3d(h, emu.w(P[f"{name}.conv2.kernel"]), P[f"{name}.conv2.bias"]) + res, f"{name}.conv2")
 
     def _d(self, P, name, x, emu, act=None):
         y = ops.dense(x, emu.w(P[f"{name}.kernel"]), P[f"{name}.bias"])
@@ -138,11 +138,11 @@ class UNet:
     def _attention(self, P, name, x, c, emu: Emu):
         """AttentionBlock.call (dm3d.py:39-63)."""
         B, s = x.shape[0], x.shape[1]
-        n = emu.a(self._bn_apply(P, f"{name}.norm", x))
+        n = emu.a(self._bn_apply(P, f"{name}.norm", x), f"{name}.norm")
         f = n.reshape(B, s ** 3, c)
         q, k, v = (emu.a(self._d(P, f"{name}.{m}", f, emu)) for m in ("query", "key", "value"))
         o = emu.a(ops.attention_core(q, k, v, float(c) ** -0.5, emu))
-        return emu.a(n + self._d(P, f"{name}.proj", o, emu).reshape(x.shape))
+        return emu.a(n + self._d(P, f"{name}.proj", o, emu).reshape(x.shape), f"{name}.proj")
 
     def context_kv(self, P, name, cemb, c, s, emu: Emu):
         """ContextMLP (conditional_dm3d.py:310-318) + key(ctx), value(ctx) (:168-169): step-invariant."""
@@ -171,7 +171,7 @@ class UNet:
         """x (B,S,S,S,C_lat) fp32, t (B,) int, ctx (B,) int class ids (conditional) -> eps_hat fp32."""
         temb = self.temb(P, t)
         cemb = P["ctx.embedding"][ctx.long()] if self.cond else None  # Embedding (conditional_dm3d.py:358)
-        x = emu.a(ops.conv3d(emu.a(x), emu.w(P["in.kernel"]), P["in.bias"]))
+        x = emu.a(ops.conv3d(emu.a(x), emu.w(P["in.kernel"]), P["in.bias"]), "in")
         skips = [x]
         for op in self.prog:
             kind = op[0]
@@ -183,12 +183,12 @@ class UNet:
             elif kind == "push":
                 skips.append(x)
             elif kind == "down":
-                x = emu.a(ops.conv3d(x, emu.w(P[f"{op[1]}.kernel"]), P[f"{op[1]}.bias"], stride=2))
+                x = emu.a(ops.conv3d(x, emu.w(P[f"{op[1]}.kernel"]), P[f"{op[1]}.bias"], stride=2), op[1])
             elif kind == "cat":
                 x = torch.cat([x, skips.pop()], dim=-1)
             elif kind == "up":
-                x = emu.a(ops.conv3d(ops.upsample_nearest2(x), emu.w(P[f"{op[1]}.kernel"]), P[f"{op[1]}.bias"]))
-        x = emu.a(ops.swish(self._bn_apply(P, "out.norm", x)))
+                x = emu.a(ops.conv3d(ops.upsample_nearest2(x), emu.w(P[f"{op[1]}.kernel"]), P[f"{op[1]}.bias"]), op[1])
+        x = emu.a(ops.swish(self._bn_apply(P, "out.norm", x)), "out.norm")
         return ops.conv3d(x, emu.w(P["out.conv.kernel"]), P["out.conv.bias"])
 
     def flops(self, batch=1):
