@@ -83,6 +83,8 @@ _SIGS = {
     "b200dm_program_add_step_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "b200dm_program_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200dm_program_num_launches": (C.c_int, [C.c_void_p]),
+    "b200dm_program_num_ops": (C.c_int, [C.c_void_p]),
+    "b200dm_program_run_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -107,10 +107,45 @@ extern "C" int b200dm_program_num_launches(const b200dm_program* p) {
   return n;
 }
 
+static int run_op(Op& op, void* stream);
+
 extern "C" int b200dm_program_run(b200dm_program* p, void* stream) {
   B2_CHECK_ARG(p, "program_run: null program");
-  int rc = B200DM_OK;
   for (auto& op : p->ops) {
+    int rc = run_op(op, stream);
+    if (rc != B200DM_OK) return rc;
+  }
+  return B200DM_OK;
+}
+
+// Same launches, with a CUDA event pair around every op on the launching stream; ms_per_op[i] = device time of
+// op i.  Synchronises the stream (profiling aid for bench.py's roofline figures; not capturable).
+extern "C" int b200dm_program_run_timed(b200dm_program* p, void* stream, float* ms_per_op, int32_t n_ops) {
+  B2_CHECK_ARG(p && ms_per_op, "program_run_timed: null argument");
+  B2_CHECK_ARG(n_ops == (int32_t)p->ops.size(), "program_run_timed: n_ops %d != %d", n_ops, (int)p->ops.size());
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(p->ops.size() + 1);
+  for (auto& e : ev) B2_CHECK_CUDA(cudaEventCreate(&e));
+  B2_CHECK_CUDA(cudaEventRecord(ev[0], s));
+  int rc = B200DM_OK;
+  for (size_t i = 0; i < p->ops.size() && rc == B200DM_OK; ++i) {
+    rc = run_op(p->ops[i], stream);
+    cudaEventRecord(ev[i + 1], s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == B200DM_OK && e == cudaSuccess)
+    for (size_t i = 0; i < p->ops.size(); ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (rc != B200DM_OK) return rc;
+  B2_CHECK_CUDA(e);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_num_ops(const b200dm_program* p) { return p ? (int)p->ops.size() : 0; }
+
+static int run_op(Op& op, void* stream) {
+  int rc = B200DM_OK;
+  {
     switch (op.kind) {
       case OP_CONV: rc = b200dm_conv_plan_run(op.conv, stream); break;
       case OP_NORM:
@@ -124,7 +159,6 @@ extern "C" int b200dm_program_run(b200dm_program* p, void* stream) {
         break;
       case OP_ADVANCE: rc = b200dm_step_advance((int32_t*)op.out, op.i1, stream); break;
     }
-    if (rc != B200DM_OK) return rc;
   }
-  return B200DM_OK;
+  return rc;
 }

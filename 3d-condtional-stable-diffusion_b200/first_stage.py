@@ -82,12 +82,18 @@ class _DecoderBase:
     out_channels: int
 
     def __init__(self):
-        self.params = Wt.init_params(self.spec, seed=1, mode="keras")
+        self._params = None   # random-initialised lazily (per-voxel PReLU alphas make D1 large)
         self.prog = None
+
+    @property
+    def params(self):
+        if self._params is None:
+            self._params = Wt.init_params(self.spec, seed=1, mode="keras")
+        return self._params
 
     def set_weights(self, params):
         Wt.check_against_spec(params, self.spec)
-        self.params = {k: torch.as_tensor(v).float().cpu() for k, v in params.items()}
+        self._params = {k: torch.as_tensor(v).float().cpu() for k, v in params.items()}
         self.prog = None
 
     def count_params(self):

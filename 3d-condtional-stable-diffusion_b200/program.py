@@ -106,6 +106,14 @@ class Program:
     def run(self):
         check(lib().b200dm_program_run(self.h, stream()))
 
+    def run_timed(self):
+        """-> [(kind, note, work, ms)] per op (CUDA events around every launch; synchronises)."""
+        n = lib().b200dm_program_num_ops(self.h)
+        ms = (C.c_float * n)()
+        check(lib().b200dm_program_run_timed(self.h, stream(), ms, n))
+        assert n == len(self.log)
+        return [(k, note, work, ms[i]) for i, (k, note, work) in enumerate(self.log)]
+
     def __del__(self):
         try:
             if getattr(self, "h", None):

@@ -120,13 +120,19 @@ class UNet:
         self.cfg = cfg
         self.blocks = _walk(cfg)
         self.spec = param_spec(cfg)
-        self.params = Wt.init_params(self.spec, seed=0, mode="keras")  # {name: fp32 CPU tensor, Keras layout}
+        self._params = None  # {name: fp32 CPU tensor, Keras layout}; random-initialised lazily
         self.prog = None
+
+    @property
+    def params(self):
+        if self._params is None:
+            self._params = Wt.init_params(self.spec, seed=0, mode="keras")
+        return self._params
 
     # ---- weights ----------------------------------------------------------------------------
     def set_weights(self, params: dict):
         Wt.check_against_spec(params, self.spec)
-        self.params = {k: torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).float().cpu() for k, v in params.items()}
+        self._params = {k: torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).float().cpu() for k, v in params.items()}
         self.prog = None
 
     def load_weights(self, path):

@@ -229,6 +229,9 @@ int b200dm_program_add_update(b200dm_program* p, const b200dm_update_desc* d, co
 int b200dm_program_add_step_advance(b200dm_program* p, int32_t* t_dev, int32_t delta);
 int b200dm_program_run(b200dm_program* p, void* stream);
 int b200dm_program_num_launches(const b200dm_program* p);
+int b200dm_program_num_ops(const b200dm_program* p);
+/* profiling aid: same launches with a CUDA-event pair around every op; synchronises the stream */
+int b200dm_program_run_timed(b200dm_program* p, void* stream, float* ms_per_op, int32_t n_ops);
 
 #ifdef __cplusplus
 }
