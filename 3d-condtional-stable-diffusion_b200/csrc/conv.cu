@@ -22,35 +22,13 @@
 #include <math.h>
 #include <new>
 #include <vector>
-#include "common.cuh"
-#include "ptx.cuh"
+#include "conv_common.cuh"
+#include "conv_halo.cuh"
 
 namespace {
 
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
-
-struct ConvParams {
-  int mode, batch;
-  int in_d, in_h, in_w;
-  int out_d, out_h, out_w;
-  int m_d, m_h, m_w;                 // M-space extent (== out for DIRECT / GEMM, == in for PARITY)
-  int box_w, box_h, box_d, box_n;    // product == 128
-  int tiles_w, tiles_h, tiles_d, tiles_n;
-  int nch0, nch1, ntaps, ksize, stride, pad;
-  int c_out, n_pad;
-  int act, post_act, y_f32, transposed_store;
-  int chan_bias_rows;
-  const float* bias;
-  const float* chan_bias;
-  const int* t_dev;
-  const __nv_bfloat16* residual;
-  const __nv_bfloat16* prelu_alpha;  // (d,h,w,c) bf16, no batch dim
-  void* y;
-  int* dbg;
-};
-
-__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
 
 template <int BLOCK_N, int NSTAGE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -102,53 +80,61 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       const int b_row = (p.mode == B200DM_CONV_PARITY ? parity : (p.mode == B200DM_CONV_BATCHED_GEMM ? n0 : 0)) * p.n_pad +
                         n_tile * BLOCK_N;
+      uint32_t s = 0, phase = 0;
+      int chunk = 0, tap = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % NSTAGE;
-        const uint32_t phase = (kb / NSTAGE) & 1;
         if (!ptx::mbar_wait(empty_bar(s), phase ^ 1, p.dbg, 1)) break;
-        const int chunk = kb / p.ntaps, tap = kb - chunk * p.ntaps;
-        int ow, oh, od;
-        if (p.mode == B200DM_CONV_PARITY) {
-          ow = (tap & 1) - 1 + pw; oh = ((tap >> 1) & 1) - 1 + ph; od = ((tap >> 2) & 1) - 1 + pd;
-        } else {
-          const int k = p.ksize;
-          ow = tap % k - p.pad; oh = (tap / k) % k - p.pad; od = tap / (k * k) - p.pad;
+        if (ptx::elect_one()) {
+          int ow, oh, od;
+          if (p.mode == B200DM_CONV_PARITY) {
+            ow = (tap & 1) - 1 + pw; oh = ((tap >> 1) & 1) - 1 + ph; od = ((tap >> 2) & 1) - 1 + pd;
+          } else {
+            const int k = p.ksize;
+            ow = tap % k - p.pad; oh = (tap / k) % k - p.pad; od = tap / (k * k) - p.pad;
+          }
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          const uint32_t b_dst = a_dst + kABytes;
+          ptx::mbar_expect_tx(full_bar(s), kStageBytes);
+          if (chunk < p.nch0)
+            ptx::tma_load_5d(a_dst, &mapA0, full_bar(s), chunk * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
+          else
+            ptx::tma_load_5d(a_dst, &mapA1, full_bar(s), (chunk - p.nch0) * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
+          ptx::tma_load_2d(b_dst, &mapB, full_bar(s), kb * 64, b_row);
         }
-        const uint32_t a_dst = smem_base + s * kStageBytes;
-        const uint32_t b_dst = a_dst + kABytes;
-        ptx::mbar_expect_tx(full_bar(s), kStageBytes);
-        if (chunk < p.nch0)
-          ptx::tma_load_5d(a_dst, &mapA0, full_bar(s), chunk * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
-        else
-          ptx::tma_load_5d(a_dst, &mapA1, full_bar(s), (chunk - p.nch0) * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
-        ptx::tma_load_2d(b_dst, &mapB, full_bar(s), kb * 64, b_row);
+        __syncwarp();
+        if (++s == NSTAGE) { s = 0; phase ^= 1; }
+        if (++tap == p.ntaps) { tap = 0; ++chunk; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {  // whole warp walks the loop; one elected lane issues (no per-lane serialisation loops around UTCHMMA)
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
+      const uint64_t a_desc0 = ptx::make_smem_desc(smem_base, 16, 1024, ptx::kLayoutSw128);
+      const uint64_t b_desc0 = ptx::make_smem_desc(smem_base + kABytes, 16, 1024, ptx::kLayoutSw128);
       bool ok = true;
+      uint32_t s = 0, phase = 0;
       for (int kb = 0; kb < nkb && ok; ++kb) {
-        const int s = kb % NSTAGE;
-        const uint32_t phase = (kb / NSTAGE) & 1;
         ok = ptx::mbar_wait(full_bar(s), phase, p.dbg, 2);
         if (!ok) break;
         ptx::tc_fence_after();
-        const uint32_t a_addr = smem_base + s * kStageBytes;
-        const uint32_t b_addr = a_addr + kABytes;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t da = ptx::make_smem_desc(a_addr + ks * 32, 16, 1024, ptx::kLayoutSw128);
-          const uint64_t db = ptx::make_smem_desc(b_addr + ks * 32, 16, 1024, ptx::kLayoutSw128);
-          ptx::tc_mma_f16(tmem_base, da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
+        if (ptx::elect_one()) {
+          const uint64_t da = a_desc0 + (uint64_t)(s * (kStageBytes >> 4));
+          const uint64_t db = b_desc0 + (uint64_t)(s * (kStageBytes >> 4));
+          ptx::tc_mma_f16(tmem_base, da, db, idesc, kb != 0 ? 1u : 0u);
+          ptx::tc_mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
+          ptx::tc_mma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
+          ptx::tc_mma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
+          ptx::tc_commit(empty_bar(s));
         }
-        ptx::tc_commit(empty_bar(s));
+        __syncwarp();
+        if (++s == NSTAGE) { s = 0; phase ^= 1; }
       }
-      ptx::tc_commit(tmem_full_bar);
+      if (ptx::elect_one()) ptx::tc_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
@@ -182,78 +168,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
         ptx::tc_wait_ld();
         if (!valid) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
-        const int ncol = (p.c_out - col0) < 16 ? (p.c_out - col0) : 16;
-        if (ncol == 16 && !p.transposed_store) {
-          // vector path: 16 channels = 32 B bf16 / 64 B fp32 per thread
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (cb) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb + col0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (p.prelu_alpha) {
-            float a[16];
-            const __nv_bfloat16* ap = p.prelu_alpha + vox * p.c_out + col0;
-            unpack8(*reinterpret_cast<const bf16x8*>(ap), *reinterpret_cast<float(*)[8]>(&a[0]));
-            unpack8(*reinterpret_cast<const bf16x8*>(ap + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) + a[j] * fminf(v[j], 0.f);
-          }
-          if (p.act != B200DM_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          if (p.residual) {
-            float a[16];
-            const __nv_bfloat16* rp = p.residual + row_off + col0;
-            unpack8(*reinterpret_cast<const bf16x8*>(rp), *reinterpret_cast<float(*)[8]>(&a[0]));
-            unpack8(*reinterpret_cast<const bf16x8*>(rp + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += a[j];
-          }
-          if (p.post_act != B200DM_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
-          }
-          if (p.y_f32) {
-            float* yo = reinterpret_cast<float*>(p.y) + row_off + col0;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + row_off + col0;
-            *reinterpret_cast<bf16x8*>(yo) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
-            *reinterpret_cast<bf16x8*>(yo + 8) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
-          }
-        } else {
-          // scalar path: ragged channel tail (e.g. C_out = 1) or per-sample transposed store
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < ncol) {
-              const int col = col0 + j;
-              float x = v[j];
-              if (p.bias) x += __ldg(p.bias + col);
-              if (cb) x += __ldg(cb + col);
-              if (p.prelu_alpha) { const float a = bf(p.prelu_alpha[vox * p.c_out + col]); x = fmaxf(x, 0.f) + a * fminf(x, 0.f); }
-              x = apply_act(x, p.act);
-              if (p.residual) x += bf(p.residual[row_off + col]);
-              x = apply_act(x, p.post_act);
-              const int64_t o = p.transposed_store ? ((int64_t)n * p.c_out + col) * vox_per + vox : row_off + col;
-              if (p.y_f32) reinterpret_cast<float*>(p.y)[o] = x;
-              else reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(x);
-            }
-          }
-        }
+        conv_epilogue16(p, rr, col0, n, vox, vox_per, row_off, cb);
       }
     }
   }
@@ -367,6 +282,8 @@ struct b200dm_conv_plan {
   size_t smem;
   int nstage;
   double flops;
+  bool halo = false;
+  int halo_td = 1, halo_mc = 1, halo_nb = 4;
 };
 
 static int* g_dbg_flag = nullptr;
@@ -462,6 +379,34 @@ static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
   return B200DM_OK;
 }
 
+template <int BLOCK_N, int TD, int NB, int MC>
+static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
+  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, 6, NB, MC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = pl->grid;
+  cfg.blockDim = dim3(halo::kThreads);
+  cfg.dynamicSmemBytes = pl->smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = MC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+  return B200DM_OK;
+}
+
+template <int BLOCK_N, int NB>
+static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
+  if (pl->halo_td == 2) return pl->halo_mc == 2 ? launch_halo<BLOCK_N, 2, NB, 2>(pl, s) : launch_halo<BLOCK_N, 2, NB, 1>(pl, s);
+  return pl->halo_mc == 2 ? launch_halo<BLOCK_N, 1, NB, 2>(pl, s) : launch_halo<BLOCK_N, 1, NB, 1>(pl, s);
+}
+
 static size_t conv_smem_bytes(int block_n, int nstage) {
   return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (2 * nstage + 1) * 8 + 16;
 }
@@ -489,11 +434,16 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   pl->desc = *d;
   pl->g = g;
   const int st = d->mode == B200DM_CONV_DIRECT ? d->stride : 1;
+  // halo-reuse kernel: 3^3 stride-1 convs on volumes that fill its 8w x 16h tile (use_halo = -1 forces it off)
+  pl->halo = d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w >= 8 && d->in_h >= 16 &&
+             d->reserved[1] == 0 && d->use_halo >= 0;
   auto encodeA = [&](CUtensorMap* m, const void* ptr, int C) -> int {
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->in_d, (cuuint64_t)d->batch};
     cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)d->in_w * C * 2, (cuuint64_t)d->in_h * d->in_w * C * 2,
                              (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)(g.box_w * st), (cuuint32_t)(g.box_h * st), (cuuint32_t)(g.box_d * st), (cuuint32_t)g.box_n};
+    if (pl->halo) { box[1] = 10; box[2] = 18; box[3] = 1; box[4] = 1; }   // one halo d-plane slab
+
     cuuint32_t es[5] = {1, (cuuint32_t)st, (cuuint32_t)st, (cuuint32_t)st, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -514,6 +464,14 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       dims[0] = (cuuint64_t)d->c0; dims[1] = (cuuint64_t)d->batch * d->c_out; strides[0] = (cuuint64_t)d->c0 * 2;
     }
     cuuint32_t box[2] = {64, (cuuint32_t)g.block_n};
+    if (pl->halo) {
+      const long long t1 = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
+      pl->halo_td = d->in_d >= 2 && t1 >= b2_num_sms() ? 2 : 1;
+      const long long tl = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + pl->halo_td - 1) / pl->halo_td) * d->batch;
+      pl->halo_mc = (d->use_halo == 1 || d->use_halo == 0) && tl >= 2LL * b2_num_sms() && d->use_halo != 3 ? 2 : 1;
+      if (d->use_halo == 3) pl->halo_mc = 1;
+      box[1] = (cuuint32_t)(g.block_n / pl->halo_mc);
+    }
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -542,6 +500,18 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   pl->grid = dim3((unsigned)mtiles, (unsigned)ntiles, d->mode == B200DM_CONV_PARITY ? 8 : 1);
   pl->nstage = 4;
   pl->smem = conv_smem_bytes(g.block_n, pl->nstage);
+  if (pl->halo) {
+    const int td = pl->halo_td, mc = pl->halo_mc;
+    p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td; p.tiles_n = d->batch;
+    long long per = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+    per = (per + mc - 1) / mc * mc;
+    p.halo_td = td; p.halo_tiles_per_ntile = (int)per; p.halo_ntn = ntiles; p.halo_total_tiles = (int)(per * ntiles);
+    int ctas = b2_num_sms() / mc * mc;
+    if (ctas > p.halo_total_tiles) ctas = p.halo_total_tiles;
+    pl->grid = dim3((unsigned)ctas, 1, 1);
+    pl->halo_nb = g.block_n >= 128 ? 4 : (g.block_n == 64 ? 6 : 8);
+    pl->smem = 1024 + (size_t)6 * halo::kSlabBytes + (size_t)pl->halo_nb * g.block_n * 128 + (2 * 6 + 2 * pl->halo_nb + 4) * 8 + 16;
+  }
   // algorithmic FLOPs: 2*k^3*Cin*Cout*B*out_voxels; convT: 2*64*Cin*Cout*B*in_voxels; GEMM: 2*M*N*K
   if (d->mode == B200DM_CONV_PARITY)
     pl->flops = d->ksize == 3 ? 2.0 * 27 * (d->c0 + d->c1) * d->c_out * (double)d->batch * g.out_d * g.out_h * g.out_w
@@ -555,6 +525,14 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
 extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
+  if (pl->halo) {
+    switch (pl->g.block_n) {
+      case 16: return dispatch_halo<16, 8>(pl, s);
+      case 32: return dispatch_halo<32, 8>(pl, s);
+      case 64: return dispatch_halo<64, 6>(pl, s);
+      case 128: return dispatch_halo<128, 4>(pl, s);
+    }
+  }
   switch (pl->g.block_n) {
     case 16: return launch_conv<16, 4>(pl, s);
     case 32: return launch_conv<32, 4>(pl, s);

@@ -1,0 +1,105 @@
+// Shared between the two implicit-GEMM conv kernels: launch parameters and the fused epilogue.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+struct ConvParams {
+  int mode, batch;
+  int in_d, in_h, in_w;
+  int out_d, out_h, out_w;
+  int m_d, m_h, m_w;                 // M-space extent (== out for DIRECT / GEMM, == in for PARITY)
+  int box_w, box_h, box_d, box_n;    // product == 128
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  int nch0, nch1, ntaps, ksize, stride, pad;
+  int c_out, n_pad;
+  int act, post_act, y_f32, transposed_store;
+  int chan_bias_rows;
+  int halo_td, halo_tiles_per_ntile, halo_ntn, halo_total_tiles;   // halo kernel only
+  const float* bias;
+  const float* chan_bias;
+  const int* t_dev;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* prelu_alpha;  // (d,h,w,c) bf16, no batch dim
+  void* y;
+  int* dbg;
+};
+
+__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+
+// Epilogue for 16 consecutive accumulator columns of one output voxel (thread = TMEM lane = GEMM row):
+//   + bias[co] + chan_bias[t][n][co]  ->  PReLU(alpha[voxel][co])  ->  act  ->  + residual  ->  post_act  ->  store
+__device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint32_t (&rr)[16], int col0, int n, int64_t vox,
+                                                int64_t vox_per, int64_t row_off, const float* cb) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+  const int ncol = (p.c_out - col0) < 16 ? (p.c_out - col0) : 16;
+  if (ncol == 16 && !p.transposed_store) {
+    // vector path: 16 channels = 32 B bf16 / 64 B fp32 per thread
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    }
+    if (cb) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb + col0 + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    }
+    if (p.prelu_alpha) {
+      float a[16];
+      const __nv_bfloat16* ap = p.prelu_alpha + vox * p.c_out + col0;
+      unpack8(*reinterpret_cast<const bf16x8*>(ap), *reinterpret_cast<float(*)[8]>(&a[0]));
+      unpack8(*reinterpret_cast<const bf16x8*>(ap + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) + a[j] * fminf(v[j], 0.f);
+    }
+    if (p.act != B200DM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+    }
+    if (p.residual) {
+      float a[16];
+      const __nv_bfloat16* rp = p.residual + row_off + col0;
+      unpack8(*reinterpret_cast<const bf16x8*>(rp), *reinterpret_cast<float(*)[8]>(&a[0]));
+      unpack8(*reinterpret_cast<const bf16x8*>(rp + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += a[j];
+    }
+    if (p.post_act != B200DM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+    }
+    if (p.y_f32) {
+      float* yo = reinterpret_cast<float*>(p.y) + row_off + col0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + row_off + col0;
+      *reinterpret_cast<bf16x8*>(yo) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
+      *reinterpret_cast<bf16x8*>(yo + 8) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
+    }
+  } else {
+    // scalar path: ragged channel tail (e.g. C_out = 1) or per-sample transposed store
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < ncol) {
+        const int col = col0 + j;
+        float x = v[j];
+        if (p.bias) x += __ldg(p.bias + col);
+        if (cb) x += __ldg(cb + col);
+        if (p.prelu_alpha) { const float a = bf(p.prelu_alpha[vox * p.c_out + col]); x = fmaxf(x, 0.f) + a * fminf(x, 0.f); }
+        x = apply_act(x, p.act);
+        if (p.residual) x += bf(p.residual[row_off + col]);
+        x = apply_act(x, p.post_act);
+        const int64_t o = p.transposed_store ? ((int64_t)n * p.c_out + col) * vox_per + vox : row_off + col;
+        if (p.y_f32) reinterpret_cast<float*>(p.y)[o] = x;
+        else reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(x);
+      }
+    }
+  }
+}

@@ -182,3 +182,47 @@ def test_batched_gemm_and_transposed_store(cuda):
     o = ops.batched_gemm(p.to(cuda, torch.bfloat16), vt)
     _check_flag()
     _close(o, torch.einsum("blL,bcL->blc", p, vt.float().cpu()), what="P V")
+
+
+HALO_CASES = [
+    # B, (D,H,W), c0, c1, cout, use_halo (0 auto incl. weight multicast when the grid is large, 3 = no multicast)
+    (1, (16, 16, 16), 64, 0, 64, 3),
+    (1, (16, 16, 16), 64, 0, 64, 0),
+    (2, (5, 24, 12), 64, 32, 64, 3),      # odd depth, ragged H/W tiles, two K-segments
+    (1, (16, 16, 16), 8, 0, 32, 3),       # C_in = 8 (TMA zero-fills the 64-channel chunk)
+    (1, (8, 16, 8), 128, 0, 256, 3),      # two N tiles
+    (1, (16, 32, 32), 32, 0, 1, 3),       # decoder head, C_out = 1
+    (8, (32, 32, 32), 64, 0, 64, 0),      # cfg-2 level-0 shape: TD=2, clusters of 2 with multicast weights
+    (3, (32, 32, 32), 64, 0, 128, 0),
+]
+
+
+@pytest.mark.parametrize("B,dhw,c0,c1,cout,mode", HALO_CASES)
+def test_conv3_halo_kernel(cuda, B, dhw, c0, c1, cout, mode):
+    """Persistent halo-reuse kernel (shifted SWIZZLE_128B descriptors over TMA-staged halo slabs) vs the oracle,
+    and bit-for-bit against the per-tap kernel (same bf16 products, fp32 accumulation; order may differ)."""
+    from b200dm import ops, _lib
+    D, H, W = dhw
+    x0 = _rand((B, D, H, W, c0), 1)
+    x1 = _rand((B, D, H, W, c1), 6) if c1 else None
+    cin = c0 + c1
+    w = _rand((3, 3, 3, cin, cout), 2, 1.0 / np.sqrt(27 * cin))
+    b = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+    res = _rand((B, D, H, W, cout), 5)
+    xin = torch.cat([x0, x1], -1) if c1 else x0
+    big = B * D * H * W * cin * cout > 2e10
+    ys = {}
+    for m in (mode, -1):
+        desc = ops.make_conv_desc(_lib.CONV_DIRECT, B, dhw, c0, c1, cout, 3, 1, y_dtype=torch.float32, use_halo=m)
+        wp = ops.pack_conv_weights(desc, w).to(cuda)
+        y = torch.empty(B, D, H, W, cout, dtype=torch.float32, device=cuda)
+        ops.ConvPlan(desc, x0.to(cuda, torch.bfloat16), wp, y, x1=x1.to(cuda, torch.bfloat16) if c1 else None,
+                     bias=b.to(cuda), residual=res.to(cuda, torch.bfloat16)).run()
+        _check_flag()
+        ys[m] = y.cpu()
+    d = (ys[mode] - ys[-1]).abs().max().item() / ys[-1].abs().max().item()
+    print(f"halo vs per-tap kernel: rel max diff {d:.3e}")
+    assert d < 2e-5
+    if not big:
+        ref = O.conv3d(xin, w, b) + res
+        _close(ys[mode], ref, what=f"halo conv B{B} {dhw} {c0}+{c1}->{cout}")
