@@ -42,6 +42,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * kStageBytes);
   // bars[0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2NSTAGE] tmem_full; then tmem ptr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -152,10 +153,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;           // voxel index within the sample
     const int64_t vox_per = (int64_t)p.out_d * p.out_h * p.out_w;
     const int64_t row_off = ((int64_t)n * vox_per + vox) * p.c_out;             // NDHWC element offset of channel 0
+    // bias (+ temb row when the tile lies inside one sample) -> smem while the MMAs run
     const float* cb = nullptr;
-    if (p.chan_bias && valid) {
+    const float* cbrow = nullptr;
+    if (p.chan_bias) {
       const int tt = p.t_dev ? p.t_dev[0] : 0;
-      cb = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? n : 0)) * p.c_out;
+      const bool uniform = p.box_n == 1 || p.chan_bias_rows <= 1;
+      const float* row = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? (uniform ? n0 : n) : 0)) * p.c_out;
+      if (uniform) cbrow = n0 < p.batch ? row : nullptr;
+      else if (valid) cb = row;
+    }
+    const bool has_bs = p.bias != nullptr || cbrow != nullptr;
+    if (has_bs) {
+      stage_bias(p, bias_s, n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 64);
+      epilogue_bar_sync();
     }
     const bool ok = ptx::mbar_wait(tmem_full_bar, 0, p.dbg, 3);
     ptx::tc_fence_after();
@@ -168,7 +179,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
         ptx::tc_wait_ld();
         if (!valid) continue;
-        conv_epilogue16(p, rr, col0, n, vox, vox_per, row_off, cb);
+        conv_epilogue16(p, rr, col0, n, vox, vox_per, row_off, has_bs ? bias_s + c0 : nullptr, cb);
       }
     }
   }
@@ -283,7 +294,7 @@ struct b200dm_conv_plan {
   int nstage;
   double flops;
   bool halo = false;
-  int halo_td = 1, halo_mc = 1, halo_nb = 4;
+  int halo_td = 1, halo_nb = 4, halo_tps = 1;
 };
 
 static int* g_dbg_flag = nullptr;
@@ -379,36 +390,35 @@ static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
   return B200DM_OK;
 }
 
-template <int BLOCK_N, int TD, int NB, int MC>
+constexpr int kHaloNS = 6;
+
+template <int BLOCK_N, int TD, int NB, int TPS>
 static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
-  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, 6, NB, MC>;
+  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, kHaloNS, NB, TPS>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = pl->grid;
-  cfg.blockDim = dim3(halo::kThreads);
-  cfg.dynamicSmemBytes = pl->smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = MC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+  kern<<<pl->grid, halo::kThreads, pl->smem, s>>>(pl->mapA0, pl->mapA1, pl->mapB, pl->p);
+  B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
 
-template <int BLOCK_N, int NB>
+// weight-ring depth / taps per stage by BLOCK_N (smem: 6 slabs x 23 KB + NB x TPS x BLOCK_N x 128 B <= 227 KB)
+static void halo_ring_config(int block_n, int* nb, int* tps) {
+  if (block_n >= 128) { *nb = 4; *tps = 1; }
+  else if (block_n == 64) { *nb = 3; *tps = 3; }
+  else { *nb = 4; *tps = 3; }
+}
+
+template <int BLOCK_N, int NB, int TPS>
 static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
-  if (pl->halo_td == 2) return pl->halo_mc == 2 ? launch_halo<BLOCK_N, 2, NB, 2>(pl, s) : launch_halo<BLOCK_N, 2, NB, 1>(pl, s);
-  return pl->halo_mc == 2 ? launch_halo<BLOCK_N, 1, NB, 2>(pl, s) : launch_halo<BLOCK_N, 1, NB, 1>(pl, s);
+  return pl->halo_td == 2 ? launch_halo<BLOCK_N, 2, NB, TPS>(pl, s) : launch_halo<BLOCK_N, 1, NB, TPS>(pl, s);
 }
 
 static size_t conv_smem_bytes(int block_n, int nstage) {
-  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (2 * nstage + 1) * 8 + 16;
+  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (2 * nstage + 1) * 8 + 16 + block_n * 4;
 }
 
 extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const void* x1, const void* w_packed,
@@ -464,19 +474,25 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       dims[0] = (cuuint64_t)d->c0; dims[1] = (cuuint64_t)d->batch * d->c_out; strides[0] = (cuuint64_t)d->c0 * 2;
     }
     cuuint32_t box[2] = {64, (cuuint32_t)g.block_n};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r;
     if (pl->halo) {
       const long long t1 = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
       pl->halo_td = d->in_d >= 2 && t1 >= b2_num_sms() ? 2 : 1;
-      const long long tl = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + pl->halo_td - 1) / pl->halo_td) * d->batch;
-      pl->halo_mc = (d->use_halo == 1 || d->use_halo == 0) && tl >= 2LL * b2_num_sms() && d->use_halo != 3 ? 2 : 1;
-      if (d->use_halo == 3) pl->halo_mc = 1;
-      box[1] = (cuuint32_t)(g.block_n / pl->halo_mc);
+      halo_ring_config(g.block_n, &pl->halo_nb, &pl->halo_tps);
+      // packed weights [n_pad rows][chunk*27 + tap][64] viewed as 3-D {64, rows, tap-chunks}: one box = TPS consecutive taps
+      cuuint64_t dims3[3] = {64, (cuuint64_t)g.n_pad, (cuuint64_t)(g.ktot / 64)};
+      cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
+      cuuint32_t box3[3] = {64, (cuuint32_t)g.block_n, (cuuint32_t)pl->halo_tps};
+      r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { b200dm_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete pl; return B200DM_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { b200dm_set_error("cuTensorMapEncodeTiled(B) failed: %d (halo %d)", (int)r, (int)pl->halo); delete pl; return B200DM_ERR_CUDA; }
   }
   ConvParams& p = pl->p;
   memset(&p, 0, sizeof(p));
@@ -501,16 +517,15 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   pl->nstage = 4;
   pl->smem = conv_smem_bytes(g.block_n, pl->nstage);
   if (pl->halo) {
-    const int td = pl->halo_td, mc = pl->halo_mc;
+    const int td = pl->halo_td;
     p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td; p.tiles_n = d->batch;
-    long long per = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
-    per = (per + mc - 1) / mc * mc;
+    const long long per = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
     p.halo_td = td; p.halo_tiles_per_ntile = (int)per; p.halo_ntn = ntiles; p.halo_total_tiles = (int)(per * ntiles);
-    int ctas = b2_num_sms() / mc * mc;
+    int ctas = b2_num_sms();
     if (ctas > p.halo_total_tiles) ctas = p.halo_total_tiles;
     pl->grid = dim3((unsigned)ctas, 1, 1);
-    pl->halo_nb = g.block_n >= 128 ? 4 : (g.block_n == 64 ? 6 : 8);
-    pl->smem = 1024 + (size_t)6 * halo::kSlabBytes + (size_t)pl->halo_nb * g.block_n * 128 + (2 * 6 + 2 * pl->halo_nb + 4) * 8 + 16;
+    pl->smem = 1024 + (size_t)kHaloNS * halo::kSlabBytes + (size_t)pl->halo_nb * pl->halo_tps * g.block_n * 128 +
+               (2 * kHaloNS + 2 * pl->halo_nb + 4) * 8 + 16 + 2 * g.block_n * 4;
   }
   // algorithmic FLOPs: 2*k^3*Cin*Cout*B*out_voxels; convT: 2*64*Cin*Cout*B*in_voxels; GEMM: 2*M*N*K
   if (d->mode == B200DM_CONV_PARITY)
@@ -527,10 +542,10 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (pl->halo) {
     switch (pl->g.block_n) {
-      case 16: return dispatch_halo<16, 8>(pl, s);
-      case 32: return dispatch_halo<32, 8>(pl, s);
-      case 64: return dispatch_halo<64, 6>(pl, s);
-      case 128: return dispatch_halo<128, 4>(pl, s);
+      case 16: return dispatch_halo<16, 4, 3>(pl, s);
+      case 32: return dispatch_halo<32, 4, 3>(pl, s);
+      case 64: return dispatch_halo<64, 3, 3>(pl, s);
+      case 128: return dispatch_halo<128, 4, 1>(pl, s);
     }
   }
   switch (pl->g.block_n) {
@@ -544,5 +559,12 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
 }
 
 extern "C" void b200dm_conv_plan_destroy(b200dm_conv_plan* p) { delete p; }
+
+// tuning aid: device buffer of 4 * 2048 int64 receiving CTA 0's per-role timeline ((clock64 << 8) | tag); nullptr = off
+extern "C" int b200dm_conv_plan_set_trace(b200dm_conv_plan* p, void* trace) {
+  B2_CHECK_ARG(p, "conv_plan_set_trace: null plan");
+  p->p.trace = (long long*)trace;
+  return B200DM_OK;
+}
 
 extern "C" double b200dm_conv_plan_flops(const b200dm_conv_plan* p) { return p ? p->flops : 0.0; }

@@ -22,24 +22,37 @@ struct ConvParams {
   const __nv_bfloat16* prelu_alpha;  // (d,h,w,c) bf16, no batch dim
   void* y;
   int* dbg;
+  long long* trace;                  // optional per-role clock64 timeline of CTA 0 (tuning aid), else nullptr
 };
+
+// timeline regions (each kTraceRegion entries): 0 = MMA issuer, 1 = epilogue warp 4, 2 = slab producer, 3 = weight producer
+constexpr int kTraceRegion = 2048;
+__device__ __forceinline__ void trace_ev(const ConvParams& p, int region, int& idx, int tag) {
+  if (p.trace && blockIdx.x == 0 && idx < kTraceRegion - 1) {
+    p.trace[region * kTraceRegion + idx] = (clock64() << 8) | (long long)(tag & 0xff);
+    ++idx;
+  }
+}
 
 __device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
 
 // Epilogue for 16 consecutive accumulator columns of one output voxel (thread = TMEM lane = GEMM row):
 //   + bias[co] + chan_bias[t][n][co]  ->  PReLU(alpha[voxel][co])  ->  act  ->  + residual  ->  post_act  ->  store
+// `bs`: 16 floats in SHARED memory = bias (+ chan_bias when it is uniform over the tile) for these columns, staged once
+// per tile (a per-chunk __ldg round trip made the epilogue as long as the tile's MMA phase); `cb`: per-row global
+// chan_bias pointer, only when a tile spans several samples.
 __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint32_t (&rr)[16], int col0, int n, int64_t vox,
-                                                int64_t vox_per, int64_t row_off, const float* cb) {
+                                                int64_t vox_per, int64_t row_off, const float* bs, const float* cb) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
   const int ncol = (p.c_out - col0) < 16 ? (p.c_out - col0) : 16;
   if (ncol == 16 && !p.transposed_store) {
     // vector path: 16 channels = 32 B bf16 / 64 B fp32 per thread
-    if (p.bias) {
+    if (bs) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
       }
     }
@@ -90,7 +103,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
       if (j < ncol) {
         const int col = col0 + j;
         float x = v[j];
-        if (p.bias) x += __ldg(p.bias + col);
+        if (bs) x += bs[j];
         if (cb) x += __ldg(cb + col);
         if (p.prelu_alpha) { const float a = bf(p.prelu_alpha[vox * p.c_out + col]); x = fmaxf(x, 0.f) + a * fminf(x, 0.f); }
         x = apply_act(x, p.act);
@@ -103,3 +116,18 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
     }
   }
 }
+
+// Stage bias[col] (+ chan_bias row `cbrow` when given) for columns [col_base, col_base + ncols) into shared memory.
+// Called by the 128 epilogue threads (tid 0..127); columns past c_out read as 0.
+__device__ __forceinline__ void stage_bias(const ConvParams& p, float* dst, int col_base, int ncols, const float* cbrow, int tid) {
+  for (int c = tid; c < ncols; c += 128) {
+    const int col = col_base + c;
+    float b = 0.f;
+    if (col < p.c_out) {
+      if (p.bias) b = __ldg(p.bias + col);
+      if (cbrow) b += __ldg(cbrow + col);
+    }
+    dst[c] = b;
+  }
+}
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }

@@ -1,7 +1,7 @@
 // 3^3 stride-1 Conv3D, persistent halo-reuse kernel (the hot conv of the U-Net and decoders).
 //
-// Why: with one TMA tile per (tap, chunk) the 27 taps re-fetch the same voxels 27x and the kernel is bound by
-// L2->SM bandwidth (~7 TB/s), not by the tensor cores.  Here each CTA stages HALO SLABS once and re-uses them:
+// Why: with one TMA tile per (tap, chunk) the 27 taps re-fetch the same voxels 27x.  Here each CTA stages HALO SLABS
+// once and re-uses them:
 //
 //   tile      8 w x 16 h x TD d output voxels (TD accumulators of M=128 in TMEM), BLOCK_N output channels
 //   slab      one input d-plane of the halo: 10 w x 18 h voxels x 64 channels, one 5-D TMA box {64,10,18,1,1} with
@@ -11,12 +11,14 @@
 //             is a pure function of the absolute smem address (verified on B200; base_offset stays 0).
 //   slab ring NS slabs; taps run kd-major so slab 0 is released after kd=0, slab 1 after kd=1, the rest after kd=2,
 //             and the next chunk's / next tile's slabs stream in behind them.
-//   B ring    one [BLOCK_N x 64] weight tile per tap, shared by the TD planes (TD*4 MMAs per barrier round trip).
-//             MC=2: the two CTAs of a cluster each fetch half of every weight tile and TMA-multicast it to both,
-//             halving the weight traffic that otherwise caps N<=64 layers.
+//   B ring    TPS taps (one kh row: kw = 0..2) of [BLOCK_N x 64] weights per stage, one 3-D TMA box {64,BLOCK_N,TPS};
+//             shared by the TD planes -> TPS*TD*4 MMAs per barrier round trip.  Measured on B200 (tools/issue_probe.cu):
+//             an mbarrier wait costs ~110 cycles and a commit ~45 on the single issuing thread, and an M128xN64xK16
+//             MMA only 48, so one tap per round trip is issue-bound; three are not.
 //   TMEM      2 accumulator stages x TD x BLOCK_N columns: the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Warps (256 threads): 0 = slab producer, 1 = weight producer, 2 = TMEM owner + MMA issuer, 3 = idle, 4-7 = epilogue.
+// Every role loop is warp-uniform; a single elected lane (elect.sync) issues TMA / tcgen05 instructions.
 #pragma once
 #include "conv_common.cuh"
 
@@ -26,47 +28,35 @@ constexpr int kThreads = 256;
 constexpr int kSlabBytes = 23 * 1024;      // 180 voxels x 128 B = 23040, rounded up to the 1024-B swizzle period
 constexpr int kSlabTx = 180 * 128;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
-          "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
 }
 
 struct Tile {
   int w0, h0, d0, n, n_tile;
-  bool live;
 };
 
 __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int id) {
   Tile t;
   t.n_tile = id / p.halo_tiles_per_ntile;
   int r = id - t.n_tile * p.halo_tiles_per_ntile;
-  t.live = r < p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
   t.w0 = (r % p.tiles_w) * 8; r /= p.tiles_w;
   t.h0 = (r % p.tiles_h) * 16; r /= p.tiles_h;
   t.d0 = (r % p.tiles_d) * p.halo_td; r /= p.tiles_d;
-  t.n = r;  // >= batch for padding tiles: every access is then out of bounds (zero fill / masked stores)
+  t.n = r;
   return t;
 }
 
-template <int BLOCK_N, int TD, int NS, int NB, int MC>
+template <int BLOCK_N, int TD, int NS, int NB, int TPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const ConvParams p) {
-  constexpr int kBBytes = BLOCK_N * 128;
+  static_assert(TPS == 1 || TPS == 3, "taps per weight stage: 1 or 3");
+  constexpr int kTapBytes = BLOCK_N * 128;
+  constexpr int kBBytes = TPS * kTapBytes;
   constexpr uint32_t kAccCols = TD * BLOCK_N;
   constexpr uint32_t kTmemCols = (2 * kAccCols) < 32 ? 32 : 2 * kAccCols;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two <= 512");
@@ -75,6 +65,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint8_t* b_ring = smem + NS * kSlabBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + NB * kBBytes);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t slab_base = ptx::smem_u32(smem);
@@ -87,16 +78,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + 2 + s); };
 
-  const uint32_t rank = MC > 1 ? cluster_ctarank() : 0u;
-  const int cluster_id = blockIdx.x / MC;
-  const int num_clusters = gridDim.x / MC;
   const int nch = p.nch0 + p.nch1;
-  // tiles of this CTA: (it * num_clusters + cluster_id) * MC + rank, it = 0.. ; halo_total_tiles is a multiple of MC
-  const int tiles_per_round = num_clusters * MC;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), 1); }
-    for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), MC); }
+    for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), 1); ptx::mbar_init(tmem_empty(s), 4); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
@@ -108,129 +95,124 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (MC > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // ===================== slab producer =====================
-    {
-      uint32_t s = 0, ph = 1;
-      bool ok = true;
-      for (int id = cluster_id * MC + (int)rank; id < p.halo_total_tiles && ok; id += tiles_per_round) {
-        const Tile t = decode_tile(p, id);
-        for (int j = 0; j < nch && ok; ++j) {
-          const CUtensorMap* map = j < p.nch0 ? &mapA0 : &mapA1;
-          const int c0 = (j < p.nch0 ? j : j - p.nch0) * 64;
-          for (int pl = 0; pl < TD + 2; ++pl) {
-            ok = ptx::mbar_wait(slab_empty(s), ph, p.dbg, 11);
-            if (!ok) break;
-            if (ptx::elect_one()) {
-              ptx::mbar_expect_tx(slab_full(s), kSlabTx);
-              ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.h0 - 1, t.d0 - 1 + pl, t.n);
-            }
-            __syncwarp();
-            if (++s == NS) { s = 0; ph ^= 1; }
+    uint32_t s = 0, ph = 1;
+    bool ok = true;
+    int ti = 0;
+    for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step) {
+      const Tile t = decode_tile(p, id);
+      for (int j = 0; j < nch && ok; ++j) {
+        const CUtensorMap* map = j < p.nch0 ? &mapA0 : &mapA1;
+        const int c0 = (j < p.nch0 ? j : j - p.nch0) * 64;
+        for (int pl = 0; pl < TD + 2; ++pl) {
+          ok = ptx::mbar_wait(slab_empty(s), ph, p.dbg, 11);
+          if (!ok) break;
+          if (lane == 0) trace_ev(p, 2, ti, 20 + pl);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(slab_full(s), kSlabTx);
+            ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.h0 - 1, t.d0 - 1 + pl, t.n);
           }
+          __syncwarp();
+          if (++s == NS) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== weight producer =====================
-    {
-      uint32_t s = 0, ph = 1;
-      bool ok = true;
-      for (int id = cluster_id * MC + (int)rank; id < p.halo_total_tiles && ok; id += tiles_per_round) {
-        const Tile t = decode_tile(p, id);
-        const int row0 = t.n_tile * BLOCK_N;
-        for (int kb = 0; kb < nch * 27; ++kb) {
-          ok = ptx::mbar_wait(b_empty(s), ph, p.dbg, 12);
-          if (!ok) break;
-          if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(b_full(s), kBBytes);
-            if (MC == 1) {
-              ptx::tma_load_2d(bring_base + s * kBBytes, &mapB, b_full(s), kb * 64, row0);
-            } else {
-              constexpr int kHalf = kBBytes / MC;
-              tma_load_2d_mc(bring_base + s * kBBytes + rank * kHalf, &mapB, b_full(s), kb * 64, row0 + (int)rank * (BLOCK_N / MC),
-                             (uint16_t)((1u << MC) - 1));
-            }
-          }
-          __syncwarp();
-          if (++s == NB) { s = 0; ph ^= 1; }
+    uint32_t s = 0, ph = 1;
+    bool ok = true;
+    for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step) {
+      const Tile t = decode_tile(p, id);
+      const int row0 = t.n_tile * BLOCK_N;
+      for (int kb = 0; kb < nch * 27; kb += TPS) {
+        ok = ptx::mbar_wait(b_empty(s), ph, p.dbg, 12);
+        if (!ok) break;
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(b_full(s), kBBytes);
+          tma_load_3d(bring_base + s * kBBytes, &mapB, b_full(s), 0, row0, kb);
         }
+        __syncwarp();
+        if (++s == NB) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
-    // The whole warp walks the loops (warp-uniform waits); one elected lane issues.  Descriptors are formed by
-    // ADDING 16-byte units to precomputed 64-bit bases (the 14-bit address field cannot carry: smem < 256 KB), so
-    // one MMA costs a handful of integer adds instead of a shift/mask/or chain per operand.
-    {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
-      const uint64_t a_desc0 = ptx::make_smem_desc(slab_base, 16, 1280, ptx::kLayoutSw128);
-      const uint64_t b_desc0 = ptx::make_smem_desc(bring_base, 16, 1024, ptx::kLayoutSw128);
-      uint32_t q = 0, bq = 0, it = 0;
-      bool ok = true;
-      for (int id = cluster_id * MC + (int)rank; id < p.halo_total_tiles && ok; id += tiles_per_round, ++it) {
-        const uint32_t as = it & 1;
-        ok = ptx::mbar_wait(tmem_empty(as), ((it >> 1) & 1) ^ 1, p.dbg, 13);
-        if (!ok) break;
-        ptx::tc_fence_after();
-        const uint32_t acc = tmem_base + as * kAccCols;
-        for (int j = 0; j < nch && ok; ++j, q += TD + 2) {
+    // Descriptors are formed by ADDING 16-byte units to precomputed 64-bit bases (the 14-bit address field cannot
+    // carry: smem < 256 KB); inside a stage every offset is a compile-time immediate.
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
+    const uint64_t a_desc0 = ptx::make_smem_desc(slab_base, 16, 1280, ptx::kLayoutSw128);
+    const uint64_t b_desc0 = ptx::make_smem_desc(bring_base, 16, 1024, ptx::kLayoutSw128);
+    uint32_t q = 0, it = 0, sb = 0, bph = 0;
+    bool ok = true;
+    int ti = 0;
+    for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step, ++it) {
+      const uint32_t as = it & 1;
+      if (lane == 0) trace_ev(p, 0, ti, 1);
+      ok = ptx::mbar_wait(tmem_empty(as), ((it >> 1) & 1) ^ 1, p.dbg, 13);
+      if (!ok) break;
+      if (lane == 0) trace_ev(p, 0, ti, 2);
+      ptx::tc_fence_after();
+      const uint32_t acc = tmem_base + as * kAccCols;
+      for (int j = 0; j < nch && ok; ++j, q += TD + 2) {
 #pragma unroll 1
-          for (int kd = 0; kd < 3 && ok; ++kd) {
-            if (kd == 0) {
-              for (int pl = 0; pl < TD && ok; ++pl) ok = ptx::mbar_wait(slab_full((q + pl) % NS), ((q + pl) / NS) & 1, p.dbg, 14);
-            } else {
-              ok = ptx::mbar_wait(slab_full((q + kd + TD - 1) % NS), ((q + kd + TD - 1) / NS) & 1, p.dbg, 14);
-            }
-            if (!ok) break;
-            uint64_t a_pl[TD];
+        for (int kd = 0; kd < 3 && ok; ++kd) {
+          if (kd == 0) {
+            for (int pl = 0; pl < TD && ok; ++pl) ok = ptx::mbar_wait(slab_full((q + pl) % NS), ((q + pl) / NS) & 1, p.dbg, 14);
+          } else {
+            ok = ptx::mbar_wait(slab_full((q + kd + TD - 1) % NS), ((q + kd + TD - 1) / NS) & 1, p.dbg, 14);
+          }
+          if (!ok) break;
+          if (lane == 0) trace_ev(p, 0, ti, 3);
+          uint64_t a_pl[TD];
 #pragma unroll
-            for (int pl = 0; pl < TD; ++pl) a_pl[pl] = a_desc0 + (uint64_t)(((q + pl + kd) % NS) * (kSlabBytes >> 4));
-            uint32_t sb = bq % NB, bph = (bq / NB) & 1;
+          for (int pl = 0; pl < TD; ++pl) a_pl[pl] = a_desc0 + (uint64_t)(((q + pl + kd) % NS) * (kSlabBytes >> 4));
+          const uint32_t first_kd = (j | kd) != 0 ? 1u : 0u;
 #pragma unroll 1
-            for (int kh = 0; kh < 3 && ok; ++kh) {
-#pragma unroll 1
-              for (int kw = 0; kw < 3; ++kw) {
-                ok = ptx::mbar_wait(b_full(sb), bph, p.dbg, 15);
-                if (!ok) break;
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) {
-                  const uint64_t db = b_desc0 + (uint64_t)(sb * (kBBytes >> 4));
-                  const uint32_t shift16 = (uint32_t)(kh * 10 + kw) * 8u;     // (kh*10+kw) rows of 128 B, in 16-B units
-                  const uint32_t first = (j | kd | kh | kw) != 0 ? 1u : 0u;
+          for (int kh = 0; kh < 3 && ok; ++kh) {
+#pragma unroll
+            for (int g = 0; g < 3 / TPS; ++g) {   // TPS=3: one stage per kh row; TPS=1: three stages
+              ok = ptx::mbar_wait(b_full(sb), bph, p.dbg, 15);
+              if (!ok) break;
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                const uint64_t db0 = b_desc0 + (uint64_t)(sb * (kBBytes >> 4));
+#pragma unroll
+                for (int u = 0; u < TPS; ++u) {
+                  const int kw = TPS == 3 ? u : g;
+                  const uint32_t first = (kw != 0) ? 1u : (first_kd | (kh != 0 ? 1u : 0u));
 #pragma unroll
                   for (int pl = 0; pl < TD; ++pl) {
-                    const uint64_t da = a_pl[pl] + shift16;
+                    const uint64_t da = a_pl[pl] + (uint64_t)(kh * 80 + kw * 8);   // (kh*10+kw) rows of 128 B in 16-B units
+                    const uint64_t db = db0 + (uint64_t)(u * (kTapBytes >> 4));
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da, db, idesc, first);
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 2, db + 2, idesc, 1u);
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 4, db + 4, idesc, 1u);
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 6, db + 6, idesc, 1u);
                   }
-                  if (MC == 1) ptx::tc_commit(b_empty(sb));
-                  else tc_commit_mc(b_empty(sb), (uint16_t)((1u << MC) - 1));
                 }
-                __syncwarp();
-                ++bq;
-                if (++sb == NB) { sb = 0; bph ^= 1; }
+                ptx::tc_commit(b_empty(sb));
               }
+              __syncwarp();
+              if (++sb == NB) { sb = 0; bph ^= 1; }
             }
-            if (!ok) break;
-            // slab pl is last used at kd = min(pl, 2)
-            if (ptx::elect_one()) {
-              if (kd < 2) ptx::tc_commit(slab_empty((q + kd) % NS));
-              else
-                for (int pl = 2; pl < TD + 2; ++pl) ptx::tc_commit(slab_empty((q + pl) % NS));
-            }
-            __syncwarp();
           }
+          if (!ok) break;
+          if (lane == 0) trace_ev(p, 0, ti, 4);
+          // slab pl is last used at kd = min(pl, 2)
+          if (ptx::elect_one()) {
+            if (kd < 2) ptx::tc_commit(slab_empty((q + kd) % NS));
+            else
+              for (int pl = 2; pl < TD + 2; ++pl) ptx::tc_commit(slab_empty((q + pl) % NS));
+          }
+          __syncwarp();
         }
-        if (ptx::elect_one()) ptx::tc_commit(tmem_full(as));
-        __syncwarp();
       }
+      if (ptx::elect_one()) ptx::tc_commit(tmem_full(as));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
@@ -239,42 +221,64 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const int iw = r & 7, ih = r >> 3;
     const int64_t vox_per = (int64_t)p.out_d * p.out_h * p.out_w;
     uint32_t it = 0;
-    for (int id = cluster_id * MC + (int)rank; id < p.halo_total_tiles; id += tiles_per_round, ++it) {
+    int ti = 0;
+    for (int id = first_tile; id < p.halo_total_tiles; id += tile_step, ++it) {
       const Tile t = decode_tile(p, id);
       const uint32_t as = it & 1;
+      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 10);
       const bool ok = ptx::mbar_wait(tmem_full(as), (it >> 1) & 1, p.dbg, 16);
       ptx::tc_fence_after();
       if (!ok) break;
+      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 11);
       const int ow = t.w0 + iw, oh = t.h0 + ih;
-      const float* cb = nullptr;
-      if (p.chan_bias && t.n < p.batch) {
-        const int tt = p.t_dev ? p.t_dev[0] : 0;
-        cb = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? t.n : 0)) * p.c_out;
+      // bias + temb row of this tile's sample -> smem once per tile (double-buffered by accumulator stage)
+      float* bs = bias_s + as * BLOCK_N;
+      const bool has_bs = p.bias != nullptr || p.chan_bias != nullptr;
+      if (has_bs) {
+        const float* cbrow = nullptr;
+        if (p.chan_bias) {
+          const int tt = p.t_dev ? p.t_dev[0] : 0;
+          cbrow = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? t.n : 0)) * p.c_out;
+        }
+        stage_bias(p, bs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128);
+        epilogue_bar_sync();
       }
 #pragma unroll 1
       for (int pl = 0; pl < TD; ++pl) {
         const int od = t.d0 + pl;
-        const bool valid = t.live && ow < p.out_w && oh < p.out_h && od < p.out_d && t.n < p.batch;
+        const bool valid = ow < p.out_w && oh < p.out_h && od < p.out_d;
         const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;
         const int64_t row_off = ((int64_t)t.n * vox_per + vox) * p.c_out;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N;
+        if (BLOCK_N >= 32) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-          const int col0 = t.n_tile * BLOCK_N + c0;
-          if (col0 >= p.c_out) break;
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            const int col0 = t.n_tile * BLOCK_N + c0;
+            if (col0 >= p.c_out) break;
+            uint32_t ra[16], rb[16];
+            ptx::tc_ld_32x32b_x16(taddr + c0, ra);
+            ptx::tc_ld_32x32b_x16(taddr + c0 + 16, rb);
+            ptx::tc_wait_ld();
+            if (valid) {
+              conv_epilogue16(p, ra, col0, t.n, vox, vox_per, row_off, has_bs ? bs + c0 : nullptr, nullptr);
+              if (col0 + 16 < p.c_out) conv_epilogue16(p, rb, col0 + 16, t.n, vox, vox_per, row_off, has_bs ? bs + c0 + 16 : nullptr, nullptr);
+            }
+          }
+        } else {
           uint32_t rr[16];
-          ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N + c0, rr);
+          ptx::tc_ld_32x32b_x16(taddr, rr);
           ptx::tc_wait_ld();
-          if (valid) conv_epilogue16(p, rr, col0, t.n, vox, vox_per, row_off, cb);
+          if (valid) conv_epilogue16(p, rr, t.n_tile * BLOCK_N, t.n, vox, vox_per, row_off, has_bs ? bs : nullptr, nullptr);
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
+      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 12);
       if (lane == 0) ptx::mbar_arrive(tmem_empty(as));
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (MC > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into / arrive on its smem
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);

@@ -202,6 +202,8 @@ int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const voi
 int b200dm_conv_plan_run(b200dm_conv_plan* p, void* stream);
 void b200dm_conv_plan_destroy(b200dm_conv_plan* p);
 double b200dm_conv_plan_flops(const b200dm_conv_plan* p);
+/* tuning aid: device int64[4*2048] receiving CTA 0's per-role timeline ((clock64 << 8) | tag); NULL switches it off */
+int b200dm_conv_plan_set_trace(b200dm_conv_plan* p, void* trace);
 /* device-side watchdog flag: non-zero if any tcgen05/TMA pipeline wait timed out since last reset */
 int b200dm_debug_flag_read_reset(int32_t* flag_out);
 

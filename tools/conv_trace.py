@@ -1,0 +1,40 @@
+"""Per-role clock64 timeline of CTA 0 of the halo conv kernel (tuning aid, GPU box)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import torch
+import b200dm
+from b200dm import ops, _lib
+
+a = [int(v) for v in sys.argv[1:]]
+B, D, H, W, c0, c1, cout = a[:7]
+dev = torch.device("cuda", 0)
+w = torch.randn(3, 3, 3, c0 + c1, cout) * 0.05
+desc = ops.make_conv_desc(0, B, (D, H, W), c0, c1, cout, 3, 1)
+wp = ops.pack_conv_weights(desc, w).to(dev)
+x0 = torch.randn(B, D, H, W, c0, device=dev).bfloat16()
+x1 = torch.randn(B, D, H, W, c1, device=dev).bfloat16() if c1 else None
+y = torch.empty(B, D, H, W, cout, device=dev, dtype=torch.bfloat16)
+plan = ops.ConvPlan(desc, x0, wp, y, x1=x1, bias=torch.zeros(cout, device=dev))
+for _ in range(3):
+    plan.run()
+tr = torch.zeros(4 * 2048, dtype=torch.int64, device=dev)
+_lib.check(_lib.lib().b200dm_conv_plan_set_trace(plan.h, C.c_void_p(tr.data_ptr())))
+plan.run()
+torch.cuda.synchronize()
+t = tr.cpu().view(4, 2048)
+names = {1: "tile:begin", 2: "tile:tmem_empty ok", 3: "kd:slabs ready", 4: "kd:issued", 10: "epi:wait", 11: "epi:tmem_full ok", 12: "epi:done"}
+t0 = min(int(v) >> 8 for v in t[0] if int(v) != 0)
+for region, label in ((0, "MMA"), (1, "EPI"), (2, "SLAB")):
+    prev = None
+    out = []
+    for v in t[region]:
+        v = int(v)
+        if v == 0:
+            break
+        clk, tag = (v >> 8) - t0, v & 0xff
+        out.append(f"{names.get(tag, 'slab'+str(tag-20))}@{clk}" + (f"(+{clk-prev})" if prev is not None else ""))
+        prev = clk
+    print(label, len(out))
+    for i in range(0, min(len(out), 60), 6):
+        print("   ", "  ".join(out[i:i + 6]))
