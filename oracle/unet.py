@@ -111,7 +111,7 @@ class UNet:
     # ---- forward -------------------------------------------------------------------
     def temb(self, P, t):
         """TimeEmbedding -> TimeMLP (dm3d.py:325-326): (B,) int -> (B,4F) fp32."""
-        e = ops.time_embedding(t, 4 * self.F)
+        e = ops.time_embedding(t, 4 * self.F).to(P["time.dense0.kernel"].dtype)  # float64 when the oracle runs in its high-precision mode
         e = ops.swish(ops.dense(e, P["time.dense0.kernel"], P["time.dense0.bias"]))
         return ops.dense(e, P["time.dense1.kernel"], P["time.dense1.bias"])
 
