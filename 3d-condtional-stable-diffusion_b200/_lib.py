@@ -72,6 +72,7 @@ _SIGS = {
     "b200dm_conv_plan_destroy": (None, [C.c_void_p]),
     "b200dm_conv_plan_flops": (C.c_double, [C.c_void_p]),
     "b200dm_conv_plan_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200dm_conv_plan_set_out_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200dm_debug_flag_read_reset": (C.c_int, [C.POINTER(C.c_int32)]),
     "b200dm_program_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "b200dm_program_destroy": (None, [C.c_void_p]),

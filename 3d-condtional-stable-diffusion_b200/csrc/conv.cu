@@ -19,6 +19,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 #include <vector>
@@ -42,7 +43,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * kStageBytes);
   // bars[0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2NSTAGE] tmem_full; then tmem ptr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
-  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [BLOCK_N]
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [2][BLOCK_N]: bias (+temb), output-affine scale
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -163,9 +164,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (uniform) cbrow = n0 < p.batch ? row : nullptr;
       else if (valid) cb = row;
     }
-    const bool has_bs = p.bias != nullptr || cbrow != nullptr;
+    const bool has_bs = p.bias != nullptr || cbrow != nullptr || p.out_scale != nullptr;
+    float* scale_s = bias_s + BLOCK_N;
     if (has_bs) {
-      stage_bias(p, bias_s, n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 64);
+      stage_bias(p, bias_s, scale_s, n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 64);
       epilogue_bar_sync();
     }
     const bool ok = ptx::mbar_wait(tmem_full_bar, 0, p.dbg, 3);
@@ -179,7 +181,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
         ptx::tc_wait_ld();
         if (!valid) continue;
-        conv_epilogue16(p, rr, col0, n, vox, vox_per, row_off, has_bs ? bias_s + c0 : nullptr, cb);
+        conv_epilogue16(p, rr, col0, n, vox, vox_per, row_off, has_bs ? bias_s + c0 : nullptr, cb,
+                        p.out_scale ? scale_s + c0 : nullptr);
       }
     }
   }
@@ -418,7 +421,7 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 }
 
 static size_t conv_smem_bytes(int block_n, int nstage) {
-  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (2 * nstage + 1) * 8 + 16 + block_n * 4;
+  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (2 * nstage + 1) * 8 + 16 + 2 * block_n * 4;
 }
 
 extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const void* x1, const void* w_packed,
@@ -514,7 +517,11 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   if (mtiles > 0x7fffffffLL) { delete pl; b200dm_set_error("conv_plan_create: too many tiles"); return B200DM_ERR_INVALID; }
   const int ntiles = d->mode == B200DM_CONV_BATCHED_GEMM ? (d->c_out + g.block_n - 1) / g.block_n : g.n_pad / g.block_n;
   pl->grid = dim3((unsigned)mtiles, (unsigned)ntiles, d->mode == B200DM_CONV_PARITY ? 8 : 1);
+  // pipeline depth: enough bytes in flight to cover the L2->smem latency (B200DM_IGEMM_STAGES=4 restores the shallow ring)
+  // 4 stages; measured on B200: a deeper ring (B200DM_IGEMM_STAGES=8: 6 stages at BLOCK_N=128, 8 below) does not help
+  // at BLOCK_N=128 (not latency-bound) and hurts below 128, where 4 stages let two CTAs share an SM
   pl->nstage = 4;
+  if (const char* e = getenv("B200DM_IGEMM_STAGES")) { if (atoi(e) == 8) pl->nstage = g.block_n >= 128 ? 6 : 8; }
   pl->smem = conv_smem_bytes(g.block_n, pl->nstage);
   if (pl->halo) {
     const int td = pl->halo_td;
@@ -525,7 +532,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     if (ctas > p.halo_total_tiles) ctas = p.halo_total_tiles;
     pl->grid = dim3((unsigned)ctas, 1, 1);
     pl->smem = 1024 + (size_t)kHaloNS * halo::kSlabBytes + (size_t)pl->halo_nb * pl->halo_tps * g.block_n * 128 +
-               (2 * kHaloNS + 2 * pl->halo_nb + 4) * 8 + 16 + 2 * g.block_n * 4;
+               (2 * kHaloNS + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * g.block_n * 4;
   }
   // algorithmic FLOPs: 2*k^3*Cin*Cout*B*out_voxels; convT: 2*64*Cin*Cout*B*in_voxels; GEMM: 2*M*N*K
   if (d->mode == B200DM_CONV_PARITY)
@@ -548,11 +555,20 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
       case 128: return dispatch_halo<128, 4, 1>(pl, s);
     }
   }
-  switch (pl->g.block_n) {
-    case 16: return launch_conv<16, 4>(pl, s);
-    case 32: return launch_conv<32, 4>(pl, s);
-    case 64: return launch_conv<64, 4>(pl, s);
-    case 128: return launch_conv<128, 4>(pl, s);
+  if (pl->nstage == 4) {
+    switch (pl->g.block_n) {
+      case 16: return launch_conv<16, 4>(pl, s);
+      case 32: return launch_conv<32, 4>(pl, s);
+      case 64: return launch_conv<64, 4>(pl, s);
+      case 128: return launch_conv<128, 4>(pl, s);
+    }
+  } else {
+    switch (pl->g.block_n) {
+      case 16: return launch_conv<16, 8>(pl, s);
+      case 32: return launch_conv<32, 8>(pl, s);
+      case 64: return launch_conv<64, 8>(pl, s);
+      case 128: return launch_conv<128, 6>(pl, s);
+    }
   }
   b200dm_set_error("conv_plan_run: unsupported BLOCK_N %d", pl->g.block_n);
   return B200DM_ERR_UNSUPPORTED;
@@ -568,3 +584,12 @@ extern "C" int b200dm_conv_plan_set_trace(b200dm_conv_plan* p, void* trace) {
 }
 
 extern "C" double b200dm_conv_plan_flops(const b200dm_conv_plan* p) { return p ? p->flops : 0.0; }
+
+extern "C" int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float* scale, const float* shift) {
+  B2_CHECK_ARG(p, "conv_plan_set_out_affine: null plan");
+  B2_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_plan_set_out_affine: give both scale and shift, or neither");
+  B2_CHECK_ARG(!scale || !p->p.prelu_alpha, "conv_plan_set_out_affine: not combinable with PReLU");
+  p->p.out_scale = scale;
+  p->p.out_shift = shift;
+  return B200DM_OK;
+}

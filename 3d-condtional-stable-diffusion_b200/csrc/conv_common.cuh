@@ -16,6 +16,8 @@ struct ConvParams {
   int chan_bias_rows;
   int halo_td, halo_tiles_per_ntile, halo_ntn, halo_total_tiles;   // halo kernel only
   const float* bias;
+  const float* out_scale;            // optional per-channel affine applied after the bias adds (a folded BatchNorm of the
+  const float* out_shift;            // CONSUMER: y = act(scale * (acc + bias + temb) + shift)), fp32[c_out]
   const float* chan_bias;
   const int* t_dev;
   const __nv_bfloat16* residual;
@@ -37,29 +39,39 @@ __device__ __forceinline__ void trace_ev(const ConvParams& p, int region, int& i
 __device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
 
 // Epilogue for 16 consecutive accumulator columns of one output voxel (thread = TMEM lane = GEMM row):
-//   + bias[co] + chan_bias[t][n][co]  ->  PReLU(alpha[voxel][co])  ->  act  ->  + residual  ->  post_act  ->  store
+//   + bias[co] + chan_bias[t][n][co]  ->  * out_scale[co] + out_shift[co]  ->  PReLU(alpha[voxel][co])  ->  act  ->
+//   + residual  ->  post_act  ->  store
 // `bs`: 16 floats in SHARED memory = bias (+ chan_bias when it is uniform over the tile) for these columns, staged once
-// per tile (a per-chunk __ldg round trip made the epilogue as long as the tile's MMA phase); `cb`: per-row global
-// chan_bias pointer, only when a tile spans several samples.
+// per tile (a per-chunk __ldg round trip made the epilogue as long as the tile's MMA phase); with an output affine
+// `sc` holds the 16 scales and `bs` holds scale * bias + shift.  `cb`: per-row global chan_bias pointer, only when a
+// tile spans several samples.
 __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint32_t (&rr)[16], int col0, int n, int64_t vox,
-                                                int64_t vox_per, int64_t row_off, const float* bs, const float* cb) {
+                                                int64_t vox_per, int64_t row_off, const float* bs, const float* cb,
+                                                const float* sc = nullptr) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
   const int ncol = (p.c_out - col0) < 16 ? (p.c_out - col0) : 16;
   if (ncol == 16 && !p.transposed_store) {
     // vector path: 16 channels = 32 B bf16 / 64 B fp32 per thread
-    if (bs) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-      }
-    }
     if (cb) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb + col0 + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    }
+    if (sc) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+        v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+      }
+    }
+    if (bs) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
       }
     }
@@ -103,8 +115,9 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
       if (j < ncol) {
         const int col = col0 + j;
         float x = v[j];
-        if (bs) x += bs[j];
         if (cb) x += __ldg(cb + col);
+        if (sc) x *= sc[j];
+        if (bs) x += bs[j];
         if (p.prelu_alpha) { const float a = bf(p.prelu_alpha[vox * p.c_out + col]); x = fmaxf(x, 0.f) + a * fminf(x, 0.f); }
         x = apply_act(x, p.act);
         if (p.residual) x += bf(p.residual[row_off + col]);
@@ -118,16 +131,20 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
 }
 
 // Stage bias[col] (+ chan_bias row `cbrow` when given) for columns [col_base, col_base + ncols) into shared memory.
+// With an output affine, dst_scale[c] = scale and dst[c] = scale * bias + shift.
 // Called by the 128 epilogue threads (tid 0..127); columns past c_out read as 0.
-__device__ __forceinline__ void stage_bias(const ConvParams& p, float* dst, int col_base, int ncols, const float* cbrow, int tid) {
+__device__ __forceinline__ void stage_bias(const ConvParams& p, float* dst, float* dst_scale, int col_base, int ncols,
+                                           const float* cbrow, int tid) {
   for (int c = tid; c < ncols; c += 128) {
     const int col = col_base + c;
-    float b = 0.f;
+    float b = 0.f, sc = 1.f;
     if (col < p.c_out) {
       if (p.bias) b = __ldg(p.bias + col);
       if (cbrow) b += __ldg(cbrow + col);
+      if (p.out_scale) { sc = __ldg(p.out_scale + col); b = fmaf(sc, b, __ldg(p.out_shift + col)); }
     }
     dst[c] = b;
+    if (p.out_scale) dst_scale[c] = sc;
   }
 }
 __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }

@@ -65,7 +65,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint8_t* b_ring = smem + NS * kSlabBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + NB * kBBytes);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4);
-  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [2][BLOCK_N]
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [2 acc stages][bias | scale][BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t slab_base = ptx::smem_u32(smem);
@@ -232,15 +232,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 11);
       const int ow = t.w0 + iw, oh = t.h0 + ih;
       // bias + temb row of this tile's sample -> smem once per tile (double-buffered by accumulator stage)
-      float* bs = bias_s + as * BLOCK_N;
-      const bool has_bs = p.bias != nullptr || p.chan_bias != nullptr;
+      float* bs = bias_s + as * 2 * BLOCK_N;
+      float* scs = bs + BLOCK_N;
+      const bool has_bs = p.bias != nullptr || p.chan_bias != nullptr || p.out_scale != nullptr;
+      const bool has_sc = p.out_scale != nullptr;
       if (has_bs) {
         const float* cbrow = nullptr;
         if (p.chan_bias) {
           const int tt = p.t_dev ? p.t_dev[0] : 0;
           cbrow = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? t.n : 0)) * p.c_out;
         }
-        stage_bias(p, bs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128);
+        stage_bias(p, bs, scs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128);
         epilogue_bar_sync();
       }
 #pragma unroll 1
@@ -260,15 +262,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             ptx::tc_ld_32x32b_x16(taddr + c0 + 16, rb);
             ptx::tc_wait_ld();
             if (valid) {
-              conv_epilogue16(p, ra, col0, t.n, vox, vox_per, row_off, has_bs ? bs + c0 : nullptr, nullptr);
-              if (col0 + 16 < p.c_out) conv_epilogue16(p, rb, col0 + 16, t.n, vox, vox_per, row_off, has_bs ? bs + c0 + 16 : nullptr, nullptr);
+              conv_epilogue16(p, ra, col0, t.n, vox, vox_per, row_off, has_bs ? bs + c0 : nullptr, nullptr, has_sc ? scs + c0 : nullptr);
+              if (col0 + 16 < p.c_out)
+                conv_epilogue16(p, rb, col0 + 16, t.n, vox, vox_per, row_off, has_bs ? bs + c0 + 16 : nullptr, nullptr,
+                                has_sc ? scs + c0 + 16 : nullptr);
             }
           }
         } else {
           uint32_t rr[16];
           ptx::tc_ld_32x32b_x16(taddr, rr);
           ptx::tc_wait_ld();
-          if (valid) conv_epilogue16(p, rr, t.n_tile * BLOCK_N, t.n, vox, vox_per, row_off, has_bs ? bs : nullptr, nullptr);
+          if (valid) conv_epilogue16(p, rr, t.n_tile * BLOCK_N, t.n, vox, vox_per, row_off, has_bs ? bs : nullptr, nullptr, has_sc ? scs : nullptr);
         }
       }
       ptx::tc_fence_before();

@@ -206,9 +206,10 @@ def pack_conv_weights(desc: L.ConvDesc, keras_kernel: torch.Tensor, transposed=F
 class ConvPlan:
     """One conv / GEMM invocation with fixed buffers (owns the TMA descriptors)."""
 
-    def __init__(self, desc, x0, w_packed, y, x1=None, bias=None, chan_bias=None, t_dev=None, residual=None, prelu_alpha=None):
+    def __init__(self, desc, x0, w_packed, y, x1=None, bias=None, chan_bias=None, t_dev=None, residual=None, prelu_alpha=None,
+                 out_affine=None):
         _dev()
-        self.keep = (x0, x1, w_packed, bias, chan_bias, t_dev, residual, prelu_alpha, y)  # keep buffers alive
+        self.keep = (x0, x1, w_packed, bias, chan_bias, t_dev, residual, prelu_alpha, y) + tuple(out_affine or ())  # keep buffers alive
         self.desc = desc
         h = C.c_void_p()
         check(lib().b200dm_conv_plan_create(C.byref(desc), ptr(x0), ptr(x1), ptr(w_packed), ptr(bias), ptr(chan_bias),
@@ -216,6 +217,8 @@ class ConvPlan:
         self.h = h
         self.y = y
         self.owned = True
+        if out_affine is not None:  # (scale, shift) of the consumer's folded BatchNorm
+            check(lib().b200dm_conv_plan_set_out_affine(self.h, ptr(out_affine[0]), ptr(out_affine[1])))
 
     @property
     def flops(self):
@@ -244,7 +247,7 @@ def conv_out_shape(mode, in_dhw, stride):
 
 
 def conv3d(x0, keras_kernel, bias=None, x1=None, mode=L.CONV_DIRECT, stride=1, act=None, post_act=None, residual=None,
-           chan_bias=None, prelu_alpha=None, y_dtype=torch.bfloat16, transposed=False):
+           chan_bias=None, prelu_alpha=None, y_dtype=torch.bfloat16, transposed=False, out_affine=None, use_halo=False):
     """Convenience one-shot conv (tests): packs, plans, runs.  x bf16 NDHWC; returns y NDHWC."""
     dev = _dev()
     B, D, H, W, c0 = x0.shape
@@ -252,11 +255,12 @@ def conv3d(x0, keras_kernel, bias=None, x1=None, mode=L.CONV_DIRECT, stride=1, a
     k = keras_kernel.shape[0]
     c_out = keras_kernel.shape[3] if transposed else keras_kernel.shape[4]
     desc = make_conv_desc(mode, B, (D, H, W), c0, c1, c_out, k, stride, act, post_act, y_dtype,
-                          chan_bias_rows=B if chan_bias is not None else 0)
+                          chan_bias_rows=B if chan_bias is not None else 0, use_halo=use_halo)
     wp = pack_conv_weights(desc, keras_kernel, transposed).to(dev)
     od, oh, ow = conv_out_shape(mode, (D, H, W), stride)
     y = torch.empty(B, od, oh, ow, c_out, dtype=y_dtype, device=dev)
-    plan = ConvPlan(desc, x0, wp, y, x1=x1, bias=bias, chan_bias=chan_bias, residual=residual, prelu_alpha=prelu_alpha)
+    plan = ConvPlan(desc, x0, wp, y, x1=x1, bias=bias, chan_bias=chan_bias, residual=residual, prelu_alpha=prelu_alpha,
+                    out_affine=out_affine)
     plan.run()
     return y
 

@@ -164,7 +164,7 @@ class UNet:
         self.temb_table = temb
 
         def conv(x0, kname, cout, y=None, x1=None, k=3, stride=1, mode=L.CONV_DIRECT, act=None, bias=True, chan_bias=None,
-                 residual=None, y_dtype=torch.bfloat16, transposed_store=False, dense=False, note=""):
+                 residual=None, y_dtype=torch.bfloat16, transposed_store=False, dense=False, out_affine=None, note=""):
             Bx, D, H, Wd, c0 = x0.shape
             c1 = x1.shape[-1] if x1 is not None else 0
             desc = ops.make_conv_desc(mode, Bx, (D, H, Wd), c0, c1, cout, k, stride, act, None, y_dtype,
@@ -177,7 +177,8 @@ class UNet:
                 od, oh, ow = ops.conv_out_shape(mode, (D, H, Wd), stride)
                 y = pr.buf((Bx, cout, od * oh * ow) if transposed_store else (Bx, od, oh, ow, cout), y_dtype)
             return pr.conv(desc, x0, wp, y, x1=x1, bias=g(f"{kname}.bias") if bias else None, chan_bias=chan_bias,
-                           t_dev=self.t_dev if chan_bias is not None else None, residual=residual, note=note or kname)
+                           t_dev=self.t_dev if chan_bias is not None else None, residual=residual, out_affine=out_affine,
+                           note=note or kname)
 
         def bgemm(a, b, y_dtype, residual=None, note=""):
             Bx, M, K = a.shape
@@ -204,8 +205,10 @@ class UNet:
                 res = pr.norm_act(x, one, zero, pr.buf((*x.shape[:-1], cin)), x1=skip, note=f"{n}.concat")
             table = ops.dense_f32(temb, g(f"{n}.temb.kernel"), g(f"{n}.temb.bias"), act_in="silu")  # (T, w)
             h = bn_act(x, f"{n}.norm1", "silu", x1=skip)
-            h = conv(h, f"{n}.conv1", w, chan_bias=pr.hold(table))
-            h = bn_act(h, f"{n}.norm2", "silu")
+            # conv1 + temb -> BN(norm2) -> swish (dm3d.py:237-244): conv1's output has no other reader, so norm2 and the
+            # activation run in conv1's epilogue on the fp32 accumulator (one HBM pass and one bf16 rounding fewer)
+            sc2, sh2 = ops.bn_fold(g(f"{n}.norm2.gamma"), g(f"{n}.norm2.beta"), g(f"{n}.norm2.mean"), g(f"{n}.norm2.var"), 1e-3)
+            h = conv(h, f"{n}.conv1", w, chan_bias=pr.hold(table), out_affine=(sc2, sh2), act="silu", note=f"{n}.conv1+norm2")
             return conv(h, f"{n}.conv2", w, residual=res)
 
         def attention_core(q, k, vT, scale, residual, note):

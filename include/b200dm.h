@@ -202,6 +202,11 @@ int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const voi
 int b200dm_conv_plan_run(b200dm_conv_plan* p, void* stream);
 void b200dm_conv_plan_destroy(b200dm_conv_plan* p);
 double b200dm_conv_plan_flops(const b200dm_conv_plan* p);
+/* Fuse the CONSUMER's BatchNormalization (inference, folded by b200dm_bn_fold) into this conv's epilogue:
+ * y = act(scale[co] * (acc + bias + chan_bias) + shift[co]), scale/shift device fp32[c_out].  Used for
+ * ResidualBlock conv1 -> BN -> swish (dm3d.py:237-244) when the un-normalised tensor has no other reader.
+ * NULL, NULL switches it off. */
+int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float* scale, const float* shift);
 /* tuning aid: device int64[4*2048] receiving CTA 0's per-role timeline ((clock64 << 8) | tag); NULL switches it off */
 int b200dm_conv_plan_set_trace(b200dm_conv_plan* p, void* trace);
 /* device-side watchdog flag: non-zero if any tcgen05/TMA pipeline wait timed out since last reset */

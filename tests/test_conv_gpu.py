@@ -226,3 +226,23 @@ def test_conv3_halo_kernel(cuda, B, dhw, c0, c1, cout, mode):
     if not big:
         ref = O.conv3d(xin, w, b) + res
         _close(ys[mode], ref, what=f"halo conv B{B} {dhw} {c0}+{c1}->{cout}")
+
+
+@pytest.mark.parametrize("B,S,cin,cout,halo", [(2, 8, 64, 128, -1), (1, 16, 64, 64, 0), (2, 16, 32, 96, 0), (4, 4, 64, 64, -1)])
+def test_conv_out_affine_fuses_consumer_batchnorm(cuda, B, S, cin, cout, halo):
+    """ResidualBlock conv1 -> +temb -> BN(norm2) -> swish (dm3d.py:237-244) in ONE epilogue: the folded BN of the
+    consumer is applied to the fp32 accumulator.  (4,4,...) covers tiles that span several samples (per-row temb)."""
+    from b200dm import ops
+    g = torch.Generator().manual_seed(9)
+    x = _rand((B, S, S, S, cin), 1)
+    w = _rand((3, 3, 3, cin, cout), 2, 1.0 / np.sqrt(27 * cin))
+    b = torch.randn(cout, generator=g)
+    temb = torch.randn(B, cout, generator=g)
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    mean, var = torch.randn(cout, generator=g) * 0.1, torch.rand(cout, generator=g) + 0.5
+    ref = O.swish(O.batchnorm_infer(O.conv3d(x, w, b) + temb[:, None, None, None, :], gamma, beta, mean, var))
+    sc, sh = ops.bn_fold(gamma.to(cuda), beta.to(cuda), mean.to(cuda), var.to(cuda), 1e-3)
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, bias=b.to(cuda), chan_bias=temb.to(cuda), act="silu", out_affine=(sc, sh),
+                   y_dtype=torch.float32, use_halo=halo)
+    _check_flag()
+    _close(y, ref, what=f"conv3 + temb + BN + swish fused, B{B} S{S} {cin}->{cout}")
