@@ -41,6 +41,11 @@ class VqDesc(C.Structure):
     _fields_ = [("n", C.c_int64), ("d", C.c_int32), ("k", C.c_int32), ("x_dtype", C.c_int32), ("q_dtype", C.c_int32)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("lq", C.c_int32), ("lk", C.c_int32), ("d", C.c_int32), ("scale", C.c_float),
+                ("reserved", C.c_int32 * 3)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("mode", C.c_int32), ("batch", C.c_int32), ("in_d", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
                 ("c0", C.c_int32), ("c1", C.c_int32), ("c_out", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
@@ -73,6 +78,11 @@ _SIGS = {
     "b200dm_conv_plan_flops": (C.c_double, [C.c_void_p]),
     "b200dm_conv_plan_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200dm_conv_plan_set_out_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200dm_attention_plan_create": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 5 + [C.POINTER(C.c_void_p)]),
+    "b200dm_attention_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200dm_attention_plan_destroy": (None, [C.c_void_p]),
+    "b200dm_attention_plan_flops": (C.c_double, [C.c_void_p]),
+    "b200dm_program_add_attention": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200dm_debug_flag_read_reset": (C.c_int, [C.POINTER(C.c_int32)]),
     "b200dm_program_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "b200dm_program_destroy": (None, [C.c_void_p]),

@@ -1,6 +1,7 @@
 // C-ABI plumbing: version, thread-local error text, device info.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -10,6 +11,12 @@ void b200dm_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool b200dm_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B200DM_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
 }
 
 extern "C" int b200dm_version(void) { return B200DM_VERSION; }

@@ -37,6 +37,27 @@ static inline int b2_num_sms() {
   return sms;
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// Every per-step kernel calls pdl_launch_dependents() first (the next kernel of the stream / graph may start its
+// prologue as soon as all CTAs of this one are resident) and pdl_wait() before its first access to global memory that
+// a predecessor may have written (or may still read): barrier init, TMEM allocation, tensor-map prefetch and launch
+// latency of kernel k+1 overlap the tail of kernel k.  B200DM_PDL=0 launches without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool b200dm_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b2_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- small device helpers ------------------------------------------------------------------
 struct __align__(16) bf16x8 {
   __nv_bfloat162 v[4];

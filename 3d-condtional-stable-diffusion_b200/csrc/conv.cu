@@ -31,7 +31,7 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
-template <int BLOCK_N, int NSTAGE>
+template <int BLOCK_N, int NSTAGE, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const ConvParams p) {
@@ -53,6 +53,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * NSTAGE);
 
   // tile decode
+  pdl_launch_dependents();
   int bx = blockIdx.x;
   const int tw = bx % p.tiles_w; bx /= p.tiles_w;
   const int th = bx % p.tiles_h; bx /= p.tiles_h;
@@ -64,8 +65,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int pw = parity & 1, ph = (parity >> 1) & 1, pd = (parity >> 2) & 1;
   const int nkb = (p.nch0 + p.nch1) * p.ntaps;
 
+  // Cluster of cl_m x cl_n CTAs (x = m-tiles, y = n-tiles): the cl_n CTAs of one m-tile each fetch 1/cl_n of the A tile and
+  // TMA-multicast it to all of them; the cl_m CTAs of one n-tile do the same with the B tile.  A stage may be refilled
+  // only when EVERY CTA of the cluster has consumed it (their tcgen05.commit multicasts onto all empty barriers).
+  // Why: one SM's TMA path sustains ~35 B/cycle (measured), a 128x128 tile wants 128 B/cycle of operands.
+  const uint32_t cl_m = CLUSTER ? (uint32_t)p.cl_m : 1u, cl_n = CLUSTER ? (uint32_t)p.cl_n : 1u;
+  const uint32_t rank_m = CLUSTER ? ptx::cluster_ctaid_x() : 0u, rank_n = CLUSTER ? ptx::cluster_ctaid_y() : 0u;
+
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), cl_m * cl_n); }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
@@ -77,8 +85,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER) ptx::cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -100,11 +110,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const uint32_t a_dst = smem_base + s * kStageBytes;
           const uint32_t b_dst = a_dst + kABytes;
           ptx::mbar_expect_tx(full_bar(s), kStageBytes);
-          if (chunk < p.nch0)
-            ptx::tma_load_5d(a_dst, &mapA0, full_bar(s), chunk * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
-          else
-            ptx::tma_load_5d(a_dst, &mapA1, full_bar(s), (chunk - p.nch0) * 64, w0 * p.stride + ow, h0 * p.stride + oh, d0 * p.stride + od, n0);
-          ptx::tma_load_2d(b_dst, &mapB, full_bar(s), kb * 64, b_row);
+          const CUtensorMap* mapA = chunk < p.nch0 ? &mapA0 : &mapA1;
+          const int cch = (chunk < p.nch0 ? chunk : chunk - p.nch0) * 64;
+          int cw = w0 * p.stride + ow, chh = h0 * p.stride + oh, cd = d0 * p.stride + od, cn = n0;
+          if (CLUSTER && cl_n > 1) {
+            const int off = (int)rank_n * p.a_split_ext;
+            if (p.a_split_dim == 1) cw += off; else if (p.a_split_dim == 2) chh += off; else if (p.a_split_dim == 3) cd += off; else cn += off;
+            uint16_t mask = 0;
+            for (uint32_t j = 0; j < cl_n; ++j) mask |= (uint16_t)(1u << (rank_m + j * cl_m));
+            ptx::tma_load_5d_mc(a_dst + rank_n * (kABytes / cl_n), mapA, full_bar(s), cch, cw, chh, cd, cn, mask);
+          } else {
+            ptx::tma_load_5d(a_dst, mapA, full_bar(s), cch, cw, chh, cd, cn);
+          }
+          if (CLUSTER && cl_m > 1) {
+            uint16_t mask = 0;
+            for (uint32_t i = 0; i < cl_m; ++i) mask |= (uint16_t)(1u << (i + rank_n * cl_m));
+            ptx::tma_load_2d_mc(b_dst + rank_m * (kBBytes / cl_m), &mapB, full_bar(s), kb * 64, b_row + (int)rank_m * (BLOCK_N / (int)cl_m), mask);
+          } else {
+            ptx::tma_load_2d(b_dst, &mapB, full_bar(s), kb * 64, b_row);
+          }
         }
         __syncwarp();
         if (++s == NSTAGE) { s = 0; phase ^= 1; }
@@ -130,7 +154,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           ptx::tc_mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
           ptx::tc_mma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
           ptx::tc_mma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
-          ptx::tc_commit(empty_bar(s));
+          if (CLUSTER) ptx::tc_commit_mc(empty_bar(s), (uint16_t)((1u << (cl_m * cl_n)) - 1u));
+          else ptx::tc_commit(empty_bar(s));
         }
         __syncwarp();
         if (++s == NSTAGE) { s = 0; phase ^= 1; }
@@ -192,6 +217,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (CLUSTER) ptx::cluster_sync_all();   // no CTA exits while a peer may still multicast into / arrive on its smem
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -309,6 +335,8 @@ static int ensure_dbg_flag() {
   return B200DM_OK;
 }
 
+int* b200dm_dbg_flag_ptr() { return ensure_dbg_flag() == B200DM_OK ? g_dbg_flag : nullptr; }
+
 extern "C" int b200dm_debug_flag_read_reset(int32_t* flag_out) {
   B2_CHECK_ARG(flag_out, "debug_flag: null");
   *flag_out = 0;
@@ -382,14 +410,31 @@ extern "C" int b200dm_conv_pack_weights(const b200dm_conv_desc* d, const float* 
 
 template <int BLOCK_N, int NSTAGE>
 static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
-  auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE>;
+  if (pl->p.cl_m * pl->p.cl_n > 1) {
+    auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = pl->grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl->p.cl_m; at[0].val.clusterDim.y = pl->p.cl_n; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+    return B200DM_OK;
+  }
+  auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, false>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     attr_set = true;
   }
-  kern<<<pl->grid, kThreads, pl->smem, s>>>(pl->mapA0, pl->mapA1, pl->mapB, pl->p);
-  B2_CHECK_LAUNCH();
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
   return B200DM_OK;
 }
 
@@ -403,8 +448,7 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     attr_set = true;
   }
-  kern<<<pl->grid, halo::kThreads, pl->smem, s>>>(pl->mapA0, pl->mapA1, pl->mapB, pl->p);
-  B2_CHECK_LAUNCH();
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
   return B200DM_OK;
 }
 
@@ -450,12 +494,37 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // halo-reuse kernel: 3^3 stride-1 convs on volumes that fill its 8w x 16h tile (use_halo = -1 forces it off)
   pl->halo = d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w >= 8 && d->in_h >= 16 &&
              d->reserved[1] == 0 && d->use_halo >= 0;
+  // igemm cluster (see the kernel): cl_n n-tiles share A, cl_m m-tiles share B; B200DM_CLUSTER="m,n" switches it on.
+  int cl_m = 1, cl_n = 1, a_split_dim = 0, a_split_ext = 0;
+  if (!pl->halo && st == 1) {
+    const long long mt = (long long)((g.m_w + g.box_w - 1) / g.box_w) * ((g.m_h + g.box_h - 1) / g.box_h) *
+                         ((g.m_d + g.box_d - 1) / g.box_d) * ((d->batch + g.box_n - 1) / g.box_n);
+    const int nt = d->mode == B200DM_CONV_BATCHED_GEMM ? (d->c_out + g.block_n - 1) / g.block_n : g.n_pad / g.block_n;
+    // Default OFF: measured on B200 (8^3 256->256 conv, 47 us unclustered) 2x1 68 us, 1x2 72 us, 2x2 91 us, 4x2 97 us --
+    // the operand stream is capped by what ONE SM can take from L2 (~40 B/clk), which multicast does not raise at
+    // cluster sizes <= 4, and the cluster-wide stage hand-shake adds latency.  Kept for experiments and tests.
+    int want_m = 1, want_n = 1;
+    if (const char* e = getenv("B200DM_CLUSTER")) { if (sscanf(e, "%d,%d", &want_m, &want_n) != 2) { want_m = 1; want_n = 1; } }
+    // B is shared by m-tiles of the same sample only in GEMM mode (x = tile within sample fastest)
+    const long long m_share = d->mode == B200DM_CONV_BATCHED_GEMM ? (g.m_w + g.box_w - 1) / g.box_w : mt;
+    for (cl_m = want_m; cl_m > 1 && (m_share % cl_m != 0 || mt % cl_m != 0 || g.block_n / cl_m < 8); cl_m >>= 1) {}
+    for (cl_n = want_n; cl_n > 1 && nt % cl_n != 0; cl_n >>= 1) {}
+    if (cl_m < 1) cl_m = 1;
+    if (cl_n < 1) cl_n = 1;
+    if (cl_n > 1) {  // split the outermost non-unit box dim of the A tile between the sharers
+      int ext[5] = {0, g.box_w, g.box_h, g.box_d, g.box_n};
+      for (int dim = 4; dim >= 1; --dim)
+        if (ext[dim] > 1) { if (ext[dim] % cl_n == 0) { a_split_dim = dim; a_split_ext = ext[dim] / cl_n; } break; }
+      if (a_split_dim == 0) cl_n = 1;
+    }
+  }
   auto encodeA = [&](CUtensorMap* m, const void* ptr, int C) -> int {
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->in_d, (cuuint64_t)d->batch};
     cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)d->in_w * C * 2, (cuuint64_t)d->in_h * d->in_w * C * 2,
                              (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)(g.box_w * st), (cuuint32_t)(g.box_h * st), (cuuint32_t)(g.box_d * st), (cuuint32_t)g.box_n};
     if (pl->halo) { box[1] = 10; box[2] = 18; box[3] = 1; box[4] = 1; }   // one halo d-plane slab
+    else if (cl_n > 1) box[a_split_dim] = (cuuint32_t)a_split_ext;          // this CTA's share of the multicast A tile
 
     cuuint32_t es[5] = {1, (cuuint32_t)st, (cuuint32_t)st, (cuuint32_t)st, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
@@ -476,7 +545,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       // (masked by the epilogue's col < c_out), K beyond c0 is zero-filled by TMA.
       dims[0] = (cuuint64_t)d->c0; dims[1] = (cuuint64_t)d->batch * d->c_out; strides[0] = (cuuint64_t)d->c0 * 2;
     }
-    cuuint32_t box[2] = {64, (cuuint32_t)g.block_n};
+    cuuint32_t box[2] = {64, (cuuint32_t)(g.block_n / cl_m)};   // this CTA's share of the multicast B tile
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r;
     if (pl->halo) {
@@ -513,6 +582,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   p.bias = bias; p.chan_bias = chan_bias; p.t_dev = t_dev;
   p.residual = (const __nv_bfloat16*)residual; p.prelu_alpha = (const __nv_bfloat16*)prelu_alpha;
   p.y = y; p.dbg = g_dbg_flag;
+  p.cl_m = cl_m; p.cl_n = cl_n; p.a_split_dim = a_split_dim; p.a_split_ext = a_split_ext;
   const long long mtiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
   if (mtiles > 0x7fffffffLL) { delete pl; b200dm_set_error("conv_plan_create: too many tiles"); return B200DM_ERR_INVALID; }
   const int ntiles = d->mode == B200DM_CONV_BATCHED_GEMM ? (d->c_out + g.block_n - 1) / g.block_n : g.n_pad / g.block_n;

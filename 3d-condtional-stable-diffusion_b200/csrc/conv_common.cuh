@@ -15,6 +15,8 @@ struct ConvParams {
   int act, post_act, y_f32, transposed_store;
   int chan_bias_rows;
   int halo_td, halo_tiles_per_ntile, halo_ntn, halo_total_tiles;   // halo kernel only
+  int cl_m, cl_n;                    // igemm cluster: cl_m m-tiles share every B tile, cl_n n-tiles share every A tile
+  int a_split_dim, a_split_ext;      // A box is split over the cl_n sharers along box dim a_split_dim (1=w..4=n), ext per part
   const float* bias;
   const float* out_scale;            // optional per-channel affine applied after the bias adds (a folded BatchNorm of the
   const float* out_shift;            // CONSUMER: y = act(scale * (acc + bias + temb) + shift)), fp32[c_out]

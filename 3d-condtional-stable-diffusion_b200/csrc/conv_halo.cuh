@@ -78,6 +78,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + 2 + s); };
 
+  pdl_launch_dependents();
   const int nch = p.nch0 + p.nch1;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
@@ -97,6 +98,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // set-up above overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ===================== slab producer =====================

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256) norm_act_kernel(b200dm_norm_desc d, const
                                                        const float* __restrict__ pa, const float* __restrict__ pb,
                                                        const float* __restrict__ mean_rstd,
                                                        __nv_bfloat16* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   const int C = d.c0 + d.c1;
   float* sa = sm;
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(256) norm_act_kernel(b200dm_norm_desc d, const
 // (sum, sumsq) pair per group to partial[n][chunk][g].  gn_final combines chunks in fp64.
 __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t voxels, int C,
                                                          int groups, int chunks, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float ssum[256 * 8];
   __shared__ float ssq[256 * 8];
   __shared__ float csum[512], csq[512];
@@ -116,6 +120,8 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
 
 __global__ void gn_final_kernel(const float* __restrict__ partial, int batch, int groups, int chunks, double count,
                                 float eps, float* __restrict__ mean_rstd) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * groups) return;
   const int n = i / groups, g = i % groups;
@@ -138,6 +144,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         const float* g1, const float* b1, const float* g2,
                                                         const float* b2, __nv_bfloat16* y0, __nv_bfloat16* y1,
                                                         __nv_bfloat16* y2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -185,6 +193,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 // ------------------------------------------------------------------ row softmax fp32 -> bf16
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p,
                                                            int64_t rows, int cols, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   __shared__ float bc;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -319,11 +329,11 @@ extern "C" int b200dm_gn_stats(const b200dm_norm_desc* d, const void* x, float e
   B2_CHECK_ARG(C <= 512 && 256 % (C / 8) == 0, "gn_stats: C=%d unsupported (need C/8 to divide 256, C<=512)", C);
   const int chunks = 64;
   cudaStream_t s = (cudaStream_t)stream;
-  gn_partial_kernel<<<dim3(chunks, d->batch), 256, 0, s>>>((const __nv_bfloat16*)x, d->voxels, C, d->groups, chunks, workspace);
+  B2_CHECK_CUDA(b2_launch(gn_partial_kernel, dim3(chunks, d->batch), dim3(256), 0, s, (const __nv_bfloat16*)x, d->voxels, C, d->groups, chunks, workspace));
   B2_CHECK_LAUNCH();
   const int tot = d->batch * d->groups;
-  gn_final_kernel<<<(tot + 127) / 128, 128, 0, s>>>(workspace, d->batch, d->groups, chunks,
-                                                    (double)d->voxels * (double)(C / d->groups), eps, mean_rstd);
+  B2_CHECK_CUDA(b2_launch(gn_final_kernel, dim3((tot + 127) / 128), dim3(128), 0, s, workspace, d->batch, d->groups, chunks,
+                                                    (double)d->voxels * (double)(C / d->groups), eps, mean_rstd));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
@@ -340,8 +350,8 @@ extern "C" int b200dm_norm_act_fwd(const b200dm_norm_desc* d, const void* x0, co
   int gx = grid_for(items, 256, 8);
   gx = (gx + d->batch - 1) / d->batch;
   if (gx < 1) gx = 1;
-  norm_act_kernel<<<dim3(gx, d->batch), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      *d, (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, a, b, mean_rstd, (__nv_bfloat16*)y);
+  B2_CHECK_CUDA(b2_launch(norm_act_kernel, dim3(gx, d->batch), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, 
+      *d, (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, a, b, mean_rstd, (__nv_bfloat16*)y));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
@@ -362,9 +372,9 @@ extern "C" int b200dm_layernorm_fwd(const void* x, int64_t rows, int32_t c, floa
   const int grid = grid_for(rows * 32, 256, 8);
   cudaStream_t s = (cudaStream_t)stream;
   const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
-  if (c <= 256) layernorm_kernel<1><<<grid, 256, 0, s>>>(xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]);
-  else if (c <= 512) layernorm_kernel<2><<<grid, 256, 0, s>>>(xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]);
-  else layernorm_kernel<4><<<grid, 256, 0, s>>>(xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]);
+  if (c <= 256) B2_CHECK_CUDA(b2_launch(layernorm_kernel<1>, dim3(grid), dim3(256), 0, s, xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]));
+  else if (c <= 512) B2_CHECK_CUDA(b2_launch(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]));
+  else B2_CHECK_CUDA(b2_launch(layernorm_kernel<4>, dim3(grid), dim3(256), 0, s, xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
@@ -373,7 +383,7 @@ extern "C" int b200dm_softmax_rows(const float* s, void* p_bf16, int64_t rows, i
   B2_CHECK_ARG(s && p_bf16 && rows > 0 && cols > 0, "softmax_rows: bad arguments");
   const int64_t cap = (int64_t)b2_num_sms() * 8;
   const int grid = (int)(rows < cap ? rows : cap);
-  softmax_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(s, (__nv_bfloat16*)p_bf16, rows, cols, scale);
+  B2_CHECK_CUDA(b2_launch(softmax_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, s, (__nv_bfloat16*)p_bf16, rows, cols, scale));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }

@@ -7,10 +7,11 @@
 #include "common.cuh"
 
 namespace {
-enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE };
+enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN };
 struct Op {
   OpKind kind;
   b200dm_conv_plan* conv = nullptr;
+  b200dm_attn_plan* attn = nullptr;
   b200dm_norm_desc nd{};
   b200dm_update_desc ud{};
   const void* p0 = nullptr; const void* p1 = nullptr; const void* p2 = nullptr; const void* p3 = nullptr; const void* p4 = nullptr;
@@ -40,12 +41,20 @@ extern "C" void b200dm_program_destroy(b200dm_program* p) {
   if (!p) return;
   for (auto& op : p->ops)
     if (op.kind == OP_CONV) b200dm_conv_plan_destroy(op.conv);
+    else if (op.kind == OP_ATTN) b200dm_attention_plan_destroy(op.attn);
   delete p;
 }
 
 extern "C" int b200dm_program_add_conv(b200dm_program* p, b200dm_conv_plan* plan) {
   B2_CHECK_ARG(p && plan, "program_add_conv: null argument");
   Op op; op.kind = OP_CONV; op.conv = plan;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_attention(b200dm_program* p, b200dm_attn_plan* plan) {
+  B2_CHECK_ARG(p && plan, "program_add_attention: null argument");
+  Op op; op.kind = OP_ATTN; op.attn = plan;
   p->ops.push_back(op);
   return B200DM_OK;
 }
@@ -158,6 +167,7 @@ static int run_op(Op& op, void* stream) {
         rc = b200dm_ddpm_update(&op.ud, (const float*)op.p0, op.p1, (const float*)op.p2, (float*)op.out, op.out2, stream);
         break;
       case OP_ADVANCE: rc = b200dm_step_advance((int32_t*)op.out, op.i1, stream); break;
+      case OP_ATTN: rc = b200dm_attention_plan_run(op.attn, stream); break;
     }
   }
   return rc;

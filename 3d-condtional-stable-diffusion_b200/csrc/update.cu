@@ -85,6 +85,8 @@ template <bool kEpsBf16>
 __global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const float* __restrict__ x_t,
                                                      const void* __restrict__ eps, const float* __restrict__ noise,
                                                      float* __restrict__ x_prev, __nv_bfloat16* __restrict__ x_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const Coef k = load_coef(d);
   const int64_t n8 = d.n_per_sample >> 3;
   const int64_t total = n8 * d.batch;
@@ -142,6 +144,8 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ 
 }
 
 __global__ void step_advance_kernel(int32_t* t_dev, int32_t delta) {
+  pdl_launch_dependents();
+  pdl_wait();
   t_dev[0] += delta;
   t_dev[1] += delta;
 }
@@ -162,9 +166,9 @@ extern "C" int b200dm_ddpm_update(const b200dm_update_desc* d, const float* x_t,
   const int grid = (int)(want < (int64_t)b2_num_sms() * 8 ? want : (int64_t)b2_num_sms() * 8);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->eps_dtype == B200DM_BF16)
-    update_kernel<true><<<grid, 256, 0, s>>>(*d, x_t, eps, noise, x_prev, (__nv_bfloat16*)x_prev_bf16);
+    B2_CHECK_CUDA(b2_launch(update_kernel<true>, dim3(grid), dim3(256), 0, s, *d, x_t, eps, noise, x_prev, (__nv_bfloat16*)x_prev_bf16));
   else
-    update_kernel<false><<<grid, 256, 0, s>>>(*d, x_t, eps, noise, x_prev, (__nv_bfloat16*)x_prev_bf16);
+    B2_CHECK_CUDA(b2_launch(update_kernel<false>, dim3(grid), dim3(256), 0, s, *d, x_t, eps, noise, x_prev, (__nv_bfloat16*)x_prev_bf16));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
@@ -183,7 +187,7 @@ extern "C" int b200dm_philox_normal(float* x, void* x_bf16, int64_t n_per_sample
 
 extern "C" int b200dm_step_advance(int32_t* t_dev, int32_t delta, void* stream) {
   B2_CHECK_ARG(t_dev, "step_advance: null t_dev");
-  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, delta);
+  B2_CHECK_CUDA(b2_launch(step_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, t_dev, delta));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }

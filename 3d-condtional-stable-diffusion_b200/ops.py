@@ -275,3 +275,47 @@ def batched_gemm(a, b, y_dtype=torch.float32, residual=None):
     plan = ConvPlan(desc, a, b, y, residual=residual)
     plan.run()
     return y
+
+
+# ------------------------------------------------------------------ K8/K9 flash attention
+class AttnPlan:
+    """softmax(scale * q k^T) v (+ residual) with fixed buffers: q (B,Lq,D), k (B,Lk,D), vt (B,D,Lk), o (B,Lq,D), bf16."""
+
+    def __init__(self, q, k, vt, o, scale, residual=None):
+        _dev()
+        B, Lq, D = q.shape
+        Lk = k.shape[1]
+        assert tuple(k.shape) == (B, Lk, D) and tuple(vt.shape) == (B, D, Lk) and tuple(o.shape) == (B, Lq, D)
+        assert all(t.dtype == torch.bfloat16 and t.is_contiguous() for t in (q, k, vt, o))
+        self.keep = (q, k, vt, o, residual)
+        d = L.AttnDesc()
+        d.batch, d.lq, d.lk, d.d, d.scale = B, Lq, Lk, D, float(scale)
+        h = C.c_void_p()
+        check(lib().b200dm_attention_plan_create(C.byref(d), ptr(q), ptr(k), ptr(vt), ptr(residual), ptr(o), C.byref(h)))
+        self.h, self.o, self.owned = h, o, True
+
+    @property
+    def flops(self):
+        return lib().b200dm_attention_plan_flops(self.h)
+
+    def run(self):
+        check(lib().b200dm_attention_plan_run(self.h, stream()))
+        return self.o
+
+    def release(self):
+        self.owned = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "owned", False) and self.h:
+                lib().b200dm_attention_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def attention(q, k, vt, scale, residual=None):
+    """One-shot flash attention (tests): returns o (B,Lq,D) bf16."""
+    o = torch.empty_like(q)
+    AttnPlan(q, k, vt, o, scale, residual).run()
+    return o

@@ -79,6 +79,16 @@ class Program:
         self.log.append(("layernorm", note, x.numel() * 2.0 * (1 + len(ys))))
         return ys
 
+    def attention(self, q, k, vt, o, scale, residual=None, note=""):
+        plan = ops.AttnPlan(q, k, vt, o, scale, residual)
+        self.flops += plan.flops
+        check(lib().b200dm_program_add_attention(self.h, plan.h))
+        plan.release()
+        self.hold(q, k, vt, o, residual)
+        self.log.append(("attn", note, plan.flops))
+        self.outputs[note] = o
+        return o
+
     def softmax(self, s, p, scale, note=""):
         cols = s.shape[-1]
         check(lib().b200dm_program_add_softmax(self.h, ptr(s), ptr(p), s.numel() // cols, cols, scale))

@@ -209,12 +209,12 @@ class UNet:
             # activation run in conv1's epilogue on the fp32 accumulator (one HBM pass and one bf16 rounding fewer)
             sc2, sh2 = ops.bn_fold(g(f"{n}.norm2.gamma"), g(f"{n}.norm2.beta"), g(f"{n}.norm2.mean"), g(f"{n}.norm2.var"), 1e-3)
             h = conv(h, f"{n}.conv1", w, chan_bias=pr.hold(table), out_affine=(sc2, sh2), act="silu", note=f"{n}.conv1+norm2")
+            pr.outputs[f"{n}.norm2"] = h
             return conv(h, f"{n}.conv2", w, residual=res)
 
         def attention_core(q, k, vT, scale, residual, note):
-            s = bgemm(q, k, torch.float32, note=f"{note}.qk")
-            p = pr.softmax(s, pr.buf(s.shape), scale, note=f"{note}.softmax")
-            return bgemm(p, vT, torch.bfloat16, residual=residual, note=f"{note}.pv")
+            # softmax(q k^T * scale) v (+ residual) in one flash-style kernel: no (B, L, L) score tensor in HBM
+            return pr.attention(q, k, vT, pr.buf(q.shape), scale, residual=residual, note=f"{note}.flash")
 
         def attn_block(b, x):  # AttentionBlock.call (dm3d.py:39-63)
             n, c, s = b["name"], b["c"], b["s"]

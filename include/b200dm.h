@@ -213,6 +213,26 @@ int b200dm_conv_plan_set_trace(b200dm_conv_plan* p, void* trace);
 int b200dm_debug_flag_read_reset(int32_t* flag_out);
 
 /* ---------------------------------------------------------------------------------------------
+ * K8/K9  flattened-voxel attention as one flash-style tcgen05 kernel:  O = softmax(scale * Q K^T) V (+ residual).
+ * Replaces the materialised (B,L,L) score path of AttentionBlock.call (networks/dm3d.py:51-61) and of
+ * CrossAttentionBlock.attention (conditional_dm3d.py:162-184): einsum -> * units^-0.5 -> tf.nn.softmax -> einsum.
+ * Single head (the reference's num_heads is always 1).  bf16 tensors, fp32 softmax statistics and accumulation:
+ *   q (B, Lq, D)   k (B, Lk, D)   vt (B, D, Lk) = V transposed per sample (conv transposed-store epilogue)
+ *   residual (B, Lq, D) or NULL   o (B, Lq, D);   D in {64, 128, 256};  Lk % 8 == 0.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, lq, lk, d;
+  float scale;
+  int32_t reserved[3];
+} b200dm_attn_desc;
+typedef struct b200dm_attn_plan b200dm_attn_plan;
+int b200dm_attention_plan_create(const b200dm_attn_desc* d, const void* q, const void* k, const void* vt,
+                                 const void* residual_or_null, void* o, b200dm_attn_plan** out);
+int b200dm_attention_plan_run(b200dm_attn_plan* p, void* stream);
+void b200dm_attention_plan_destroy(b200dm_attn_plan* p);
+double b200dm_attention_plan_flops(const b200dm_attn_plan* p);
+
+/* ---------------------------------------------------------------------------------------------
  * Step program: an ordered list of the above ops with fixed buffers, launched natively in one
  * call (one ctypes crossing per U-Net forward instead of ~250), CUDA-graph capturable.
  * --------------------------------------------------------------------------------------------- */
@@ -228,6 +248,7 @@ int b200dm_program_add_gn_stats(b200dm_program* p, const b200dm_norm_desc* d, co
 int b200dm_program_add_layernorm(b200dm_program* p, const void* x, int64_t rows, int32_t c, float eps,
                                  int32_t n_out, const float* const* gammas, const float* const* betas,
                                  void* const* ys);
+int b200dm_program_add_attention(b200dm_program* p, b200dm_attn_plan* plan /* ownership moves */);
 int b200dm_program_add_softmax(b200dm_program* p, const float* s, void* p_bf16, int64_t rows,
                                int32_t cols, float scale);
 int b200dm_program_add_update(b200dm_program* p, const b200dm_update_desc* d, const float* x_t,

@@ -4,7 +4,7 @@ reverse chain with injected noise -- product (CUDA, through the C ABI) vs oracle
 Tolerances (stated, and why):
   * every kernel accumulates in fp32, so on IDENTICAL inputs a layer matches the oracle to ~1e-6 (tests/test_conv_gpu.py);
     test_unet_layer_trace pins that inside the assembled network: 'in' conv rel-L2 <= 1e-5 and the first ResidualBlock
-    <= 1e-3 against the oracle that rounds to bf16 at the same storage points (Emu(True)).
+    <= 1e-3 (4e-3 behind the fused conv1+norm2 epilogue, which skips one bf16 rounding) against the oracle that rounds to bf16 at the same storage points (Emu(True)).
   * activations are STORED in bf16 (north_star).  A network of ~100 bf16 storage points is chaotic at the ulp level:
     one rounding flip (4e-3 of an element) perturbs 27*C downstream sums and flips more, so after ~10 layers the
     product and the emulating oracle are decorrelated at the bf16 noise floor.  The whole-network bound is therefore
@@ -72,8 +72,10 @@ def test_unet_layer_trace(cuda):
     ou.forward(P, x, tt, emu=Emu(True, tr))
     errs = {k: rel(v.reshape(tr[k].shape), tr[k]) for k, v in net.prog.outputs.items() if k in tr}
     assert errs["in"] <= 1e-5, errs["in"]
-    for k in ("down.0.res.0.norm1", "down.0.res.0.conv1", "down.0.res.0.norm2", "down.0.res.0.conv2"):
-        assert errs[k] <= 1e-3, (k, errs[k])
+    # conv1 -> norm2 -> swish is ONE kernel (BN applied to the fp32 accumulator): the emulating oracle rounds conv1's
+    # output to bf16 first, so that tensor differs by one extra bf16 rounding (<= 2^-8 per element)
+    for k, tol in (("down.0.res.0.norm1", 1e-3), ("down.0.res.0.norm2", 4e-3), ("down.0.res.0.conv2", 4e-3)):
+        assert errs[k] <= tol, (k, errs[k])
     assert max(errs.values()) <= 2.5e-2
 
 
