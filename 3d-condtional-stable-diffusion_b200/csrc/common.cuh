@@ -63,6 +63,12 @@ struct __align__(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
 
+__device__ __forceinline__ bf16x8 ldg_bf16x8(const bf16x8* p) {   // 16-byte read-only load
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  bf16x8 r;
+  memcpy(&r, &u, 16);
+  return r;
+}
 __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

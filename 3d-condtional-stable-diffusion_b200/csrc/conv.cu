@@ -582,6 +582,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   p.bias = bias; p.chan_bias = chan_bias; p.t_dev = t_dev;
   p.residual = (const __nv_bfloat16*)residual; p.prelu_alpha = (const __nv_bfloat16*)prelu_alpha;
   p.y = y; p.dbg = g_dbg_flag;
+  if (const char* e = getenv("B200DM_EPI_DBG")) p.epi_dbg = atoi(e);
   p.cl_m = cl_m; p.cl_n = cl_n; p.a_split_dim = a_split_dim; p.a_split_ext = a_split_ext;
   const long long mtiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
   if (mtiles > 0x7fffffffLL) { delete pl; b200dm_set_error("conv_plan_create: too many tiles"); return B200DM_ERR_INVALID; }

@@ -15,6 +15,7 @@ struct ConvParams {
   int act, post_act, y_f32, transposed_store;
   int chan_bias_rows;
   int halo_td, halo_tiles_per_ntile, halo_ntn, halo_total_tiles;   // halo kernel only
+  int epi_dbg;                       // tuning aid (B200DM_EPI_DBG): 1 = skip global stores, 2 = skip TMEM loads too
   int cl_m, cl_n;                    // igemm cluster: cl_m m-tiles share every B tile, cl_n n-tiles share every A tile
   int a_split_dim, a_split_ext;      // A box is split over the cl_n sharers along box dim a_split_dim (1=w..4=n), ext per part
   const float* bias;
@@ -49,7 +50,7 @@ __device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162f
 // tile spans several samples.
 __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint32_t (&rr)[16], int col0, int n, int64_t vox,
                                                 int64_t vox_per, int64_t row_off, const float* bs, const float* cb,
-                                                const float* sc = nullptr) {
+                                                const float* sc = nullptr, const bf16x8* rpre = nullptr) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
@@ -91,9 +92,14 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
     }
     if (p.residual) {
       float a[16];
-      const __nv_bfloat16* rp = p.residual + row_off + col0;
-      unpack8(*reinterpret_cast<const bf16x8*>(rp), *reinterpret_cast<float(*)[8]>(&a[0]));
-      unpack8(*reinterpret_cast<const bf16x8*>(rp + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
+      if (rpre) {   // residual already in registers (prefetched while the MMAs ran)
+        unpack8(rpre[0], *reinterpret_cast<float(*)[8]>(&a[0]));
+        unpack8(rpre[1], *reinterpret_cast<float(*)[8]>(&a[8]));
+      } else {
+        const __nv_bfloat16* rp = p.residual + row_off + col0;
+        unpack8(*reinterpret_cast<const bf16x8*>(rp), *reinterpret_cast<float(*)[8]>(&a[0]));
+        unpack8(*reinterpret_cast<const bf16x8*>(rp + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += a[j];
     }
@@ -134,10 +140,10 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
 
 // Stage bias[col] (+ chan_bias row `cbrow` when given) for columns [col_base, col_base + ncols) into shared memory.
 // With an output affine, dst_scale[c] = scale and dst[c] = scale * bias + shift.
-// Called by the 128 epilogue threads (tid 0..127); columns past c_out read as 0.
+// Called by the epilogue threads (tid 0..nthreads-1); columns past c_out read as 0.
 __device__ __forceinline__ void stage_bias(const ConvParams& p, float* dst, float* dst_scale, int col_base, int ncols,
-                                           const float* cbrow, int tid) {
-  for (int c = tid; c < ncols; c += 128) {
+                                           const float* cbrow, int tid, int nthreads = 128) {
+  for (int c = tid; c < ncols; c += nthreads) {
     const int col = col_base + c;
     float b = 0.f, sc = 1.f;
     if (col < p.c_out) {
@@ -150,3 +156,4 @@ __device__ __forceinline__ void stage_bias(const ConvParams& p, float* dst, floa
   }
 }
 __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }

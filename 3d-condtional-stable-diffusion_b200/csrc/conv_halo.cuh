@@ -17,14 +17,14 @@
 //             MMA only 48, so one tap per round trip is issue-bound; three are not.
 //   TMEM      2 accumulator stages x TD x BLOCK_N columns: the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Warps (256 threads): 0 = slab producer, 1 = weight producer, 2 = TMEM owner + MMA issuer, 3 = idle, 4-7 = epilogue.
+// Warps (384 threads): 0 = slab producer, 1 = weight producer, 2 = TMEM owner + MMA issuer, 3 = idle, 4-11 = epilogue.
 // Every role loop is warp-uniform; a single elected lane (elect.sync) issues TMA / tcgen05 instructions.
 #pragma once
 #include "conv_common.cuh"
 
 namespace halo {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kSlabBytes = 23 * 1024;      // 180 voxels x 128 B = 23040, rounded up to the 1024-B swizzle period
 constexpr int kSlabTx = 180 * 128;
 
@@ -85,7 +85,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), 1); }
     for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), 1); ptx::mbar_init(tmem_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), 1); ptx::mbar_init(tmem_empty(s), 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
@@ -217,8 +217,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    // ===================== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 =====================
+    // Measured on B200 (64->64 @ 32^3): with 4 warps the epilogue of a tile took as long as the tile's MMA phase and any
+    // extra work (residual read, SiLU) made the kernel epilogue-bound; two warps per lane quarter split the columns, and
+    // the residual is fetched into registers BEFORE the accumulator is ready.
+    constexpr int kHalfCols = BLOCK_N >= 32 ? BLOCK_N / 2 : BLOCK_N;
+    constexpr int kChunks = kHalfCols / 16;
     const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const bool active = BLOCK_N >= 32 || half == 0;
+    const int cbase = BLOCK_N >= 32 ? half * kHalfCols : 0;
     const int r = qd * 32 + lane;
     const int iw = r & 7, ih = r >> 3;
     const int64_t vox_per = (int64_t)p.out_d * p.out_h * p.out_w;
@@ -227,12 +235,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     for (int id = first_tile; id < p.halo_total_tiles; id += tile_step, ++it) {
       const Tile t = decode_tile(p, id);
       const uint32_t as = it & 1;
+      const int ow = t.w0 + iw, oh = t.h0 + ih;
+      const int colt = t.n_tile * BLOCK_N + cbase;       // first output channel of this warp
+      // residual rows of this thread -> registers while the MMAs of this tile are still running
+      bf16x8 rpre[TD][kChunks][2];
+      const bool pre = p.residual != nullptr && active && colt + kHalfCols <= p.c_out;
+      if (pre) {
+#pragma unroll
+        for (int pl = 0; pl < TD; ++pl) {
+          const int od = t.d0 + pl;
+          if (ow < p.out_w && oh < p.out_h && od < p.out_d) {
+            const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;
+            const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + ((int64_t)t.n * vox_per + vox) * p.c_out + colt);
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) { rpre[pl][c][0] = ldg_bf16x8(rp + 2 * c); rpre[pl][c][1] = ldg_bf16x8(rp + 2 * c + 1); }
+          }
+        }
+      }
       if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 10);
       const bool ok = ptx::mbar_wait(tmem_full(as), (it >> 1) & 1, p.dbg, 16);
       ptx::tc_fence_after();
       if (!ok) break;
       if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 11);
-      const int ow = t.w0 + iw, oh = t.h0 + ih;
       // bias + temb row of this tile's sample -> smem once per tile (double-buffered by accumulator stage)
       float* bs = bias_s + as * 2 * BLOCK_N;
       float* scs = bs + BLOCK_N;
@@ -244,37 +268,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           const int tt = p.t_dev ? p.t_dev[0] : 0;
           cbrow = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? t.n : 0)) * p.c_out;
         }
-        stage_bias(p, bs, scs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128);
-        epilogue_bar_sync();
+        stage_bias(p, bs, scs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128, 256);
+        epilogue_bar_sync256();
       }
-#pragma unroll 1
-      for (int pl = 0; pl < TD; ++pl) {
-        const int od = t.d0 + pl;
-        const bool valid = ow < p.out_w && oh < p.out_h && od < p.out_d;
-        const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;
-        const int64_t row_off = ((int64_t)t.n * vox_per + vox) * p.c_out;
-        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N;
-        if (BLOCK_N >= 32) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            const int col0 = t.n_tile * BLOCK_N + c0;
+      if (active) {
+#pragma unroll
+        for (int pl = 0; pl < TD; ++pl) {
+          const int od = t.d0 + pl;
+          const bool valid = ow < p.out_w && oh < p.out_h && od < p.out_d;
+          const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;
+          const int64_t row_off = ((int64_t)t.n * vox_per + vox) * p.c_out;
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N + cbase;
+#pragma unroll
+          for (int c = 0; c < kChunks; c += 2) {
+            const int col0 = colt + c * 16;
             if (col0 >= p.c_out) break;
             uint32_t ra[16], rb[16];
-            ptx::tc_ld_32x32b_x16(taddr + c0, ra);
-            ptx::tc_ld_32x32b_x16(taddr + c0 + 16, rb);
-            ptx::tc_wait_ld();
-            if (valid) {
-              conv_epilogue16(p, ra, col0, t.n, vox, vox_per, row_off, has_bs ? bs + c0 : nullptr, nullptr, has_sc ? scs + c0 : nullptr);
-              if (col0 + 16 < p.c_out)
-                conv_epilogue16(p, rb, col0 + 16, t.n, vox, vox_per, row_off, has_bs ? bs + c0 + 16 : nullptr, nullptr,
-                                has_sc ? scs + c0 + 16 : nullptr);
+            if (p.epi_dbg < 2) {
+              ptx::tc_ld_32x32b_x16(taddr + c * 16, ra);
+              if (c + 1 < kChunks) ptx::tc_ld_32x32b_x16(taddr + c * 16 + 16, rb);
+              ptx::tc_wait_ld();
+            }
+            if (valid && p.epi_dbg == 0) {
+              conv_epilogue16(p, ra, col0, t.n, vox, vox_per, row_off, has_bs ? bs + cbase + c * 16 : nullptr, nullptr,
+                              has_sc ? scs + cbase + c * 16 : nullptr, pre ? rpre[pl][c] : nullptr);
+              if (c + 1 < kChunks && col0 + 16 < p.c_out)
+                conv_epilogue16(p, rb, col0 + 16, t.n, vox, vox_per, row_off, has_bs ? bs + cbase + c * 16 + 16 : nullptr, nullptr,
+                                has_sc ? scs + cbase + c * 16 + 16 : nullptr, pre ? rpre[pl][c + 1 < kChunks ? c + 1 : c] : nullptr);
             }
           }
-        } else {
-          uint32_t rr[16];
-          ptx::tc_ld_32x32b_x16(taddr, rr);
-          ptx::tc_wait_ld();
-          if (valid) conv_epilogue16(p, rr, t.n_tile * BLOCK_N, t.n, vox, vox_per, row_off, has_bs ? bs : nullptr, nullptr, has_sc ? scs : nullptr);
         }
       }
       ptx::tc_fence_before();

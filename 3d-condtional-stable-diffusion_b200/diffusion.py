@@ -11,10 +11,14 @@ SURVEY 8b): ``x_T=``, ``noise=`` (inject), ``seed=``, ``sample_id0=`` (multi-GPU
 ``steps=``, per-sample ``context=`` ids, and ``decode(latents, quantize=False)``.
 
 The reverse loop is one captured CUDA graph per step: U-Net program + fused posterior update + a device-side
-timestep decrement, replayed T times with zero host work in between.
+timestep decrement, replayed T times with zero host work in between.  Samples are independent (BatchNorm in inference
+mode, per-sample attention), so the batch is split into ``chains`` sub-batches whose kernel chains are captured on
+parallel graph branches: the small 8^3-level kernels of one chain (<= 64 CTAs) run beside another chain's instead of
+leaving most of the 148 SMs idle.  B200DM_CHAINS overrides the default.
 """
 from __future__ import annotations
 
+import copy
 import ctypes
 import os
 
@@ -89,33 +93,67 @@ class DiffusionModel:
         return mean, var.reshape(1, 1, 1, 1, 1).expand(x_t.shape[0], 1, 1, 1, 1)
 
     # ------------------------------------------------------------------ compiled step
+    @staticmethod
+    def _num_chains(batch):
+        want = int(os.environ.get("B200DM_CHAINS", "2"))
+        c = max(1, min(want, batch))
+        while batch % c:
+            c -= 1
+        return c
+
     def _compile(self, batch, sampler, inject_noise, seed, sample_id0):
-        key = (batch, sampler, inject_noise)
+        key = (batch, sampler, inject_noise, self._num_chains(batch))
         if self._step is not None and self._step["key"] == key:
             st = self._step
-            if (st["desc"].seed, st["desc"].sample_id0) != (seed, sample_id0):
-                st["desc"].seed, st["desc"].sample_id0 = seed, sample_id0
+            if (st["seed"], st["sample_id0"]) != (seed, sample_id0):
+                st["seed"], st["sample_id0"] = seed, sample_id0
+                for c, d in enumerate(st["descs"]):
+                    d.seed, d.sample_id0 = seed, sample_id0 + c * st["chain_batch"]
                 st["graph"] = None  # kernel arguments are baked into a captured graph
             return st
         L.require_gpu()
         dev = torch.device("cuda", torch.cuda.current_device())
         self.b.to(dev)
         t_dev = torch.zeros(2, dtype=torch.int32, device=dev)
-        net = self.network.compile(batch, self.timesteps, dev, t_dev=t_dev)
+        chains = key[3]
+        cb = batch // chains
+        # one compiled program per chain: shallow copies of self.network (weights shared on the host, buffers per chain)
+        nets = [copy.copy(self.network).compile(cb, self.timesteps, dev, t_dev=t_dev) for _ in range(chains)]
         S, Cl = self.latent_size, self.lc
         x = torch.zeros(batch, S, S, S, Cl, dtype=torch.float32, device=dev)
         noise = torch.zeros_like(x) if inject_noise else None
-        desc = ops.make_update_desc(self.b, x[0].numel(), batch, 0, -1, 1 if sampler == "ddim" else 0, seed, sample_id0,
-                                    L.F32, t_dev=t_dev)
-        self._step = dict(key=key, net=net, x=x, noise=noise, desc=desc, t_dev=t_dev, graph=None, dev=dev, delta=-1)
+        descs = [ops.make_update_desc(self.b, x[0].numel(), cb, 0, -1, 1 if sampler == "ddim" else 0, seed,
+                                      sample_id0 + c * cb, L.F32, t_dev=t_dev) for c in range(chains)]
+        self._step = dict(key=key, nets=nets, net=nets[0], x=x, noise=noise, descs=descs, t_dev=t_dev, graph=None, dev=dev,
+                          delta=-1, chains=chains, chain_batch=cb, seed=seed, sample_id0=sample_id0, streams=None)
         return self._step
 
-    def _run_step_eager(self, st):
-        """U-Net forward -> fused update (x in place, bf16 copy into the U-Net input) -> t -= delta."""
-        st["net"].prog.run()
-        d = st["desc"]
-        L.check(L.lib().b200dm_ddpm_update(ctypes.byref(d), L.ptr(st["x"]), L.ptr(st["net"].eps), L.ptr(st["noise"]),
-                                           L.ptr(st["x"]), L.ptr(st["net"].x_in), L.stream()))
+    def _run_chain(self, st, c):
+        """U-Net forward of chain c -> fused update of its samples (x in place, bf16 copy into the U-Net input)."""
+        cb, net = st["chain_batch"], st["nets"][c]
+        net.prog.run()
+        xs = st["x"][c * cb:(c + 1) * cb]
+        nz = st["noise"][c * cb:(c + 1) * cb] if st["noise"] is not None else None
+        L.check(L.lib().b200dm_ddpm_update(ctypes.byref(st["descs"][c]), L.ptr(xs), L.ptr(net.eps), L.ptr(nz), L.ptr(xs),
+                                           L.ptr(net.x_in), L.stream()))
+
+    def _run_step_eager(self, st, parallel=False):
+        """Every chain's forward + update, then t -= delta.  ``parallel``: fork the chains onto side streams (inside a
+        graph capture this records parallel branches)."""
+        if parallel and st["chains"] > 1:
+            if st["streams"] is None:
+                st["streams"] = [torch.cuda.Stream() for _ in range(st["chains"] - 1)]
+            main = torch.cuda.current_stream()
+            for c, s in enumerate(st["streams"], start=1):
+                s.wait_stream(main)
+                with torch.cuda.stream(s):
+                    self._run_chain(st, c)
+            self._run_chain(st, 0)
+            for s in st["streams"]:
+                main.wait_stream(s)
+        else:
+            for c in range(st["chains"]):
+                self._run_chain(st, c)
         L.check(L.lib().b200dm_step_advance(L.ptr(st["t_dev"]), st["delta"], L.stream()))
 
     def _capture(self, st):
@@ -123,11 +161,11 @@ class DiffusionModel:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self._run_step_eager(st)  # warm-up (sets kernel attributes outside capture)
+            self._run_step_eager(st, parallel=True)  # warm-up (sets kernel attributes outside capture)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         with torch.cuda.graph(g):
-            self._run_step_eager(st)
+            self._run_step_eager(st, parallel=True)
         st["graph"] = g
         return g
 
@@ -139,17 +177,26 @@ class DiffusionModel:
         B = shape[0]
         assert shape[1] == self.latent_size and shape[-1] == self.lc, "shape must match the compiled latent geometry"
         st = self._compile(B, sampler, noise is not None, seed, sample_id0)
-        dev, net = st["dev"], st["net"]
+        dev, nets, cb = st["dev"], st["nets"], st["chain_batch"]
         if self.conditional:
             ctx = context if context is not None else (0 if context_value is None else context_value)
-            net.set_context(torch.as_tensor(ctx).reshape(-1))
+            ctx = torch.as_tensor(ctx).reshape(-1)
+            if ctx.numel() == 1:
+                ctx = ctx.expand(B)  # the reference feeds a batch-1 context (conditional_dm3d.py:552)
+            for c, net in enumerate(nets):
+                net.set_context(ctx[c * cb:(c + 1) * cb])
         if x_T is None:  # samples = tf.random.normal(shape) (dm3d.py:513): Philox stream 1
             x0, xb = ops.philox_normal(shape, seed, sample_id0, 0, 1, want_bf16=True)
         else:
             x0 = x_T.to(dev, torch.float32).contiguous()
             xb = ops.cast(x0, torch.bfloat16)
-        st["x"].copy_(x0)
-        net.x_in.copy_(xb)
+
+        def load_state():
+            st["x"].copy_(x0)
+            for c, net in enumerate(nets):
+                net.x_in.copy_(xb[c * cb:(c + 1) * cb])
+
+        load_state()
         T = self.timesteps
         if sampler == "ddim":
             n = steps or T
@@ -165,8 +212,7 @@ class DiffusionModel:
                 st["t_dev"].copy_(torch.tensor([seq[0], seq[0] + delta], dtype=torch.int32))
                 # capture runs one warm-up step + records one: restore state afterwards
                 self._capture(st)
-                st["x"].copy_(x0)
-                net.x_in.copy_(xb)
+                load_state()
             st["t_dev"].copy_(torch.tensor([seq[0], seq[0] + delta], dtype=torch.int32))
             for _ in seq:
                 st["graph"].replay()
@@ -180,7 +226,7 @@ class DiffusionModel:
                 st["delta"] = 0
                 self._run_step_eager(st)
                 if on_step is not None:
-                    on_step(i, st["x"], net.eps)
+                    on_step(i, st["x"], torch.cat([net.eps for net in nets], 0))
             st["delta"] = -1 if st["graph"] is None else st["delta"]
         return st["x"].clone()
 

@@ -198,8 +198,8 @@ def run_ours(args):
     assert torch.isfinite(lat).all(), "non-finite latents"
     assert L.debug_flag() == 0, "tcgen05/TMA watchdog fired"
     st = dm._step
-    graph, net = st["graph"], st["net"]
-    launches_per_step = net.prog.num_launches + 2
+    graph, nets = st["graph"], st["nets"]
+    launches_per_step = sum(net.prog.num_launches + 1 for net in nets) + 1   # per chain: U-Net program + update; + t advance
 
     def reset(t0):
         st["t_dev"].copy_(torch.tensor([t0, t0 - 1], dtype=torch.int32))
@@ -242,26 +242,29 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world), "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * K}
+            "config": dict(workload_config(world), chains=st["chains"]), "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * K}
 
     if rank == 0:
         # ---- roofline of the dominant kernel (conv_igemm): per-launch CUDA events over one more step
         pk = peaks()
         reset(T - 1)
-        net.prog.run_timed()
-        rows = net.prog.run_timed()
-        conv_ms = sum(r[3] for r in rows if r[0] == "conv")
-        conv_fl = sum(r[2] for r in rows if r[0] == "conv")
-        ew_ms = sum(r[3] for r in rows if r[0] != "conv")
-        ew_by = sum(r[2] for r in rows if r[0] != "conv")
-        n_conv = sum(1 for r in rows if r[0] == "conv")
+        rows = []
+        for net in nets:          # every chain's program, one launch at a time with an event pair around each
+            net.prog.run_timed()
+            rows += net.prog.run_timed()
+        tc = ("conv", "attn")     # tensor-core kernels: implicit-GEMM convs / GEMMs and flash attention
+        conv_ms = sum(r[3] for r in rows if r[0] in tc)
+        conv_fl = sum(r[2] for r in rows if r[0] in tc)
+        ew_ms = sum(r[3] for r in rows if r[0] not in tc)
+        ew_by = sum(r[2] for r in rows if r[0] not in tc)
+        n_conv = sum(1 for r in rows if r[0] in tc)
         ach = conv_fl / (conv_ms * 1e-3) / 1e12
-        line["roofline"] = {"kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM Conv3D / GEMM), all launches of one step",
+        line["roofline"] = {"kernel": "conv_halo_kernel / conv_igemm_kernel / flash_attn_kernel (tcgen05 implicit-GEMM Conv3D, GEMMs, attention), all launches of one step",
                             "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                             "peak_source": f"{pk['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
                             "traffic": None, "launches": n_conv, "avg_launch_ms": conv_ms / n_conv,
                             "algorithmic_gflop_per_step": conv_fl / 1e9, "share_of_step": conv_ms / (conv_ms + ew_ms)}
-        line["roofline_hbm_kernels"] = {"kernels": "norm_act / layernorm / softmax (fused elementwise passes of one step)",
+        line["roofline_hbm_kernels"] = {"kernels": "norm_act / layernorm (fused elementwise passes of one step)",
                                         "bound": "hbm", "achieved": ew_by / (ew_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                         "frac": ew_by / (ew_ms * 1e-3) / 1e9 / pk["hbm"], "share_of_step": ew_ms / (conv_ms + ew_ms)}
         if world == 1 and not args.no_cpu:
@@ -282,8 +285,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--batch", type=int, default=None, help="tuning aid: per-GPU batch other than the cfg-2 value (8); not a bench line")
     ap.add_argument("--dump-ops", default=None, help="write per-op (kind,name,work,ms) CSV of one step")
     args = ap.parse_args()
+    if args.batch:
+        CFG["B"] = args.batch
     if args.impl == "reference":
         run_reference(args)
     else:
