@@ -31,7 +31,9 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
-template <int BLOCK_N, int NSTAGE, bool CLUSTER>
+// CMODE 0: plain; 1: cluster with TMA-multicast operands (experiment); 2: split-K cluster (K range per CTA, partial
+// accumulators reduced through distributed shared memory by the cluster's first CTA).
+template <int BLOCK_N, int NSTAGE, int CMODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const ConvParams p) {
@@ -54,7 +56,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   // tile decode
   pdl_launch_dependents();
-  int bx = blockIdx.x;
+  constexpr bool CLUSTER = CMODE == 1;
+  constexpr bool KSPLIT = CMODE == 2;
+  const int ks = KSPLIT ? p.ksplit : 1;
+  const int krank = KSPLIT ? (int)ptx::cluster_ctaid_x() : 0;
+  int bx = KSPLIT ? blockIdx.x / ks : blockIdx.x;
   const int tw = bx % p.tiles_w; bx /= p.tiles_w;
   const int th = bx % p.tiles_h; bx /= p.tiles_h;
   const int td = bx % p.tiles_d; bx /= p.tiles_d;
@@ -63,7 +69,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int n_tile = blockIdx.y;
   const int parity = blockIdx.z;
   const int pw = parity & 1, ph = (parity >> 1) & 1, pd = (parity >> 2) & 1;
-  const int nkb = (p.nch0 + p.nch1) * p.ntaps;
+  const int nkb_all = (p.nch0 + p.nch1) * p.ntaps;
+  const int kb0 = KSPLIT ? (int)((long long)krank * nkb_all / ks) : 0;            // this CTA's K range
+  const int kb1 = KSPLIT ? (int)((long long)(krank + 1) * nkb_all / ks) : nkb_all;
 
   // Cluster of cl_m x cl_n CTAs (x = m-tiles, y = n-tiles): the cl_n CTAs of one m-tile each fetch 1/cl_n of the A tile and
   // TMA-multicast it to all of them; the cl_m CTAs of one n-tile do the same with the B tile.  A stage may be refilled
@@ -86,6 +94,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   ptx::tc_fence_before();
   __syncthreads();
   if (CLUSTER) ptx::cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
+  bool mid_synced = false;                // split-K: every thread of the cluster passes ONE mid-kernel cluster barrier
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();   // everything above overlapped the previous kernel's tail; from here on we touch its outputs
@@ -96,8 +105,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int b_row = (p.mode == B200DM_CONV_PARITY ? parity : (p.mode == B200DM_CONV_BATCHED_GEMM ? n0 : 0)) * p.n_pad +
                         n_tile * BLOCK_N;
       uint32_t s = 0, phase = 0;
-      int chunk = 0, tap = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      int chunk = kb0 / p.ntaps, tap = kb0 % p.ntaps;
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (!ptx::mbar_wait(empty_bar(s), phase ^ 1, p.dbg, 1)) break;
         if (ptx::elect_one()) {
           int ow, oh, od;
@@ -143,14 +152,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const uint64_t b_desc0 = ptx::make_smem_desc(smem_base + kABytes, 16, 1024, ptx::kLayoutSw128);
       bool ok = true;
       uint32_t s = 0, phase = 0;
-      for (int kb = 0; kb < nkb && ok; ++kb) {
+      for (int kb = kb0; kb < kb1 && ok; ++kb) {
         ok = ptx::mbar_wait(full_bar(s), phase, p.dbg, 2);
         if (!ok) break;
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t da = a_desc0 + (uint64_t)(s * (kStageBytes >> 4));
           const uint64_t db = b_desc0 + (uint64_t)(s * (kStageBytes >> 4));
-          ptx::tc_mma_f16(tmem_base, da, db, idesc, kb != 0 ? 1u : 0u);
+          ptx::tc_mma_f16(tmem_base, da, db, idesc, kb != kb0 ? 1u : 0u);
           ptx::tc_mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
           ptx::tc_mma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
           ptx::tc_mma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
@@ -197,27 +206,53 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     const bool ok = ptx::mbar_wait(tmem_full_bar, 0, p.dbg, 3);
     ptx::tc_fence_after();
-    if (ok) {
+    // split-K staging: partial accumulators as fp32 [col][row] in this CTA's (now idle) pipeline stages
+    float* stage_f = reinterpret_cast<float*>(smem);
+    if (KSPLIT && krank != 0) {
+      if (ok) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        const int col0 = n_tile * BLOCK_N + c0;
-        if (col0 >= p.c_out) break;  // warp-uniform
-        uint32_t rr[16];
-        ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
-        ptx::tc_wait_ld();
-        if (!valid) continue;
-        conv_epilogue16(p, rr, col0, n, vox, vox_per, row_off, has_bs ? bias_s + c0 : nullptr, cb,
-                        p.out_scale ? scale_s + c0 : nullptr);
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+          uint32_t rr[16];
+          ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
+          ptx::tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) stage_f[(c0 + j) * 128 + r] = __uint_as_float(rr[j]);
+        }
+      }
+      ptx::cluster_sync_all();   // release: the leader may now read the staging through DSMEM
+      mid_synced = true;
+    } else {
+      if (KSPLIT) { ptx::cluster_sync_all(); mid_synced = true; }   // acquire: every peer's partial tile is staged
+      if (ok) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+          const int col0 = n_tile * BLOCK_N + c0;
+          if (col0 >= p.c_out) break;  // warp-uniform
+          uint32_t rr[16];
+          ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
+          ptx::tc_wait_ld();
+          if (KSPLIT) {
+            for (int pr = 1; pr < ks; ++pr) {
+              const uint32_t remote = ptx::mapa_shared(ptx::smem_u32(stage_f + c0 * 128 + r), (uint32_t)pr);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + ptx::ld_dsmem_f32(remote + j * 512));
+            }
+          }
+          if (!valid) continue;
+          conv_epilogue16(p, rr, col0, n, vox, vox_per, row_off, has_bs ? bias_s + c0 : nullptr, cb,
+                          p.out_scale ? scale_s + c0 : nullptr);
+        }
       }
     }
   }
+  if (KSPLIT && !mid_synced) ptx::cluster_sync_all();   // producer / MMA warps: their half of the mid-kernel barrier
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
-  if (CLUSTER) ptx::cluster_sync_all();   // no CTA exits while a peer may still multicast into / arrive on its smem
+  if (CLUSTER || KSPLIT) ptx::cluster_sync_all();   // no CTA exits while a peer may still write / read its shared memory
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -410,8 +445,26 @@ extern "C" int b200dm_conv_pack_weights(const b200dm_conv_desc* d, const float* 
 
 template <int BLOCK_N, int NSTAGE>
 static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
+  if (pl->p.ksplit > 1) {
+    auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, 2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = pl->grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl->p.ksplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+    return B200DM_OK;
+  }
   if (pl->p.cl_m * pl->p.cl_n > 1) {
-    auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, true>;
+    auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, 1>;
     static bool attr_set = false;
     if (!attr_set) {
       B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -428,7 +481,7 @@ static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
     B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
     return B200DM_OK;
   }
-  auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, false>;
+  auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, 0>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -588,6 +641,17 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   if (mtiles > 0x7fffffffLL) { delete pl; b200dm_set_error("conv_plan_create: too many tiles"); return B200DM_ERR_INVALID; }
   const int ntiles = d->mode == B200DM_CONV_BATCHED_GEMM ? (d->c_out + g.block_n - 1) / g.block_n : g.n_pad / g.block_n;
   pl->grid = dim3((unsigned)mtiles, (unsigned)ntiles, d->mode == B200DM_CONV_PARITY ? 8 : 1);
+  // split-K: when the tile grid leaves most SMs idle and K is long, ksplit CTAs (one cluster) share a tile.  Each CTA
+  // streams its K range at the per-SM operand rate (~40 B/clk), so an under-filled grid is K-latency-bound otherwise.
+  p.ksplit = 1;
+  if (!pl->halo && cl_m * cl_n == 1 && d->reserved[1] == 0) {
+    const long long ctas = mtiles * ntiles * (d->mode == B200DM_CONV_PARITY ? 8 : 1);
+    const int nkb = (g.nch0 + g.nch1) * g.ntaps;
+    int ksp = 1;
+    while (ksp < 8 && ctas * (ksp * 2) <= b2_num_sms() && nkb / (ksp * 2) >= 13) ksp *= 2;   // >= 13 k-blocks per CTA: 3^3 convs only
+    if (const char* e = getenv("B200DM_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 8 && (v & (v - 1)) == 0 && nkb / v >= 1) ksp = v; }
+    if (ksp > 1) { p.ksplit = ksp; pl->grid.x = (unsigned)(mtiles * ksp); }
+  }
   // pipeline depth: enough bytes in flight to cover the L2->smem latency (B200DM_IGEMM_STAGES=4 restores the shallow ring)
   // 4 stages; measured on B200: a deeper ring (B200DM_IGEMM_STAGES=8: 6 stages at BLOCK_N=128, 8 below) does not help
   // at BLOCK_N=128 (not latency-bound) and hurts below 128, where 4 stages let two CTAs share an SM

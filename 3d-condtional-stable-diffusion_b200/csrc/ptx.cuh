@@ -81,6 +81,17 @@ __device__ __forceinline__ uint32_t cluster_ctaid_y() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// distributed shared memory: address of `local_smem_addr` in CTA `rank` of the cluster, and a 4-byte load from it
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
 // Multicast loads: the box lands at the same CTA-relative smem offset in every CTA of `mask`, and each of those CTAs'
 // mbarrier (same offset) receives the complete_tx.
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {

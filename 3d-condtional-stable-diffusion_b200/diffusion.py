@@ -12,9 +12,8 @@ SURVEY 8b): ``x_T=``, ``noise=`` (inject), ``seed=``, ``sample_id0=`` (multi-GPU
 
 The reverse loop is one captured CUDA graph per step: U-Net program + fused posterior update + a device-side
 timestep decrement, replayed T times with zero host work in between.  Samples are independent (BatchNorm in inference
-mode, per-sample attention), so the batch is split into ``chains`` sub-batches whose kernel chains are captured on
-parallel graph branches: the small 8^3-level kernels of one chain (<= 64 CTAs) run beside another chain's instead of
-leaving most of the 148 SMs idle.  B200DM_CHAINS overrides the default.
+mode, per-sample attention), so the batch can be split into ``chains`` sub-batches whose kernel chains are captured on
+parallel graph branches (B200DM_CHAINS; default 1 -- measured no gain on B200, see _num_chains).
 """
 from __future__ import annotations
 
@@ -95,7 +94,10 @@ class DiffusionModel:
     # ------------------------------------------------------------------ compiled step
     @staticmethod
     def _num_chains(batch):
-        want = int(os.environ.get("B200DM_CHAINS", "2"))
+        # default 1: measured on B200 (cfg-2, B=8) 1 chain 4.98 ms/step, 2 chains 5.22, 4 chains 5.31 -- the persistent
+        # 148-CTA conv kernels of one chain leave no SMs for the other chain's small kernels, and smaller sub-batches
+        # make the 8^3-level GEMM grids even thinner
+        want = int(os.environ.get("B200DM_CHAINS", "1"))
         c = max(1, min(want, batch))
         while batch % c:
             c -= 1
