@@ -720,6 +720,24 @@ extern "C" int b200dm_conv_plan_set_trace(b200dm_conv_plan* p, void* trace) {
 
 extern "C" double b200dm_conv_plan_flops(const b200dm_conv_plan* p) { return p ? p->flops : 0.0; }
 
+extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, const float* scale, const float* shift, int32_t act) {
+  B2_CHECK_ARG(p && y_extra && scale && shift, "conv_plan_add_output: null argument");
+  B2_CHECK_ARG(p->desc.c_out % 16 == 0 && p->desc.reserved[1] == 0, "conv_plan_add_output: needs c_out %% 16 == 0 and a plain (non-transposed) store");
+  B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
+  if (!p->p.y2) { p->p.y2 = (__nv_bfloat16*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
+  else if (!p->p.y3) { p->p.y3 = (__nv_bfloat16*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
+  else { b200dm_set_error("conv_plan_add_output: at most two extra outputs"); return B200DM_ERR_UNSUPPORTED; }
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_conv_plan_info(const b200dm_conv_plan* p, int32_t* halo, int32_t* block_n, int32_t* ksplit) {
+  B2_CHECK_ARG(p, "conv_plan_info: null plan");
+  if (halo) *halo = p->halo ? 1 : 0;
+  if (block_n) *block_n = p->g.block_n;
+  if (ksplit) *ksplit = p->p.ksplit;
+  return B200DM_OK;
+}
+
 extern "C" int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float* scale, const float* shift) {
   B2_CHECK_ARG(p, "conv_plan_set_out_affine: null plan");
   B2_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_plan_set_out_affine: give both scale and shift, or neither");

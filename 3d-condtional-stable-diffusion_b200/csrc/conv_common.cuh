@@ -27,6 +27,11 @@ struct ConvParams {
   const __nv_bfloat16* residual;
   const __nv_bfloat16* prelu_alpha;  // (d,h,w,c) bf16, no batch dim
   void* y;
+  // up to two EXTRA bf16 outputs of the same shape: y_k = act_k(scale_k[co] * v + shift_k[co]) of the final value v --
+  // the folded BatchNorm (+ swish) of the tensor's consumers, written by the producer so that no separate
+  // normalisation pass ever re-reads the tensor
+  __nv_bfloat16* y2; const float* scale2; const float* shift2; int act2;
+  __nv_bfloat16* y3; const float* scale3; const float* shift3; int act3;
   int* dbg;
   long long* trace;                  // optional per-role clock64 timeline of CTA 0 (tuning aid), else nullptr
 };
@@ -41,6 +46,22 @@ __device__ __forceinline__ void trace_ev(const ConvParams& p, int region, int& i
 }
 
 __device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+
+// one extra normalised copy of 16 channels: act(scale * v + shift) -> bf16
+__device__ __forceinline__ void extra_output16(const float (&v)[16], __nv_bfloat16* yo, const float* sc, const float* sh, int act) {
+  float w[16];
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(sc + j)), b = __ldg(reinterpret_cast<const float4*>(sh + j));
+    w[j] = fmaf(a.x, v[j], b.x); w[j + 1] = fmaf(a.y, v[j + 1], b.y); w[j + 2] = fmaf(a.z, v[j + 2], b.z); w[j + 3] = fmaf(a.w, v[j + 3], b.w);
+  }
+  if (act != B200DM_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = apply_act(w[j], act);
+  }
+  *reinterpret_cast<bf16x8*>(yo) = pack8(*reinterpret_cast<float(*)[8]>(&w[0]));
+  *reinterpret_cast<bf16x8*>(yo + 8) = pack8(*reinterpret_cast<float(*)[8]>(&w[8]));
+}
 
 // Epilogue for 16 consecutive accumulator columns of one output voxel (thread = TMEM lane = GEMM row):
 //   + bias[co] + chan_bias[t][n][co]  ->  * out_scale[co] + out_shift[co]  ->  PReLU(alpha[voxel][co])  ->  act  ->
@@ -117,6 +138,8 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
       *reinterpret_cast<bf16x8*>(yo) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
       *reinterpret_cast<bf16x8*>(yo + 8) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
     }
+    if (p.y2) extra_output16(v, p.y2 + row_off + col0, p.scale2 + col0, p.shift2 + col0, p.act2);
+    if (p.y3) extra_output16(v, p.y3 + row_off + col0, p.scale3 + col0, p.shift3 + col0, p.act3);
   } else {
     // scalar path: ragged channel tail (e.g. C_out = 1) or per-sample transposed store
 #pragma unroll

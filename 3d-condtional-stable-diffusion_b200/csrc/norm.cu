@@ -50,20 +50,36 @@ __global__ void __launch_bounds__(256) norm_act_kernel(b200dm_norm_desc d, const
   const __nv_bfloat16* s1 = x1 ? x1 + (int64_t)n * d.voxels * d.c1 : nullptr;
   __nv_bfloat16* yo = y + (int64_t)n * d.voxels * C;
   const int act = d.act;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t v = i / c8n;
-    const int c8 = (int)(i - v * c8n);
-    const bf16x8 p = (c8 < c08) ? *reinterpret_cast<const bf16x8*>(s0 + v * d.c0 + (c8 << 3))
-                                : *reinterpret_cast<const bf16x8*>(s1 + v * d.c1 + ((c8 - c08) << 3));
-    float f[8];
-    unpack8(p, f);
-    const float4 a0 = *reinterpret_cast<const float4*>(sa + (c8 << 3)), a1 = *reinterpret_cast<const float4*>(sa + (c8 << 3) + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(sb + (c8 << 3)), b1 = *reinterpret_cast<const float4*>(sb + (c8 << 3) + 4);
-    f[0] = apply_act(fmaf(f[0], a0.x, b0.x), act); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), act);
-    f[2] = apply_act(fmaf(f[2], a0.z, b0.z), act); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), act);
-    f[4] = apply_act(fmaf(f[4], a1.x, b1.x), act); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), act);
-    f[6] = apply_act(fmaf(f[6], a1.z, b1.z), act); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), act);
-    *reinterpret_cast<bf16x8*>(yo + v * C + (c8 << 3)) = pack8(f);
+  // 4 independent 16-byte vectors per thread per trip (loads issued before any use), 32-bit index arithmetic
+  // (total < 2^31 vectors per sample is checked on the host): the pass is a pure HBM stream.
+  constexpr int U = 4;
+  const uint32_t tot32 = (uint32_t)total, stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < tot32; i0 += stride * U) {
+    bf16x8 pk[U];
+    uint32_t vv[U], cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * stride;
+      vv[u] = i / (uint32_t)c8n;
+      cc[u] = i - vv[u] * (uint32_t)c8n;
+      if (i < tot32)
+        pk[u] = ((int)cc[u] < c08) ? *reinterpret_cast<const bf16x8*>(s0 + (int64_t)vv[u] * d.c0 + (cc[u] << 3))
+                                   : *reinterpret_cast<const bf16x8*>(s1 + (int64_t)vv[u] * d.c1 + ((cc[u] - c08) << 3));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= tot32) break;
+      const int c8 = (int)cc[u];
+      float f[8];
+      unpack8(pk[u], f);
+      const float4 a0 = *reinterpret_cast<const float4*>(sa + (c8 << 3)), a1 = *reinterpret_cast<const float4*>(sa + (c8 << 3) + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + (c8 << 3)), b1 = *reinterpret_cast<const float4*>(sb + (c8 << 3) + 4);
+      f[0] = apply_act(fmaf(f[0], a0.x, b0.x), act); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), act);
+      f[2] = apply_act(fmaf(f[2], a0.z, b0.z), act); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), act);
+      f[4] = apply_act(fmaf(f[4], a1.x, b1.x), act); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), act);
+      f[6] = apply_act(fmaf(f[6], a1.z, b1.z), act); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), act);
+      *reinterpret_cast<bf16x8*>(yo + (int64_t)vv[u] * C + (c8 << 3)) = pack8(f);
+    }
   }
 }
 
@@ -347,7 +363,8 @@ extern "C" int b200dm_norm_act_fwd(const b200dm_norm_desc* d, const void* x0, co
   B2_CHECK_ARG(d->kind == 0 || mean_rstd, "norm_act_fwd: group norm needs mean_rstd");
   const int C = d->c0 + d->c1;
   const int64_t items = d->voxels * (C >> 3);
-  int gx = grid_for(items, 256, 8);
+  B2_CHECK_ARG(items < (1ll << 31), "norm_act_fwd: more than 2^31 16-byte vectors per sample");
+  int gx = grid_for((items * d->batch + 3) / 4, 256, 8);
   gx = (gx + d->batch - 1) / d->batch;
   if (gx < 1) gx = 1;
   B2_CHECK_CUDA(b2_launch(norm_act_kernel, dim3(gx, d->batch), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, 

@@ -224,6 +224,19 @@ class ConvPlan:
     def flops(self):
         return lib().b200dm_conv_plan_flops(self.h)
 
+    @property
+    def info(self):
+        halo, bn, ks = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().b200dm_conv_plan_info(self.h, C.byref(halo), C.byref(bn), C.byref(ks)))
+        return dict(halo=bool(halo.value), block_n=bn.value, ksplit=ks.value)
+
+    def add_output(self, y_extra, scale, shift, act=None):
+        """Extra bf16 output act(scale*v + shift) of the final value (the consumer's folded BatchNorm), same shape as y."""
+        assert y_extra.shape == self.y.shape and y_extra.dtype == torch.bfloat16
+        check(lib().b200dm_conv_plan_add_output(self.h, ptr(y_extra), ptr(scale), ptr(shift), L.ACT[act]))
+        self.keep = self.keep + (y_extra, scale, shift)
+        return y_extra
+
     def run(self):
         check(lib().b200dm_conv_plan_run(self.h, stream()))
         return self.y

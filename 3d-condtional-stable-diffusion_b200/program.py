@@ -23,6 +23,7 @@ class Program:
         self.bytes = 0.0     # algorithmic HBM bytes of the elementwise ops per run
         self.log = []        # (kind, note) per op, for profiles / debugging
         self.outputs = {}    # note -> output tensor (layer-by-layer parity debugging)
+        self.producers = {}  # data_ptr of a conv output -> its ConvPlan (extra normalised outputs are attached there)
 
     # -- allocation helper
     def buf(self, shape, dtype=torch.bfloat16):
@@ -45,8 +46,25 @@ class Program:
         check(lib().b200dm_program_add_conv(self.h, plan.h))
         plan.release()
         self.keep.extend(t for t in plan.keep if t is not None)
-        self.log.append(("conv", note, plan.flops))
+        self.log.append(("conv" if not plan.info["halo"] else "conv_halo", note, plan.flops))
         self.outputs[note] = y
+        self.producers[y.data_ptr()] = plan
+        return y
+
+    def normalized_by_producer(self, t, scale, shift, act=None, note=""):
+        """act(scale*t + shift) as an extra output of the conv that produces ``t``; None if ``t`` is not a conv output or
+        the producer has no free output slot (the caller then runs a norm pass)."""
+        plan = self.producers.get(t.data_ptr())
+        if plan is None or t.dtype != torch.bfloat16 or t.shape[-1] % 16 != 0:
+            return None
+        y = self.buf(t.shape)
+        try:
+            plan.add_output(y, scale, shift, act)
+        except L.B200dmError:
+            return None
+        self.hold(scale, shift)
+        if note:
+            self.outputs[note] = y
         return y
 
     def norm_act(self, x0, a, b, y, act=None, x1=None, kind=0, groups=1, mean_rstd=None, note=""):

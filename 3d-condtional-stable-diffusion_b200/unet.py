@@ -16,6 +16,7 @@ computed once per generate() call.
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -151,6 +152,10 @@ class UNet:
         F, B, S = cfg.first_conv_channels, batch, cfg.img_size
         pr = Program(dev)
         self.prog = pr
+        # Producer-side normalisation (conv epilogues write the consumers' BN(+swish) copies as extra outputs) removes every
+        # norm pass, but measured SLOWER on B200 (cfg-2: 5.47 vs 5.08 ms/step): the extra stores lengthen the conv
+        # epilogues, which are on the critical path, by more than the streaming pass costs.  Off unless B200DM_FUSE_NORMS=1.
+        self.fuse_norms = os.environ.get("B200DM_FUSE_NORMS", "0") == "1"
         self.t_dev = t_dev if t_dev is not None else torch.zeros(2, dtype=torch.int32, device=dev)
         g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
 
@@ -188,10 +193,22 @@ class UNet:
             return pr.conv(desc, a, b, y, residual=residual, note=note)
 
         def bn_act(x0, name, act, x1=None, note=""):
+            """BatchNorm(inference) [+ swish] of x0 (or of the concat [x0, x1]) -> (y0, y1|None): the conv that reads it takes
+            the two channel segments separately.  When the sources are conv outputs the normalised copies are written by
+            the PRODUCERS' epilogues (extra outputs) and no pass runs here; otherwise one fused norm(+concat) pass."""
             sc, sh = ops.bn_fold(g(f"{name}.gamma"), g(f"{name}.beta"), g(f"{name}.mean"), g(f"{name}.var"), 1e-3)
-            C = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+            c0 = x0.shape[-1]
+            if self.fuse_norms:
+                y0 = pr.normalized_by_producer(x0, sc[:c0], sh[:c0], act, note=(note or name) if x1 is None else "")
+                if y0 is not None and x1 is None:
+                    return y0, None
+                if y0 is not None:
+                    y1 = pr.normalized_by_producer(x1, sc[c0:], sh[c0:], act)
+                    if y1 is not None:
+                        return y0, y1
+            C = c0 + (x1.shape[-1] if x1 is not None else 0)
             y = pr.buf((*x0.shape[:-1], C))
-            return pr.norm_act(x0, sc, sh, y, act=act, x1=x1, note=note or name)
+            return pr.norm_act(x0, sc, sh, y, act=act, x1=x1, note=note or name), None
 
         def resblock(b, x, skip):
             n, w = b["name"], b["cout"]
@@ -204,11 +221,11 @@ class UNet:
                 one, zero = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
                 res = pr.norm_act(x, one, zero, pr.buf((*x.shape[:-1], cin)), x1=skip, note=f"{n}.concat")
             table = ops.dense_f32(temb, g(f"{n}.temb.kernel"), g(f"{n}.temb.bias"), act_in="silu")  # (T, w)
-            h = bn_act(x, f"{n}.norm1", "silu", x1=skip)
+            h, h1 = bn_act(x, f"{n}.norm1", "silu", x1=skip)
             # conv1 + temb -> BN(norm2) -> swish (dm3d.py:237-244): conv1's output has no other reader, so norm2 and the
             # activation run in conv1's epilogue on the fp32 accumulator (one HBM pass and one bf16 rounding fewer)
             sc2, sh2 = ops.bn_fold(g(f"{n}.norm2.gamma"), g(f"{n}.norm2.beta"), g(f"{n}.norm2.mean"), g(f"{n}.norm2.var"), 1e-3)
-            h = conv(h, f"{n}.conv1", w, chan_bias=pr.hold(table), out_affine=(sc2, sh2), act="silu", note=f"{n}.conv1+norm2")
+            h = conv(h, f"{n}.conv1", w, x1=h1, chan_bias=pr.hold(table), out_affine=(sc2, sh2), act="silu", note=f"{n}.conv1+norm2")
             pr.outputs[f"{n}.norm2"] = h
             return conv(h, f"{n}.conv2", w, residual=res)
 
@@ -219,7 +236,7 @@ class UNet:
         def attn_block(b, x):  # AttentionBlock.call (dm3d.py:39-63)
             n, c, s = b["name"], b["c"], b["s"]
             Lq = s ** 3
-            nrm = bn_act(x, f"{n}.norm", None)
+            nrm, _ = bn_act(x, f"{n}.norm", None)
             q = conv(nrm, f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
             kk = conv(nrm, f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
             vT = conv(nrm, f"{n}.value", c, k=1, dense=True, transposed_store=True)
@@ -232,7 +249,7 @@ class UNet:
             n, c, s = b["name"], b["c"], b["s"]
             Lq = s ** 3
             scale = float(c) ** -0.5
-            nrm = bn_act(x, f"{n}.norm", None)
+            nrm, _ = bn_act(x, f"{n}.norm", None)
             h = conv(nrm, f"{n}.proj_in", c, k=1, act="relu")
             gam = [g(f"{n}.norm{i}.gamma") for i in (1, 2, 3)]
             bet = [g(f"{n}.norm{i}.beta") for i in (1, 2, 3)]
@@ -270,7 +287,7 @@ class UNet:
             elif k == "up":
                 x = conv(x, b["name"], b["c"], mode=L.CONV_PARITY)
             elif k == "out":
-                h = bn_act(x, "out.norm", "silu")
+                h, _ = bn_act(x, "out.norm", "silu")
                 conv(h, "out.conv", b["cout"], y=self.eps, y_dtype=torch.float32)
         torch.cuda.synchronize(dev)
         return self

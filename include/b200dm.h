@@ -207,6 +207,13 @@ double b200dm_conv_plan_flops(const b200dm_conv_plan* p);
  * ResidualBlock conv1 -> BN -> swish (dm3d.py:237-244) when the un-normalised tensor has no other reader.
  * NULL, NULL switches it off. */
 int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float* scale, const float* shift);
+/* Up to two EXTRA bf16 outputs with the shape of y: y_extra = act(scale[co] * v + shift[co]) of the final value v
+ * (after residual / post-act).  The producer writes the BatchNorm(+swish) its consumers would apply
+ * (dm3d.py:235-236 norm1 of the next ResidualBlock, the skip-connection half of an up-path norm1, dm3d.py:46 the
+ * attention block's norm, dm3d.py:371-372 the output norm), so those tensors are never re-read by a separate pass. */
+int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, const float* scale, const float* shift, int32_t act);
+/* which kernel / tile configuration the plan launches (profiling): halo 1 = persistent halo-reuse kernel */
+int b200dm_conv_plan_info(const b200dm_conv_plan* p, int32_t* halo, int32_t* block_n, int32_t* ksplit);
 /* tuning aid: device int64[4*2048] receiving CTA 0's per-role timeline ((clock64 << 8) | tag); NULL switches it off */
 int b200dm_conv_plan_set_trace(b200dm_conv_plan* p, void* trace);
 /* device-side watchdog flag: non-zero if any tcgen05/TMA pipeline wait timed out since last reset */

@@ -246,3 +246,28 @@ def test_conv_out_affine_fuses_consumer_batchnorm(cuda, B, S, cin, cout, halo):
                    y_dtype=torch.float32, use_halo=halo)
     _check_flag()
     _close(y, ref, what=f"conv3 + temb + BN + swish fused, B{B} S{S} {cin}->{cout}")
+
+
+@pytest.mark.parametrize("B,S,cin,cout,halo", [(2, 8, 64, 128, -1), (1, 16, 64, 64, 0)])
+def test_conv_extra_normalised_outputs(cuda, B, S, cin, cout, halo):
+    """b200dm_conv_plan_add_output: the producer also writes act(scale*y + shift) copies (its consumers' folded BatchNorm)."""
+    from b200dm import ops, _lib
+    g = torch.Generator().manual_seed(11)
+    x = _rand((B, S, S, S, cin), 1)
+    w = _rand((3, 3, 3, cin, cout), 2, 1.0 / np.sqrt(27 * cin))
+    b = torch.randn(cout, generator=g)
+    res = _rand((B, S, S, S, cout), 5)
+    s2, h2 = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    s3, h3 = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = O.conv3d(x, w, b) + res
+    desc = ops.make_conv_desc(_lib.CONV_DIRECT, B, (S, S, S), cin, 0, cout, 3, 1, use_halo=halo)
+    wp = ops.pack_conv_weights(desc, w).to(cuda)
+    y = torch.empty(B, S, S, S, cout, dtype=torch.bfloat16, device=cuda)
+    plan = ops.ConvPlan(desc, x.to(cuda, torch.bfloat16), wp, y, bias=b.to(cuda), residual=res.to(cuda, torch.bfloat16))
+    y2 = plan.add_output(torch.empty_like(y), s2.to(cuda), h2.to(cuda), "silu")
+    y3 = plan.add_output(torch.empty_like(y), s3.to(cuda), h3.to(cuda), None)
+    plan.run()
+    _check_flag()
+    _close(y, ref, tol=6e-3, what="main output")
+    _close(y2, O.swish(ref * s2 + h2), tol=8e-3, what="extra output 1 (BN + swish)")
+    _close(y3, ref * s3 + h3, tol=8e-3, what="extra output 2 (BN)")
