@@ -41,6 +41,12 @@ class VqDesc(C.Structure):
     _fields_ = [("n", C.c_int64), ("d", C.c_int32), ("k", C.c_int32), ("x_dtype", C.c_int32), ("q_dtype", C.c_int32)]
 
 
+class NormExDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("out_d", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32), ("c", C.c_int32),
+                ("kind", C.c_int32), ("groups", C.c_int32), ("act", C.c_int32), ("post_act", C.c_int32), ("upsample", C.c_int32),
+                ("x_dtype", C.c_int32), ("y_dtype", C.c_int32)]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("lq", C.c_int32), ("lk", C.c_int32), ("d", C.c_int32), ("scale", C.c_float),
                 ("reserved", C.c_int32 * 3)]
@@ -64,6 +70,11 @@ _SIGS = {
     "b200dm_gn_stats": (C.c_int, [C.POINTER(NormDesc), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200dm_gn_stats_workspace": (C.c_size_t, [C.POINTER(NormDesc)]),
     "b200dm_norm_act_fwd": (C.c_int, [C.POINTER(NormDesc)] + [C.c_void_p] * 7),
+    "b200dm_norm_act_ex": (C.c_int, [C.POINTER(NormExDesc)] + [C.c_void_p] * 8),
+    "b200dm_stats_f32_workspace": (C.c_size_t, [C.c_int32]),
+    "b200dm_stats_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200dm_program_add_norm_act_ex": (C.c_int, [C.c_void_p, C.POINTER(NormExDesc)] + [C.c_void_p] * 7),
+    "b200dm_program_add_stats_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200dm_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "b200dm_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "b200dm_vq_argmin_gather": (C.c_int, [C.POINTER(VqDesc)] + [C.c_void_p] * 7),

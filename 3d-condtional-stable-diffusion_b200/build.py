@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200dm.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "update.cu", "norm.cu", "vq.cu", "conv.cu", "attention.cu", "program.cu"]
+SOURCES = ["api.cu", "update.cu", "norm.cu", "norm_ex.cu", "vq.cu", "conv.cu", "attention.cu", "program.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-DB200DM_BUILD", "--expt-relaxed-constexpr"]

@@ -7,12 +7,14 @@
 #include "common.cuh"
 
 namespace {
-enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN };
+enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN, OP_NORM_EX, OP_STATS_F32 };
 struct Op {
   OpKind kind;
   b200dm_conv_plan* conv = nullptr;
   b200dm_attn_plan* attn = nullptr;
   b200dm_norm_desc nd{};
+  b200dm_norm_ex_desc ned{};
+  const void* p5 = nullptr;
   b200dm_update_desc ud{};
   const void* p0 = nullptr; const void* p1 = nullptr; const void* p2 = nullptr; const void* p3 = nullptr; const void* p4 = nullptr;
   void* out = nullptr; void* out2 = nullptr;
@@ -48,6 +50,25 @@ extern "C" void b200dm_program_destroy(b200dm_program* p) {
 extern "C" int b200dm_program_add_conv(b200dm_program* p, b200dm_conv_plan* plan) {
   B2_CHECK_ARG(p && plan, "program_add_conv: null argument");
   Op op; op.kind = OP_CONV; op.conv = plan;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_norm_act_ex(b200dm_program* p, const b200dm_norm_ex_desc* d, const void* x, const float* a,
+                                              const float* b, const float* mean_rstd, const void* prelu_alpha,
+                                              const void* residual, void* y) {
+  B2_CHECK_ARG(p && d && x && a && b && y, "program_add_norm_act_ex: null argument");
+  Op op; op.kind = OP_NORM_EX; op.ned = *d; op.p0 = x; op.p1 = a; op.p2 = b; op.p3 = mean_rstd; op.p4 = prelu_alpha; op.p5 = residual;
+  op.out = y;
+  p->ops.push_back(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_stats_f32(b200dm_program* p, const float* x, int32_t batch, int64_t per_sample, float eps,
+                                            float* mean_rstd, void* workspace, size_t ws_bytes) {
+  B2_CHECK_ARG(p && x && mean_rstd && workspace, "program_add_stats_f32: null argument");
+  Op op; op.kind = OP_STATS_F32; op.p0 = x; op.i1 = batch; op.i0 = per_sample; op.f0 = eps; op.out = mean_rstd; op.out2 = workspace;
+  op.ws = ws_bytes; op.launches = 2;
   p->ops.push_back(op);
   return B200DM_OK;
 }
@@ -168,6 +189,10 @@ static int run_op(Op& op, void* stream) {
         break;
       case OP_ADVANCE: rc = b200dm_step_advance((int32_t*)op.out, op.i1, stream); break;
       case OP_ATTN: rc = b200dm_attention_plan_run(op.attn, stream); break;
+      case OP_NORM_EX:
+        rc = b200dm_norm_act_ex(&op.ned, op.p0, (const float*)op.p1, (const float*)op.p2, (const float*)op.p3, op.p4, op.p5, op.out, stream);
+        break;
+      case OP_STATS_F32: rc = b200dm_stats_f32((const float*)op.p0, op.i1, op.i0, op.f0, (float*)op.out, op.out2, op.ws, stream); break;
     }
   }
   return rc;

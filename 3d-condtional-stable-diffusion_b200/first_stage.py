@@ -227,6 +227,147 @@ class AttnCpDecoder(_DecoderBase):
         return self
 
 
+class VqganFamilyDecoder(_DecoderBase):
+    """Decoders D2 / D3 / D4 (act_fn='prelu'):  'vqgan' networks/vqgan.py:378-475, 'gnorm' vqgan_gnorm.py:382-484,
+    'stride' vqgan_stride.py:376-480 (residual units :256-286 of each file).
+
+      stem   Conv3 -> [BN | GN(8,1e-6) | -] -> PReLU
+      level  R x relu(x + PReLU(Norm(Conv3(relu(Conv3 x)))))
+             'vqgan'/'gnorm': ConvT(k4,s2) -> [BN | GN] (-> PReLU unless last)
+             'stride':        Conv3D(k4,s1,'same') -> UpSampling3D(2) -> [GN(out/2,1e-6) if out<32] (-> PReLU unless last)
+    BatchNorm (inference) is folded into the preceding conv's weights; GroupNorm runs as statistics + one fused
+    norm -> PReLU -> +residual -> ReLU pass; the up-sampling is folded into that pass's read."""
+
+    def __init__(self, variant, in_channels, out_channels, num_channels, num_res_layers, num_res_channels, in_size,
+                 output_act=None):
+        assert variant in ("vqgan", "gnorm", "stride")
+        self.variant, self.cin, self.out_channels, self.R, self.in_size = variant, in_channels, out_channels, num_res_layers, in_size
+        self.ch, self.rch = list(reversed(num_channels)), list(reversed(num_res_channels))
+        self.output_act = output_act
+        s, c = in_size, self.ch[0]
+        sp = [("stem.kernel", (3, 3, 3, in_channels, c), "glorot"), ("stem.bias", (c,), "zeros")]
+        sp += self._norm_spec("stem.norm", self._stem_norm()[0], c) + [("stem.prelu.alpha", (s, s, s, c), "zeros")]
+        for i, c in enumerate(self.ch):
+            for j in range(self.R):
+                n, rc = f"level.{i}.res.{j}", self.rch[i]
+                sp += [(f"{n}.conv1.kernel", (3, 3, 3, c, rc), "glorot"), (f"{n}.conv1.bias", (rc,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, rc, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros")]
+                sp += self._norm_spec(f"{n}.norm", self._res_norm(c)[0], c) + [(f"{n}.prelu.alpha", (s, s, s, c), "zeros")]
+            last = i == len(self.ch) - 1
+            out = out_channels if last else self.ch[i + 1]
+            sp += [(f"level.{i}.up.kernel", (4, 4, 4, c, out) if variant == "stride" else (4, 4, 4, out, c), "glorot"),
+                   (f"level.{i}.up.bias", (out,), "zeros")]
+            s *= 2
+            sp += self._norm_spec(f"level.{i}.up.norm", self._up_norm(out)[0], out)
+            if not last:
+                sp += [(f"level.{i}.up.prelu.alpha", (s, s, s, out), "zeros")]
+        self.spec = sp
+        super().__init__()
+
+    # (kind, groups, eps) per site, as written in the reference files
+    def _stem_norm(self):
+        return {"vqgan": ("bn", 0, 1e-3), "gnorm": ("gn", 8, 1e-6), "stride": (None, 0, 0.0)}[self.variant]
+
+    def _res_norm(self, c):
+        if self.variant == "gnorm":
+            return ("gn", 1, 1e-3) if c == 2 else ("gn", 8, 1e-6)
+        return ("bn", 0, 1e-3)
+
+    def _up_norm(self, out):
+        if self.variant == "vqgan":
+            return ("bn", 0, 1e-3)
+        if self.variant == "gnorm":
+            return ("gn", int(out / 2), 1e-3) if out < 32 else ("gn", 8, 1e-6)
+        return ("gn", int(out / 2), 1e-6) if out < 32 else (None, 0, 0.0)
+
+    @staticmethod
+    def _norm_spec(name, kind, c):
+        if kind is None:
+            return []
+        sp = [(f"{name}.gamma", (c,), "ones"), (f"{name}.beta", (c,), "zeros")]
+        return sp + ([(f"{name}.mean", (c,), "zeros"), (f"{name}.var", (c,), "ones")] if kind == "bn" else [])
+
+    def compile(self, batch, in_size=None):
+        L.require_gpu()
+        assert in_size in (None, self.in_size), "per-voxel PReLU alphas lock the decoder to its build resolution"
+        P = self.params
+        self.device = dev = torch.device("cuda", torch.cuda.current_device())
+        pr = self.prog = Program(dev)
+        s = self.in_size
+        self.z_in = pr.buf((batch, s, s, s, self.cin))
+        alpha = lambda n: P[n].to(dev, torch.bfloat16).contiguous()  # noqa: E731
+        g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
+
+        def bn_fold(name, kernel, bias, eps, transposed=False):
+            """conv -> BN(inference) == conv with w' = w * scale[co], b' = b * scale + shift."""
+            scale = P[f"{name}.gamma"] * torch.rsqrt(P[f"{name}.var"] + eps)
+            shift = P[f"{name}.beta"] - P[f"{name}.mean"] * scale
+            k = kernel * (scale.view(1, 1, 1, -1, 1) if transposed else scale)
+            return k, bias * scale + shift
+
+        def gn_apply(h, name, groups, eps, y, **kw):
+            """GroupNorm statistics of h (taken BEFORE any up-sampling) + the fused apply pass into y."""
+            if groups < 1:
+                raise ValueError(f"{name}: GroupNormalization(groups={groups}) -- the reference layer cannot be built either")
+            if h.dtype == torch.float32:
+                if groups != 1:
+                    raise L.B200dmError(f"{name}: fp32 group norm supports one group (the 1-2 channel network output)")
+                mr = pr.stats_f32(h, eps, note=f"{name}.stats")
+            else:
+                mr = pr.gn_stats(h, groups, eps, note=f"{name}.stats")
+            return pr.norm_act_ex(h, g(f"{name}.gamma"), g(f"{name}.beta"), y, kind=1, groups=groups, mean_rstd=mr, note=name, **kw)
+
+        c = self.ch[0]
+        kind, groups, eps = self._stem_norm()
+        if kind == "bn":
+            k, b = bn_fold("stem.norm", P["stem.kernel"], P["stem.bias"], eps)
+            x = self._conv(pr, self.z_in, k, b, c, prelu_alpha=alpha("stem.prelu.alpha"), note="stem")
+        elif kind == "gn":
+            h = self._conv(pr, self.z_in, P["stem.kernel"], P["stem.bias"], c, note="stem")
+            x = gn_apply(h, "stem.norm", groups, eps, pr.buf(h.shape), prelu_alpha=alpha("stem.prelu.alpha"))
+        else:
+            x = self._conv(pr, self.z_in, P["stem.kernel"], P["stem.bias"], c, prelu_alpha=alpha("stem.prelu.alpha"), note="stem")
+        for i, c in enumerate(self.ch):
+            for j in range(self.R):
+                n = f"level.{i}.res.{j}"
+                h = self._conv(pr, x, P[f"{n}.conv1.kernel"], P[f"{n}.conv1.bias"], self.rch[i], act="relu", note=f"{n}.conv1")
+                kind, groups, eps = self._res_norm(c)
+                if kind == "bn":
+                    k, b = bn_fold(f"{n}.norm", P[f"{n}.conv2.kernel"], P[f"{n}.conv2.bias"], eps)
+                    x = self._conv(pr, h, k, b, c, prelu_alpha=alpha(f"{n}.prelu.alpha"), residual=x, post_act="relu", note=f"{n}.conv2")
+                else:
+                    h = self._conv(pr, h, P[f"{n}.conv2.kernel"], P[f"{n}.conv2.bias"], c, note=f"{n}.conv2")
+                    x = gn_apply(h, f"{n}.norm", groups, eps, pr.buf(h.shape), prelu_alpha=alpha(f"{n}.prelu.alpha"), residual=x,
+                                 post_act="relu")
+            last = i == len(self.ch) - 1
+            out = self.out_channels if last else self.ch[i + 1]
+            n = f"level.{i}.up"
+            kind, groups, eps = self._up_norm(out)
+            pa = None if last else alpha(f"{n}.prelu.alpha")
+            final_act = "relu" if (last and self.output_act) else None
+            y_dtype = torch.float32 if last else torch.bfloat16
+            B_, D_ = x.shape[0], x.shape[1]
+            if self.variant == "stride":
+                # Conv3D(k=4, s=1, 'same') at low resolution, then ONE pass: nearest x2 + [GN] + [PReLU]
+                h = self._conv(pr, x, P[f"{n}.kernel"], P[f"{n}.bias"], out, k=4, y_dtype=y_dtype, note=n)
+                y = pr.buf((B_, 2 * D_, 2 * D_, 2 * D_, out), y_dtype)
+                if kind == "gn":
+                    x = gn_apply(h, f"{n}.norm", groups, eps, y, prelu_alpha=pa, act=final_act, upsample=True)
+                else:
+                    one, zero = torch.ones(out, device=dev), torch.zeros(out, device=dev)
+                    x = pr.norm_act_ex(h, one, zero, y, prelu_alpha=pa, act=final_act, upsample=True, note=f"{n}.upsample")
+            elif kind == "bn":
+                k, b = bn_fold(f"{n}.norm", P[f"{n}.kernel"], P[f"{n}.bias"], eps, transposed=True)
+                x = self._conv(pr, x, k, b, out, k=4, mode=L.CONV_PARITY, prelu_alpha=pa, act=final_act, y_dtype=y_dtype,
+                               transposed=True, note=n)
+            else:
+                h = self._conv(pr, x, P[f"{n}.kernel"], P[f"{n}.bias"], out, k=4, mode=L.CONV_PARITY, y_dtype=y_dtype, transposed=True, note=n)
+                x = gn_apply(h, f"{n}.norm", groups, eps, pr.buf(h.shape, y_dtype), prelu_alpha=pa, act=final_act)
+        self.out = x
+        torch.cuda.synchronize(dev)
+        return self
+
+
 # ================================================================== model wrappers (constructor surface)
 class _NoEncoder:
     def __call__(self, *a, **k):
@@ -258,14 +399,24 @@ class VQVAE:
 
 
 class VQGAN:
-    """networks/vqgan_attn_cp.VQGAN surface for the path: 32^3 <-> 128^3 first stage with a 3-entry channel list."""
+    """The VQGAN constructor surface for the path.  ``variant`` selects the reference module:
+        'attn_cp' networks/vqgan_attn_cp.VQGAN (default; 32^3 <-> 128^3 with a 3-entry channel list, codebook (K,D))
+        'vqgan'   networks/vqgan.VQGAN (codebook (D,K))   'gnorm' networks/vqgan_gnorm.VQGAN   'stride' networks/vqgan_stride.VQGAN
+    The non-attn_cp decoders carry per-voxel PReLU alphas: ``latent_size`` fixes their resolution (Keras infers it from the
+    128^3 input)."""
 
     def __init__(self, in_channels=1, out_channels=1, num_channels=(32, 64, 128), num_res_layers=2, num_res_channels=None,
-                 num_embeddings=1024, embedding_dim=256, **_training_only):
-        self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
+                 num_embeddings=1024, embedding_dim=256, variant="attn_cp", latent_size=None, output_act=None, **_training_only):
+        self.num_embeddings, self.embedding_dim, self.variant = num_embeddings, embedding_dim, variant
         self.encoder = _NoEncoder()
-        self.decoder = AttnCpDecoder(embedding_dim, out_channels, num_channels)
-        self.quantizer = VectorQuantizer(num_embeddings, embedding_dim, layout="KD")
+        if variant == "attn_cp":
+            self.decoder = AttnCpDecoder(embedding_dim, out_channels, num_channels)
+        else:
+            if latent_size is None:
+                latent_size = 128 // (2 ** len(num_channels))
+            self.decoder = VqganFamilyDecoder(variant, embedding_dim, out_channels, num_channels, num_res_layers,
+                                              num_res_channels or num_channels, latent_size, output_act)
+        self.quantizer = VectorQuantizer(num_embeddings, embedding_dim, layout="DK" if variant == "vqgan" else "KD")
 
     def load_weights(self, path):
         p = Wt.load_npz(path)

@@ -88,6 +88,35 @@ class Program:
         self.log.append(("gn_stats", note, x.numel() * 2.0))
         return mr
 
+    def norm_act_ex(self, x, a, b, y, kind=0, groups=1, mean_rstd=None, prelu_alpha=None, residual=None, act=None, post_act=None,
+                    upsample=False, note=""):
+        """y = post_act(residual + act(PReLU(norm(x)))), x optionally nearest-upsampled x2; y (B,D,H,W,C) bf16 | fp32."""
+        d = L.NormExDesc()
+        d.batch, d.out_d, d.out_h, d.out_w, d.c = y.shape
+        d.kind, d.groups, d.act, d.post_act, d.upsample = kind, groups, L.ACT[act], L.ACT[post_act], int(upsample)
+        d.x_dtype, d.y_dtype = L.dt(x), L.dt(y)
+        check(lib().b200dm_program_add_norm_act_ex(self.h, C.byref(d), ptr(x), ptr(a), ptr(b), ptr(mean_rstd), ptr(prelu_alpha),
+                                                   ptr(residual), ptr(y)))
+        self.hold(x, a, b, mean_rstd, prelu_alpha, residual, y)
+        nbytes = float(x.numel() * x.element_size() + y.numel() * y.element_size() +
+                       (prelu_alpha.numel() * 2 if prelu_alpha is not None else 0) + (residual.numel() * 2 if residual is not None else 0))
+        self.bytes += nbytes
+        self.log.append(("norm_act", note, nbytes))
+        self.outputs[note] = y
+        return y
+
+    def stats_f32(self, x, eps, note=""):
+        """(mean, rstd) over each whole sample of an fp32 tensor -> fp32 (B, 1, 2)."""
+        B = x.shape[0]
+        ws_bytes = lib().b200dm_stats_f32_workspace(B)
+        ws = self.buf((ws_bytes // 8,), torch.float64)
+        mr = self.buf((B, 1, 2), torch.float32)
+        check(lib().b200dm_program_add_stats_f32(self.h, ptr(x), B, x[0].numel(), eps, ptr(mr), ptr(ws), ws_bytes))
+        self.hold(x)
+        self.bytes += x.numel() * 4.0
+        self.log.append(("gn_stats", note, x.numel() * 4.0))
+        return mr
+
     def layernorm(self, x, gammas, betas, ys, eps=1e-3, note=""):
         c = x.shape[-1]
         check(lib().b200dm_program_add_layernorm(self.h, ptr(x), x.numel() // c, c, eps, len(gammas), ops._ptr_array(gammas),

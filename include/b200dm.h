@@ -112,6 +112,28 @@ size_t b200dm_gn_stats_workspace(const b200dm_norm_desc* d);
 int b200dm_norm_act_fwd(const b200dm_norm_desc* d, const void* x0, const void* x1_or_null,
                         const float* scale_or_gamma, const float* shift_or_beta,
                         const float* mean_rstd_or_null, void* y, void* stream);
+/* Extended pass for the VQ-GAN decoder variants (vqgan.py:256-284,378-475; vqgan_gnorm.py:256-286,382-484;
+ * vqgan_stride.py:256-286,376-480):
+ *   y = post_act( residual + act( PReLU_alpha( norm(x) ) ) ),  x optionally read through a nearest x2 up-sampling
+ * (layers.UpSampling3D(2)); norm = per-channel affine (kind 0) or GroupNorm with given (mean, rstd) (kind 1).
+ * Replaces GroupNormalization -> PReLU -> Add -> ReLU and UpSampling3D -> GroupNormalization -> PReLU.
+ * alpha (out voxels, C) bf16 (Keras PReLU: one alpha per (d,h,w,c)); residual / y (B, out voxels, C). */
+typedef struct {
+  int32_t batch, out_d, out_h, out_w, c;
+  int32_t kind, groups;            /* 0 affine, 1 group norm */
+  int32_t act, post_act;           /* B200DM_ACT_* */
+  int32_t upsample;                /* 1: x has spatial size out/2 */
+  int32_t x_dtype, y_dtype;
+} b200dm_norm_ex_desc;
+int b200dm_norm_act_ex(const b200dm_norm_ex_desc* d, const void* x, const float* scale_or_gamma, const float* shift_or_beta,
+                       const float* mean_rstd_or_null, const void* prelu_alpha_or_null, const void* residual_or_null,
+                       void* y, void* stream);
+/* whole-sample mean / rstd of an fp32 tensor (GroupNormalization with one group over the 1-2 channel network output,
+ * vqgan_gnorm.py:460-461): mean_rstd fp32[B][2]; deterministic two-stage reduction, fp64 combine */
+size_t b200dm_stats_f32_workspace(int32_t batch);
+int b200dm_stats_f32(const float* x, int32_t batch, int64_t per_sample, float eps, float* mean_rstd, void* workspace,
+                     size_t ws_bytes, void* stream);
+
 /* LayerNormalization(axis=-1, eps) with up to 3 (gamma,beta) sets applied to ONE read of x:
  * CrossAttentionBlock.norm1/2/3 (conditional_dm3d.py:125-127,191-193).  x,y bf16 (rows, C). */
 int b200dm_layernorm_fwd(const void* x, int64_t rows, int32_t c, float eps, int32_t n_out,
@@ -255,6 +277,11 @@ int b200dm_program_add_gn_stats(b200dm_program* p, const b200dm_norm_desc* d, co
 int b200dm_program_add_layernorm(b200dm_program* p, const void* x, int64_t rows, int32_t c, float eps,
                                  int32_t n_out, const float* const* gammas, const float* const* betas,
                                  void* const* ys);
+int b200dm_program_add_norm_act_ex(b200dm_program* p, const b200dm_norm_ex_desc* d, const void* x, const float* a, const float* b,
+                                   const float* mean_rstd_or_null, const void* prelu_alpha_or_null,
+                                   const void* residual_or_null, void* y);
+int b200dm_program_add_stats_f32(b200dm_program* p, const float* x, int32_t batch, int64_t per_sample, float eps,
+                                 float* mean_rstd, void* workspace, size_t ws_bytes);
 int b200dm_program_add_attention(b200dm_program* p, b200dm_attn_plan* plan /* ownership moves */);
 int b200dm_program_add_softmax(b200dm_program* p, const float* s, void* p_bf16, int64_t rows,
                                int32_t cols, float scale);

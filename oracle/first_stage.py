@@ -174,3 +174,102 @@ def monai_vqvae_param_count(in_channels, out_channels, num_channels, num_res_lay
             tr += n
     tr += embedding_dim * num_embeddings
     return tr, nt
+
+
+# ------------------------------------------------------------------ decoders D2 / D3 / D4 (vqgan, vqgan_gnorm, vqgan_stride)
+class VqganFamilyDecoder:
+    """The three VQ-GAN decoder variants that share one block list (act_fn='prelu', the scripts' default):
+
+      'vqgan'  (D2, networks/vqgan.py:378-475, res unit :256-284)   stem Conv3 -> BN -> PReLU;  ConvT(k4,s2) -> BN [-> PReLU]
+      'gnorm'  (D3, networks/vqgan_gnorm.py:382-484, :256-286)       BN -> GroupNorm: GN(8, eps 1e-6); res unit GN(groups=1,
+               default eps 1e-3) when its width is 2; after ConvT GN(int(out/2), default eps 1e-3) when out < 32
+      'stride' (D4, networks/vqgan_stride.py:376-480, :256-286)      stem Conv3 -> PReLU (no norm); res unit with BN;
+               Conv3D(k=4, s=1, 'same' = pad (1,2)) -> UpSampling3D(2) -> [GN(int(out/2), eps 1e-6) if out < 32] [-> PReLU]
+    Res unit everywhere: relu(x + PReLU(Norm(Conv3(relu(Conv3(x)))))).  PReLU has one alpha per (d,h,w,c) element.
+    The level's activation is skipped after the last level; `output_act` appends a ReLU."""
+
+    def __init__(self, variant, in_channels, out_channels, num_channels, num_res_layers, num_res_channels, in_size,
+                 output_act=None):
+        assert variant in ("vqgan", "gnorm", "stride")
+        self.variant, self.cin, self.cout = variant, in_channels, out_channels
+        self.ch, self.rch = list(reversed(num_channels)), list(reversed(num_res_channels))
+        self.R, self.s0, self.output_act = num_res_layers, in_size, output_act
+
+    # (kind, groups, eps) of the normalisation at each site; kind None = no norm
+    def stem_norm(self):
+        return {"vqgan": ("bn", 0, 1e-3), "gnorm": ("gn", 8, 1e-6), "stride": (None, 0, 0.0)}[self.variant]
+
+    def res_norm(self, c):
+        if self.variant == "gnorm":
+            return ("gn", 1, 1e-3) if c == 2 else ("gn", 8, 1e-6)
+        return ("bn", 0, 1e-3)
+
+    def up_norm(self, out):
+        if self.variant == "vqgan":
+            return ("bn", 0, 1e-3)
+        if self.variant == "gnorm":
+            return ("gn", int(out / 2), 1e-3) if out < 32 else ("gn", 8, 1e-6)
+        return ("gn", int(out / 2), 1e-6) if out < 32 else (None, 0, 0.0)
+
+    @staticmethod
+    def _norm_spec(name, kind, c):
+        if kind is None:
+            return []
+        sp = [(f"{name}.gamma", (c,), "ones"), (f"{name}.beta", (c,), "zeros")]
+        if kind == "bn":
+            sp += [(f"{name}.mean", (c,), "zeros"), (f"{name}.var", (c,), "ones")]
+        return sp
+
+    def spec(self):
+        s, c = self.s0, self.ch[0]
+        sp = [("stem.kernel", (3, 3, 3, self.cin, c), "glorot"), ("stem.bias", (c,), "zeros")]
+        sp += self._norm_spec("stem.norm", self.stem_norm()[0], c) + [("stem.prelu.alpha", (s, s, s, c), "zeros")]
+        for i, c in enumerate(self.ch):
+            for j in range(self.R):
+                n, rc = f"level.{i}.res.{j}", self.rch[i]
+                sp += [(f"{n}.conv1.kernel", (3, 3, 3, c, rc), "glorot"), (f"{n}.conv1.bias", (rc,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, rc, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros")]
+                sp += self._norm_spec(f"{n}.norm", self.res_norm(c)[0], c) + [(f"{n}.prelu.alpha", (s, s, s, c), "zeros")]
+            last = i == len(self.ch) - 1
+            out = self.cout if last else self.ch[i + 1]
+            if self.variant == "stride":
+                sp += [(f"level.{i}.up.kernel", (4, 4, 4, c, out), "glorot")]
+            else:
+                sp += [(f"level.{i}.up.kernel", (4, 4, 4, out, c), "glorot")]
+            sp += [(f"level.{i}.up.bias", (out,), "zeros")]
+            s *= 2
+            sp += self._norm_spec(f"level.{i}.up.norm", self.up_norm(out)[0], out)
+            if not last:
+                sp += [(f"level.{i}.up.prelu.alpha", (s, s, s, out), "zeros")]
+        return sp
+
+    @staticmethod
+    def _norm(P, name, x, kind, groups, eps):
+        if kind is None:
+            return x
+        if kind == "bn":
+            return ops.batchnorm_infer(x, P[f"{name}.gamma"], P[f"{name}.beta"], P[f"{name}.mean"], P[f"{name}.var"], eps)
+        return ops.groupnorm(x, P[f"{name}.gamma"], P[f"{name}.beta"], groups, eps)
+
+    def forward(self, P, z, emu: Emu = EXACT):
+        x = ops.conv3d(emu.a(z), emu.w(P["stem.kernel"]), P["stem.bias"])
+        x = emu.a(ops.prelu(self._norm(P, "stem.norm", x, *self.stem_norm()), P["stem.prelu.alpha"]))
+        for i, c in enumerate(self.ch):
+            for j in range(self.R):
+                n = f"level.{i}.res.{j}"
+                h = emu.a(torch.relu(ops.conv3d(x, emu.w(P[f"{n}.conv1.kernel"]), P[f"{n}.conv1.bias"])))
+                h = ops.conv3d(h, emu.w(P[f"{n}.conv2.kernel"]), P[f"{n}.conv2.bias"])
+                h = self._norm(P, f"{n}.norm", h, *self.res_norm(c))
+                x = emu.a(torch.relu(x + ops.prelu(h, P[f"{n}.prelu.alpha"])))
+            last = i == len(self.ch) - 1
+            out = self.cout if last else self.ch[i + 1]
+            if self.variant == "stride":
+                x = ops.upsample_nearest2(ops.conv3d(x, emu.w(P[f"level.{i}.up.kernel"]), P[f"level.{i}.up.bias"]))
+            else:
+                x = ops.conv3d_transpose(x, emu.w(P[f"level.{i}.up.kernel"]), P[f"level.{i}.up.bias"])
+            x = self._norm(P, f"level.{i}.up.norm", x, *self.up_norm(out))
+            if not last:
+                x = emu.a(ops.prelu(x, P[f"level.{i}.up.prelu.alpha"]))
+        if self.output_act:
+            x = torch.relu(x)
+        return x

@@ -90,6 +90,18 @@ def test_first_stage_tables_match_oracle():
     assert [(n, tuple(s)) for n, s, _ in mv.decoder.spec] == [(n, tuple(s)) for n, s, _ in om.spec()]
 
 
+@pytest.mark.parametrize("variant", ["vqgan", "gnorm", "stride"])
+def test_vqgan_family_tables_match_oracle(variant):
+    vq = b200dm.VQGAN(in_channels=2, out_channels=2, num_channels=(32, 64, 128), num_res_layers=3, num_res_channels=(32, 64, 128),
+                      num_embeddings=256, embedding_dim=64, variant=variant)
+    od = OF.VqganFamilyDecoder(variant, 64, 2, (32, 64, 128), 3, (32, 64, 128), 16)
+    assert [(n, tuple(s)) for n, s, _ in vq.decoder.spec] == [(n, tuple(s)) for n, s, _ in od.spec()]
+    assert vq.quantizer.layout == ("DK" if variant == "vqgan" else "KD")      # vqgan.py:164-170 vs vqgan_gnorm.py:164-170
+    # an out_channels=1 gnorm/stride decoder asks for GroupNormalization(groups=0): unbuildable in the reference as well
+    if variant != "vqgan":
+        assert od.up_norm(1)[1] == 0
+
+
 # ----------------------------------------------------------------------------------------- DiffusionModel host surface
 def _args(T=20, n=1, bs=2):
     return types.SimpleNamespace(timesteps=T, num_gpus=n, kernel_resize=False, bs=bs)

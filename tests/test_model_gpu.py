@@ -165,3 +165,27 @@ def test_attn_cp_decoder_and_quantize(cuda):
     r_e, r_x = rel(y, od.forward(P, q_ref, Emu(True))), rel(y, od.forward(P, q_ref))
     print(f"attn_cp decoder: rel-L2 vs emu {r_e:.3e}, vs fp32 {r_x:.3e}")
     assert r_e <= 8e-3 and r_x <= 3e-2
+
+
+@pytest.mark.parametrize("variant", ["vqgan", "gnorm", "stride"])
+@pytest.mark.parametrize("channels", [(32, 64), (16, 32)])
+def test_vqgan_family_decoders(cuda, variant, channels):
+    """Decoders D2 / D3 / D4 (vqgan.py, vqgan_gnorm.py, vqgan_stride.py; in/out channels 2 as in the main_exp_* scripts) vs
+    the oracle: BN folds, GroupNorm + per-voxel PReLU + residual passes, ConvT / conv4+upsample, 2-channel fp32 output with a
+    one-group GroupNorm.  (16, 32) exercises the `out < 32` GroupNorm sites.  Same tolerances as the other decoders."""
+    import b200dm
+    D = 16
+    vq = b200dm.VQGAN(in_channels=2, out_channels=2, num_channels=channels, num_res_layers=1, num_res_channels=channels,
+                      num_embeddings=64, embedding_dim=D, variant=variant, latent_size=4)
+    od = OF.VqganFamilyDecoder(variant, D, 2, channels, 1, channels, 4)
+    assert [(n, tuple(s)) for n, s, _ in vq.decoder.spec] == [(n, tuple(s)) for n, s, _ in od.spec()]
+    P = OI.make_params(od.spec(), 5, "stress")
+    vq.decoder.set_weights(P)
+    z = OI.normal((2, 4, 4, 4, D), 11, 0.5)
+    y = vq.decoder(z.to(cuda))
+    from b200dm import _lib
+    assert _lib.debug_flag() == 0
+    assert tuple(y.shape) == (2, 16, 16, 16, 2) and y.dtype == torch.float32
+    r_e, r_x = rel(y, od.forward(P, z, Emu(True))), rel(y, od.forward(P, z))
+    print(f"{variant} {channels} decoder: rel-L2 vs emu {r_e:.3e}, vs fp32 {r_x:.3e}")
+    assert r_e <= 1e-2 and r_x <= 3e-2

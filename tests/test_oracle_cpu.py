@@ -281,3 +281,18 @@ def test_bf16_emulation_is_close_to_exact():
     a, b = u.forward(P, x, t), u.forward(P, x, t, emu=O.Emu(True))
     r = ((a - b).norm() / a.norm()).item()
     assert 0 < r < 2.5e-2, r
+
+
+@pytest.mark.parametrize("variant", ["vqgan", "gnorm", "stride"])
+def test_vqgan_family_oracle_structure(variant):
+    """D2-D4 oracle: output doubles per level, keras-init (alpha = 0, gamma = 1) makes PReLU a ReLU, and with zero conv
+    weights the output is the norm/bias chain of a zero tensor (finite, sample-independent)."""
+    d = OF.VqganFamilyDecoder(variant, 16, 2, (32, 64), 1, (32, 64), 4)
+    P = OI.make_params(d.spec(), 5, "stress")
+    z = OI.normal((2, 4, 4, 4, 16), 1, 0.5)
+    y = d.forward(P, z)
+    assert y.shape == (2, 16, 16, 16, 2) and torch.isfinite(y).all()
+    one = d.forward(P, z[1:])
+    assert close(one, y[1:], rel=1e-5)                      # samples are independent (GN is per sample, BN is inference)
+    Pk = OI.make_params(d.spec(), 5, "keras")
+    assert all(float(v.abs().max()) == 0 for k, v in Pk.items() if k.endswith("alpha"))
