@@ -56,6 +56,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   // tile decode
   pdl_launch_dependents();
+  int tix = 0;   // timeline index of this thread's region (tuning aid: b200dm_conv_plan_set_trace)
+  if (threadIdx.x == 0) trace_ev(p, 3, tix, 40);
   constexpr bool CLUSTER = CMODE == 1;
   constexpr bool KSPLIT = CMODE == 2;
   const int ks = KSPLIT ? p.ksplit : 1;
@@ -97,7 +99,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   bool mid_synced = false;                // split-K: every thread of the cluster passes ONE mid-kernel cluster barrier
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) trace_ev(p, 3, tix, 41);
   pdl_wait();   // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  if (threadIdx.x == 0) trace_ev(p, 3, tix, 42);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -108,6 +112,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       int chunk = kb0 / p.ntaps, tap = kb0 % p.ntaps;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (!ptx::mbar_wait(empty_bar(s), phase ^ 1, p.dbg, 1)) break;
+        if (lane == 0 && kb == kb0) trace_ev(p, 3, tix, 43);
         if (ptx::elect_one()) {
           int ow, oh, od;
           if (p.mode == B200DM_CONV_PARITY) {
@@ -155,6 +160,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int kb = kb0; kb < kb1 && ok; ++kb) {
         ok = ptx::mbar_wait(full_bar(s), phase, p.dbg, 2);
         if (!ok) break;
+        if (lane == 0) trace_ev(p, 0, tix, 44);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t da = a_desc0 + (uint64_t)(s * (kStageBytes >> 4));
@@ -204,8 +210,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       stage_bias(p, bias_s, scale_s, n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 64);
       epilogue_bar_sync();
     }
+    if (warp == 2 && lane == 0) trace_ev(p, 1, tix, 45);
     const bool ok = ptx::mbar_wait(tmem_full_bar, 0, p.dbg, 3);
     ptx::tc_fence_after();
+    if (warp == 2 && lane == 0) trace_ev(p, 1, tix, 46);
     // split-K staging: partial accumulators as fp32 [col][row] in this CTA's (now idle) pipeline stages
     float* stage_f = reinterpret_cast<float*>(smem);
     if (KSPLIT && krank != 0) {
@@ -229,8 +237,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const int col0 = n_tile * BLOCK_N + c0;
           if (col0 >= p.c_out) break;  // warp-uniform
           uint32_t rr[16];
-          ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
-          ptx::tc_wait_ld();
+          if (p.epi_dbg < 2) {
+            ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
+            ptx::tc_wait_ld();
+          }
+          if (p.epi_dbg != 0) continue;
           if (KSPLIT) {
             for (int pr = 1; pr < ks; ++pr) {
               const uint32_t remote = ptx::mapa_shared(ptx::smem_u32(stage_f + c0 * 128 + r), (uint32_t)pr);
@@ -245,6 +256,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
   }
+  if (warp == 2 && lane == 0) trace_ev(p, 1, tix, 47);
   if (KSPLIT && !mid_synced) ptx::cluster_sync_all();   // producer / MMA warps: their half of the mid-kernel barrier
   ptx::tc_fence_before();
   __syncthreads();
@@ -253,6 +265,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
   if (CLUSTER || KSPLIT) ptx::cluster_sync_all();   // no CTA exits while a peer may still write / read its shared memory
+  if (threadIdx.x == 0) trace_ev(p, 3, tix, 48);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -324,6 +337,11 @@ int compute_geometry(const b200dm_conv_desc* d, Geometry* g) {
   else if (d->c_out <= 64) g->n_pad = 64;
   else g->n_pad = ((d->c_out + 127) / 128) * 128;
   g->block_n = g->n_pad < 128 ? g->n_pad : 128;
+  if (const char* e = getenv("B200DM_IGEMM_BN")) {   // tuning aid: narrower N tiles (more CTAs, shorter epilogues)
+    const int v = atoi(e);
+    if ((v == 64 || v == 32) && g->n_pad >= 128 && !(d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w >= 8 && d->in_h >= 16))
+      g->block_n = v;
+  }
   g->ktot = (size_t)(g->nch0 + g->nch1) * g->ntaps * 64;
   // M tile box, product 128
   if (d->mode == B200DM_CONV_BATCHED_GEMM) {

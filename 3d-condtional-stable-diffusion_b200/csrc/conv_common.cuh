@@ -39,7 +39,7 @@ struct ConvParams {
 // timeline regions (each kTraceRegion entries): 0 = MMA issuer, 1 = epilogue warp 4, 2 = slab producer, 3 = weight producer
 constexpr int kTraceRegion = 2048;
 __device__ __forceinline__ void trace_ev(const ConvParams& p, int region, int& idx, int tag) {
-  if (p.trace && blockIdx.x == 0 && idx < kTraceRegion - 1) {
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && idx < kTraceRegion - 1) {
     p.trace[region * kTraceRegion + idx] = (clock64() << 8) | (long long)(tag & 0xff);
     ++idx;
   }
