@@ -36,15 +36,19 @@ constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 template <int BLOCK_N, int NSTAGE, int CMODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                  const __grid_constant__ CUtensorMap mapB, const ConvParams p) {
+                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvOutMaps om, const ConvParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr int kResBytes = BLOCK_N >= 64 ? BLOCK_N * 256 : 0;   // staged epilogue: 128 rows x BLOCK_N bf16 residual tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * kStageBytes);
-  // bars[0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2NSTAGE] tmem_full; then tmem ptr
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+  const bool staged = BLOCK_N >= 64 && CMODE != 1 && p.tma_epi != 0;
+  const bool staged_res = staged && p.residual != nullptr;
+  uint8_t* res_smem = smem + NSTAGE * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_smem + (staged_res ? kResBytes : 0));
+  // bars[0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2NSTAGE] tmem_full, [2NSTAGE+1] residual tile; then tmem ptr
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 3);   // (+3 keeps bias_s 16-byte aligned)
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [2][BLOCK_N]: bias (+temb), output-affine scale
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,6 +57,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * NSTAGE);
+  const uint32_t res_bar = bar_base + 8u * (2 * NSTAGE + 1);
 
   // tile decode
   pdl_launch_dependents();
@@ -85,9 +90,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), cl_m * cl_n); }
     ptx::mbar_init(tmem_full_bar, 1);
+    ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
+    if (staged) ptx::prefetch_tmap(&om.y[blockIdx.z]);
   }
   if (warp == 1) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), kTmemCols);
@@ -110,6 +117,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                         n_tile * BLOCK_N;
       uint32_t s = 0, phase = 0;
       int chunk = kb0 / p.ntaps, tap = kb0 % p.ntaps;
+      if (BLOCK_N >= 64 && staged_res && krank == 0 && ptx::elect_one()) {
+        // residual tile (same box as the output tile) -> smem, consumed by the epilogue long after it has landed
+        int ng = 0;
+        for (int g = 0; g < BLOCK_N / 64; ++g) if (n_tile * BLOCK_N + g * 64 < p.c_out) ++ng;
+        ptx::mbar_expect_tx(res_bar, (uint32_t)ng * 16384u);
+        for (int g = 0; g < ng; ++g)
+          ptx::tma_load_5d(ptx::smem_u32(res_smem) + g * 16384, &om.r, res_bar, n_tile * BLOCK_N + g * 64, w0, h0, d0, n0);
+      }
+      __syncwarp();
       for (int kb = kb0; kb < kb1; ++kb) {
         if (!ptx::mbar_wait(empty_bar(s), phase ^ 1, p.dbg, 1)) break;
         if (lane == 0 && kb == kb0) trace_ev(p, 3, tix, 43);
@@ -224,14 +240,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
           ptx::tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) stage_f[(c0 + j) * 128 + r] = __uint_as_float(rr[j]);
+          for (int j = 0; j < 16; j += 4)   // [col / 4][row] float4: conflict-free 16-byte accesses on both sides
+            *reinterpret_cast<float4*>(stage_f + ((c0 + j) * 128 + r * 4)) =
+                make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3]));
         }
       }
       ptx::cluster_sync_all();   // release: the leader may now read the staging through DSMEM
       mid_synced = true;
     } else {
       if (KSPLIT) { ptx::cluster_sync_all(); mid_synced = true; }   // acquire: every peer's partial tile is staged
-      if (ok) {
+      if (BLOCK_N >= 64 && staged) {
+        // ---- staged epilogue: 64-column groups -> bf16 SWIZZLE_128B tile in the (idle) pipeline stages -> one TMA store
+        // per group.  Row-per-thread global stores touch 32 lines per instruction (measured ~1000 cycles per 16-column
+        // chunk); the TMA store writes whole 128-byte rows and clips the ragged edges itself.
+        if (ok) {
+          if (staged_res) ptx::mbar_wait(res_bar, 0, p.dbg, 4);
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+          for (int g = 0; g < BLOCK_N / 64; ++g) {
+            const int colg = n_tile * BLOCK_N + g * 64;
+            if (colg >= p.c_out) break;   // CTA-uniform (c_out % 64 == 0 on this path)
+            uint8_t* stg = smem + g * kStageBytes;
+            const uint8_t* rs = staged_res ? res_smem + g * 16384 : nullptr;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = g * 64 + h * 32;
+              uint32_t ra[16], rb[16];
+              ptx::tc_ld_32x32b_x16(trow + (uint32_t)c0, ra);
+              ptx::tc_ld_32x32b_x16(trow + (uint32_t)c0 + 16, rb);
+              ptx::tc_wait_ld();
+              if (KSPLIT) {
+                for (int pr = 1; pr < ks; ++pr) {
+                  const uint32_t remote = ptx::mapa_shared(ptx::smem_u32(stage_f + c0 * 128 + r * 4), (uint32_t)pr);
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4) {
+                    const float4 a4 = ptx::ld_dsmem_f32x4(remote + j * 512), b4 = ptx::ld_dsmem_f32x4(remote + (16 + j) * 512);
+                    ra[j] = __float_as_uint(__uint_as_float(ra[j]) + a4.x); ra[j + 1] = __float_as_uint(__uint_as_float(ra[j + 1]) + a4.y);
+                    ra[j + 2] = __float_as_uint(__uint_as_float(ra[j + 2]) + a4.z); ra[j + 3] = __float_as_uint(__uint_as_float(ra[j + 3]) + a4.w);
+                    rb[j] = __float_as_uint(__uint_as_float(rb[j]) + b4.x); rb[j + 1] = __float_as_uint(__uint_as_float(rb[j + 1]) + b4.y);
+                    rb[j + 2] = __float_as_uint(__uint_as_float(rb[j + 2]) + b4.z); rb[j + 3] = __float_as_uint(__uint_as_float(rb[j + 3]) + b4.w);
+                  }
+                }
+              }
+              conv_epilogue16_staged(p, ra, r, h * 32, n_tile * BLOCK_N + c0, has_bs ? bias_s + c0 : nullptr, cb,
+                                     p.out_scale ? scale_s + c0 : nullptr, rs, stg);
+              conv_epilogue16_staged(p, rb, r, h * 32 + 16, n_tile * BLOCK_N + c0 + 16, has_bs ? bias_s + c0 + 16 : nullptr, cb,
+                                     p.out_scale ? scale_s + c0 + 16 : nullptr, rs, stg);
+            }
+            ptx::fence_proxy_async();
+            epilogue_bar_sync();
+            if (threadIdx.x == 64) {
+              ptx::tma_store_5d(&om.y[parity], ptx::smem_u32(stg), colg, w0, h0, d0, n0);
+              ptx::bulk_commit_group();
+            }
+          }
+          if (threadIdx.x == 64) ptx::bulk_wait_read_all();
+        }
+      } else if (ok) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
           const int col0 = n_tile * BLOCK_N + c0;
@@ -244,9 +309,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           if (p.epi_dbg != 0) continue;
           if (KSPLIT) {
             for (int pr = 1; pr < ks; ++pr) {
-              const uint32_t remote = ptx::mapa_shared(ptx::smem_u32(stage_f + c0 * 128 + r), (uint32_t)pr);
+              const uint32_t remote = ptx::mapa_shared(ptx::smem_u32(stage_f + c0 * 128 + r * 4), (uint32_t)pr);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + ptx::ld_dsmem_f32(remote + j * 512));
+              for (int j = 0; j < 16; j += 4) {
+                const float4 a4 = ptx::ld_dsmem_f32x4(remote + j * 512);
+                rr[j] = __float_as_uint(__uint_as_float(rr[j]) + a4.x); rr[j + 1] = __float_as_uint(__uint_as_float(rr[j + 1]) + a4.y);
+                rr[j + 2] = __float_as_uint(__uint_as_float(rr[j + 2]) + a4.z); rr[j + 3] = __float_as_uint(__uint_as_float(rr[j + 3]) + a4.w);
+              }
             }
           }
           if (!valid) continue;
@@ -371,6 +440,7 @@ struct b200dm_conv_plan {
   Geometry g;
   ConvParams p;
   CUtensorMap mapA0, mapA1, mapB;
+  ConvOutMaps om;
   dim3 grid;
   size_t smem;
   int nstage;
@@ -461,13 +531,23 @@ extern "C" int b200dm_conv_pack_weights(const b200dm_conv_desc* d, const float* 
   return B200DM_OK;
 }
 
+static size_t conv_smem_bytes(int block_n, int nstage, bool staged_res) {
+  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (staged_res ? (size_t)block_n * 256 : 0) + (2 * nstage + 3) * 8 + 16 +
+         2 * block_n * 4;
+}
+
+static size_t conv_smem_attr(int block_n, int nstage) {   // opt-in ceiling of one kernel instantiation
+  const size_t v = conv_smem_bytes(block_n, nstage, true);
+  return v > 232448 ? 232448 : v;
+}
+
 template <int BLOCK_N, int NSTAGE>
 static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
   if (pl->p.ksplit > 1) {
     auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, 2>;
     static bool attr_set = false;
     if (!attr_set) {
-      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_attr(BLOCK_N, NSTAGE)));
       attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -478,14 +558,14 @@ static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
-    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->om, pl->p));
     return B200DM_OK;
   }
   if (pl->p.cl_m * pl->p.cl_n > 1) {
     auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, 1>;
     static bool attr_set = false;
     if (!attr_set) {
-      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_attr(BLOCK_N, NSTAGE)));
       attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -496,30 +576,31 @@ static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
-    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->om, pl->p));
     return B200DM_OK;
   }
   auto kern = conv_igemm_kernel<BLOCK_N, NSTAGE, 0>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_attr(BLOCK_N, NSTAGE)));
     attr_set = true;
   }
-  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om, pl->p));
   return B200DM_OK;
 }
 
-constexpr int kHaloNS = 6;
+constexpr int kHaloNS = 6;         // slab ring depth, direct-store epilogue
+constexpr int kHaloNSStaged = 5;   // staged epilogue: one slab less, the room holds the output staging tiles
 
-template <int BLOCK_N, int TD, int NB, int TPS>
+template <int BLOCK_N, int TD, int NB, int TPS, bool STAGED>
 static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
-  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, kHaloNS, NB, TPS>;
+  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, STAGED ? kHaloNSStaged : kHaloNS, NB, TPS, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     attr_set = true;
   }
-  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->p));
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
   return B200DM_OK;
 }
 
@@ -532,11 +613,17 @@ static void halo_ring_config(int block_n, int* nb, int* tps) {
 
 template <int BLOCK_N, int NB, int TPS>
 static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
-  return pl->halo_td == 2 ? launch_halo<BLOCK_N, 2, NB, TPS>(pl, s) : launch_halo<BLOCK_N, 1, NB, TPS>(pl, s);
+  if constexpr (BLOCK_N >= 64) {
+    if (pl->p.tma_epi) return pl->halo_td == 2 ? launch_halo<BLOCK_N, 2, NB, TPS, true>(pl, s) : launch_halo<BLOCK_N, 1, NB, TPS, true>(pl, s);
+  }
+  return pl->halo_td == 2 ? launch_halo<BLOCK_N, 2, NB, TPS, false>(pl, s) : launch_halo<BLOCK_N, 1, NB, TPS, false>(pl, s);
 }
 
-static size_t conv_smem_bytes(int block_n, int nstage) {
-  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (2 * nstage + 1) * 8 + 16 + 2 * block_n * 4;
+static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
+  const bool st = pl->p.tma_epi != 0;
+  const int ns = st ? kHaloNSStaged : kHaloNS;
+  return 1024 + (size_t)ns * halo::kSlabBytes + (size_t)pl->halo_nb * pl->halo_tps * pl->g.block_n * 128 +
+         (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
 }
 
 extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const void* x1, const void* w_packed,
@@ -670,12 +757,43 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     if (const char* e = getenv("B200DM_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 8 && (v & (v - 1)) == 0 && nkb / v >= 1) ksp = v; }
     if (ksp > 1) { p.ksplit = ksp; pl->grid.x = (unsigned)(mtiles * ksp); }
   }
-  // pipeline depth: enough bytes in flight to cover the L2->smem latency (B200DM_IGEMM_STAGES=4 restores the shallow ring)
-  // 4 stages; measured on B200: a deeper ring (B200DM_IGEMM_STAGES=8: 6 stages at BLOCK_N=128, 8 below) does not help
-  // at BLOCK_N=128 (not latency-bound) and hurts below 128, where 4 stages let two CTAs share an SM
+  // pipeline depth 4; measured on B200: a deeper ring (6 stages at BLOCK_N=128, 8 below) does not help at BLOCK_N=128 (the
+  // operand stream is bandwidth-, not latency-bound) and hurts below 128, where 4 stages let two CTAs share an SM
   pl->nstage = 4;
-  if (const char* e = getenv("B200DM_IGEMM_STAGES")) { if (atoi(e) == 8) pl->nstage = g.block_n >= 128 ? 6 : 8; }
-  pl->smem = conv_smem_bytes(g.block_n, pl->nstage);
+  // staged (TMA-store) epilogue of the per-tap GEMM kernel: bf16 NDHWC output with whole 64-channel groups
+  memset(&pl->om, 0, sizeof(pl->om));
+  {
+    bool want = cl_m * cl_n == 1 && d->y_dtype == B200DM_BF16 && d->reserved[1] == 0 && !prelu_alpha &&
+                d->c_out % 64 == 0 && g.block_n >= 64 && !(d->mode == B200DM_CONV_PARITY && residual);
+    if (const char* e = getenv("B200DM_TMA_EPI")) { if (atoi(e) == 0) want = false; }
+    if (want) {
+      const int par = d->mode == B200DM_CONV_PARITY ? 8 : 1;
+      const int ps = d->mode == B200DM_CONV_PARITY ? 2 : 1;   // output voxel stride of one M-space step
+      const cuuint64_t C = (cuuint64_t)d->c_out;
+      auto encodeY = [&](CUtensorMap* m, const void* base) -> bool {
+        cuuint64_t dims[5] = {C, (cuuint64_t)g.m_w, (cuuint64_t)g.m_h, (cuuint64_t)g.m_d, (cuuint64_t)d->batch};
+        cuuint64_t strides[4] = {C * 2 * ps, (cuuint64_t)g.out_w * C * 2 * ps, (cuuint64_t)g.out_h * g.out_w * C * 2 * ps,
+                                 (cuuint64_t)g.out_d * g.out_h * g.out_w * C * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)g.box_w, (cuuint32_t)g.box_h, (cuuint32_t)g.box_d, (cuuint32_t)g.box_n};
+        if (pl->halo) { box[1] = 8; box[2] = 16; box[3] = 1; box[4] = 1; }   // one output plane of the halo kernel's tile
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      };
+      bool okm = true;
+      for (int q = 0; q < par && okm; ++q) {
+        const size_t off = d->mode == B200DM_CONV_PARITY
+                               ? ((size_t)((q >> 2) & 1) * g.out_h * g.out_w + (size_t)((q >> 1) & 1) * g.out_w + (size_t)(q & 1)) * d->c_out * 2
+                               : 0;
+        okm = encodeY(&pl->om.y[q], (const char*)y + off);
+      }
+      if (okm && residual && !pl->halo) okm = encodeY(&pl->om.r, residual);
+      if (!okm) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(Y) failed"); return B200DM_ERR_CUDA; }
+      p.tma_epi = 1;
+    }
+  }
+  pl->smem = conv_smem_bytes(g.block_n, pl->nstage, p.tma_epi && residual);
+  if (pl->smem > 232448) { p.tma_epi = 0; pl->smem = conv_smem_bytes(g.block_n, pl->nstage, false); }
   if (pl->halo) {
     const int td = pl->halo_td;
     p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td; p.tiles_n = d->batch;
@@ -684,8 +802,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     int ctas = b2_num_sms();
     if (ctas > p.halo_total_tiles) ctas = p.halo_total_tiles;
     pl->grid = dim3((unsigned)ctas, 1, 1);
-    pl->smem = 1024 + (size_t)kHaloNS * halo::kSlabBytes + (size_t)pl->halo_nb * pl->halo_tps * g.block_n * 128 +
-               (2 * kHaloNS + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * g.block_n * 4;
+    pl->smem = halo_smem_bytes(pl);
   }
   // algorithmic FLOPs: 2*k^3*Cin*Cout*B*out_voxels; convT: 2*64*Cin*Cout*B*in_voxels; GEMM: 2*M*N*K
   if (d->mode == B200DM_CONV_PARITY)
@@ -708,20 +825,11 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
       case 128: return dispatch_halo<128, 4, 1>(pl, s);
     }
   }
-  if (pl->nstage == 4) {
-    switch (pl->g.block_n) {
-      case 16: return launch_conv<16, 4>(pl, s);
-      case 32: return launch_conv<32, 4>(pl, s);
-      case 64: return launch_conv<64, 4>(pl, s);
-      case 128: return launch_conv<128, 4>(pl, s);
-    }
-  } else {
-    switch (pl->g.block_n) {
-      case 16: return launch_conv<16, 8>(pl, s);
-      case 32: return launch_conv<32, 8>(pl, s);
-      case 64: return launch_conv<64, 8>(pl, s);
-      case 128: return launch_conv<128, 6>(pl, s);
-    }
+  switch (pl->g.block_n) {
+    case 16: return launch_conv<16, 4>(pl, s);
+    case 32: return launch_conv<32, 4>(pl, s);
+    case 64: return launch_conv<64, 4>(pl, s);
+    case 128: return launch_conv<128, 4>(pl, s);
   }
   b200dm_set_error("conv_plan_run: unsupported BLOCK_N %d", pl->g.block_n);
   return B200DM_ERR_UNSUPPORTED;
@@ -742,6 +850,7 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   B2_CHECK_ARG(p && y_extra && scale && shift, "conv_plan_add_output: null argument");
   B2_CHECK_ARG(p->desc.c_out % 16 == 0 && p->desc.reserved[1] == 0, "conv_plan_add_output: needs c_out %% 16 == 0 and a plain (non-transposed) store");
   B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
+  if (p->p.tma_epi) { p->p.tma_epi = 0; p->smem = p->halo ? halo_smem_bytes(p) : conv_smem_bytes(p->g.block_n, p->nstage, false); }
   if (!p->p.y2) { p->p.y2 = (__nv_bfloat16*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (__nv_bfloat16*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
   else { b200dm_set_error("conv_plan_add_output: at most two extra outputs"); return B200DM_ERR_UNSUPPORTED; }

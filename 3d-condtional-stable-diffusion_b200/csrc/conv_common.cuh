@@ -15,6 +15,7 @@ struct ConvParams {
   int act, post_act, y_f32, transposed_store;
   int chan_bias_rows;
   int halo_td, halo_tiles_per_ntile, halo_ntn, halo_total_tiles;   // halo kernel only
+  int tma_epi;                       // staged epilogue: bf16 tile -> swizzled smem -> TMA store (residual tile TMA-loaded)
   int epi_dbg;                       // tuning aid (B200DM_EPI_DBG): 1 = skip global stores, 2 = skip TMEM loads too
   int ksplit;                        // igemm split-K: cluster of ksplit CTAs per tile, each owns a K range (0/1 = off)
   int cl_m, cl_n;                    // igemm cluster: cl_m m-tiles share every B tile, cl_n n-tiles share every A tile
@@ -34,6 +35,12 @@ struct ConvParams {
   __nv_bfloat16* y3; const float* scale3; const float* shift3; int act3;
   int* dbg;
   long long* trace;                  // optional per-role clock64 timeline of CTA 0 (tuning aid), else nullptr
+};
+
+// Output-side tensor maps of the staged (TMA-store) epilogue: y[parity] (parity 0 only outside PARITY mode), r = residual.
+struct ConvOutMaps {
+  CUtensorMap y[8];
+  CUtensorMap r;
 };
 
 // timeline regions (each kTraceRegion entries): 0 = MMA issuer, 1 = epilogue warp 4, 2 = slab producer, 3 = weight producer
@@ -160,6 +167,64 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
       }
     }
   }
+}
+
+// Staged epilogue for 16 consecutive columns of GEMM row `r` (c_local = first column within the 64-column group):
+// same arithmetic as the vector path of conv_epilogue16 (no PReLU / fp32 / transposed forms -- the host never selects
+// the staged path for those), residual read from the TMA-loaded swizzled tile `rs`, result written as bf16 into the
+// swizzled staging tile `stg` ([128 rows][128 B], 16-byte chunk index XOR (row & 7) = CU_TENSOR_MAP_SWIZZLE_128B).
+__device__ __forceinline__ void conv_epilogue16_staged(const ConvParams& p, const uint32_t (&rr)[16], int r, int c_local, int col0,
+                                                       const float* bs, const float* cb, const float* sc, const uint8_t* rs,
+                                                       uint8_t* stg, bool has_rpre = false, const bf16x8* rpre = nullptr) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+  if (cb) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(cb + col0 + j));
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (sc) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+      v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+    }
+  }
+  if (bs) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (p.act != B200DM_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+  }
+  const int ch = c_local >> 3, sw = r & 7;
+  const uint32_t o0 = (uint32_t)r * 128u + (uint32_t)(((ch) ^ sw) << 4), o1 = (uint32_t)r * 128u + (uint32_t)(((ch + 1) ^ sw) << 4);
+  if (rs) {
+    float a[16];
+    unpack8(*reinterpret_cast<const bf16x8*>(rs + o0), *reinterpret_cast<float(*)[8]>(&a[0]));
+    unpack8(*reinterpret_cast<const bf16x8*>(rs + o1), *reinterpret_cast<float(*)[8]>(&a[8]));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += a[j];
+  } else if (has_rpre) {   // residual row already in registers (rpre is dereferenced only here: stays in registers)
+    float a[16];
+    unpack8(rpre[0], *reinterpret_cast<float(*)[8]>(&a[0]));
+    unpack8(rpre[1], *reinterpret_cast<float(*)[8]>(&a[8]));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += a[j];
+  }
+  if (p.post_act != B200DM_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+  }
+  *reinterpret_cast<bf16x8*>(stg + o0) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
+  *reinterpret_cast<bf16x8*>(stg + o1) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
 }
 
 // Stage bias[col] (+ chan_bias row `cbrow` when given) for columns [col_base, col_base + ncols) into shared memory.

@@ -50,10 +50,15 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int id) {
   return t;
 }
 
-template <int BLOCK_N, int TD, int NS, int NB, int TPS>
+// staged epilogue: output staging buffers (each holds one plane's BLOCK_N/64 column groups of 128 rows x 128 B)
+constexpr int stage_bufs(int block_n) { return block_n == 64 ? 2 : 1; }
+constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs(block_n) * (block_n / 64) * 16384 : 0; }
+
+template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const ConvParams p) {
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const ConvParams p) {
+  static_assert(!STAGED || BLOCK_N >= 64, "staged epilogue works on whole 64-channel groups");
   static_assert(TPS == 1 || TPS == 3, "taps per weight stage: 1 or 3");
   constexpr int kTapBytes = BLOCK_N * 128;
   constexpr int kBBytes = TPS * kTapBytes;
@@ -63,7 +68,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_ring = smem + NS * kSlabBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + NB * kBBytes);
+  uint8_t* stg_base = b_ring + NB * kBBytes;   // (1024-aligned: slabs and weight stages are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + stage_bytes(BLOCK_N, STAGED));
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [2 acc stages][bias | scale][BLOCK_N]
 
@@ -89,6 +95,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
+    if (STAGED) ptx::prefetch_tmap(&mapY);
   }
   if (warp == 2) {
     ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), kTmemCols);
@@ -232,6 +239,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const int64_t vox_per = (int64_t)p.out_d * p.out_h * p.out_w;
     uint32_t it = 0;
     int ti = 0;
+    uint32_t nstore = 0;   // staged epilogue: plane stores issued so far (selects the staging buffer)
     for (int id = first_tile; id < p.halo_total_tiles; id += tile_step, ++it) {
       const Tile t = decode_tile(p, id);
       const uint32_t as = it & 1;
@@ -271,6 +279,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         stage_bias(p, bs, scs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128, 256);
         epilogue_bar_sync256();
       }
+      if constexpr (STAGED) {
+        // bf16 plane tile -> swizzled smem -> one TMA store per 64-channel group (whole 128-byte rows, edges clipped by
+        // the TMA unit) instead of row-per-thread 16-byte stores that touch 32 lines per instruction
+        constexpr int kNG = BLOCK_N / 64, kBufs = stage_bufs(BLOCK_N);
+        const int grp = cbase >> 6, cl0 = cbase & 63;
+#pragma unroll
+        for (int pl = 0; pl < TD; ++pl) {
+          const int od = t.d0 + pl;
+          if (od >= p.out_d) break;   // CTA-uniform
+          uint8_t* stg = stg_base + ((nstore % kBufs) * kNG + grp) * 16384;
+          if (warp == 4 && lane == 0) {   // the store that last used this buffer has finished reading it
+            if (kBufs == 2) ptx::bulk_wait_read_1(); else ptx::bulk_wait_read_all();
+          }
+          epilogue_bar_sync256();
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N + cbase;
+#pragma unroll
+          for (int c = 0; c < kChunks; c += 2) {
+            const int col0 = colt + c * 16;
+            uint32_t ra[16], rb[16];
+            ptx::tc_ld_32x32b_x16(taddr + c * 16, ra);
+            ptx::tc_ld_32x32b_x16(taddr + c * 16 + 16, rb);
+            ptx::tc_wait_ld();
+            conv_epilogue16_staged(p, ra, r, cl0 + c * 16, col0, has_bs ? bs + cbase + c * 16 : nullptr, nullptr,
+                                   has_sc ? scs + cbase + c * 16 : nullptr, nullptr, stg, pre, rpre[pl][c]);
+            conv_epilogue16_staged(p, rb, r, cl0 + c * 16 + 16, col0 + 16, has_bs ? bs + cbase + c * 16 + 16 : nullptr, nullptr,
+                                   has_sc ? scs + cbase + c * 16 + 16 : nullptr, nullptr, stg, pre, rpre[pl][c + 1]);
+          }
+          ptx::fence_proxy_async();
+          epilogue_bar_sync256();
+          if (warp == 4 && lane == 0) {
+            for (int g = 0; g < kNG; ++g)
+              if (t.n_tile * BLOCK_N + g * 64 < p.c_out)
+                ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.n_tile * BLOCK_N + g * 64,
+                                  t.w0, t.h0, od, t.n);
+            ptx::bulk_commit_group();
+          }
+          ++nstore;
+        }
+      } else
       if (active) {
 #pragma unroll
         for (int pl = 0; pl < TD; ++pl) {
@@ -304,6 +351,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 12);
       if (lane == 0) ptx::mbar_arrive(tmem_empty(as));
     }
+    if (STAGED && warp == 4 && lane == 0) ptx::bulk_wait_read_all();   // smem must outlive the last store's reads
   }
   ptx::tc_fence_before();
   __syncthreads();
