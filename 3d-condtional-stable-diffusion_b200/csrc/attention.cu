@@ -60,14 +60,16 @@ struct Smem {
   static constexpr int kK = BKV * D * 2;                 // D/64 chunks of [BKV rows][128 B]
   static constexpr int kV = D * BKV * 2;                 // BKV/64 chunks of [D rows][128 B]
   static constexpr int kP = 128 * BKV * 2;               // BKV/64 chunks of [128 rows][128 B]
-  static constexpr int kBars = 1 + 4 * NST + 4 + 2 * NPB + 1;
+  static constexpr int kBars = 1 + 4 * NST + 4 + 2 * NPB + 2;
+  static_assert(NST * kK >= kQ, "the residual tile is staged in the (drained) K ring");
   static constexpr size_t kTotal = 1024 + kQ + (size_t)NST * (kK + kV) + (size_t)NPB * kP + kBars * 8 + 16;
 };
 
 template <int D, int BKV, int NST, int NPB>
 __global__ void __launch_bounds__(kThreads, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                  const __grid_constant__ CUtensorMap mapVt, const AttnParams p) {
+                  const __grid_constant__ CUtensorMap mapVt, const __grid_constant__ CUtensorMap mapO,
+                  const __grid_constant__ CUtensorMap mapR, const AttnParams p) {
   using SM = Smem<D, BKV, NST, NPB>;
   static_assert(D % 64 == 0 && D <= 256 && BKV % 64 == 0 && BKV <= 128, "tile shape");
   constexpr int kDC = D / 64, kKC = BKV / 64;
@@ -93,6 +95,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   auto p_full = [&](int b) { return bar_base + 8u * (1 + 4 * NST + 4 + b); };
   auto p_free = [&](int b) { return bar_base + 8u * (1 + 4 * NST + 4 + NPB + b); };
   const uint32_t o_done = bar_base + 8u * (1 + 4 * NST + 4 + 2 * NPB);
+  const uint32_t res_full = bar_base + 8u * (1 + 4 * NST + 4 + 2 * NPB + 1);
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,7 +110,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(s_full(b), 1); ptx::mbar_init(s_free(b), 4); }
     for (int b = 0; b < NPB; ++b) { ptx::mbar_init(p_full(b), 4); ptx::mbar_init(p_free(b), 1); }
     ptx::mbar_init(o_done, 1);
+    ptx::mbar_init(res_full, 1);
     ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&mapO);
     ptx::prefetch_tmap(&mapQ); ptx::prefetch_tmap(&mapK); ptx::prefetch_tmap(&mapVt);
   }
   if (warp == 1) {
@@ -142,6 +147,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       }
       __syncwarp();
       if (++s == NST) { s = 0; ph ^= 1; }
+    }
+    if (p.residual) {
+      // residual tile -> the K ring once every Q K^T has drained it (same [chunk][128 rows][128 B] layout as the Q tile);
+      // it lands while the last softmax / P V are still running
+      bool okr = true;
+      for (int i = 0; i < NST && okr; ++i) {
+        okr = ptx::mbar_wait(k_empty(s), ph, p.dbg, 32);
+        if (++s == NST) { s = 0; ph ^= 1; }
+      }
+      if (okr && ptx::elect_one()) {
+        ptx::mbar_expect_tx(res_full, SM::kQ);
+        for (int c = 0; c < kDC; ++c) tma_load_3d(k_base + c * (128 * 128), &mapR, res_full, c * 64, q0, n);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -285,29 +304,44 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     // ---- epilogue: O / l (+ residual) -> bf16
     if (ok) ok = ptx::mbar_wait(o_done, (ntile - 1) & 1, p.dbg, 31);
     ptx::tc_fence_after();
-    const int row = q0 + r;
+    // O tile -> bf16 in the (idle) Q tile's smem, SWIZZLE_128B -> one TMA store per 64-column chunk: whole 128-byte rows,
+    // rows past Lq clipped by the TMA unit (row-per-thread global stores touch 32 lines per instruction)
+    if (ok && p.residual) ok = ptx::mbar_wait(res_full, 0, p.dbg, 33);
     if (ok) {
       const float inv = 1.f / l;
-      const int64_t off = ((int64_t)n * p.lq + row) * D;
+      uint8_t* q_ptr = smem;
+      const uint8_t* r_ptr = smem + SM::kQ;
 #pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        uint32_t rr[16];
-        ptx::tc_ld_32x32b_x16(lane_addr + kOCol + c0, rr);
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t ra[16], rb[16];
+        ptx::tc_ld_32x32b_x16(lane_addr + kOCol + c0, ra);
+        ptx::tc_ld_32x32b_x16(lane_addr + kOCol + c0 + 16, rb);
         ptx::tc_wait_ld();
-        if (row < p.lq) {
-          float v[16];
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) * inv;
+        for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(ra[i]) * inv; v[16 + i] = __uint_as_float(rb[i]) * inv; }
+        const uint32_t base = (uint32_t)(c0 >> 6) * (128 * 128) + (uint32_t)r * 128u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t o = base + (uint32_t)(((((c0 & 63) >> 3) + u) ^ (r & 7)) << 4);
           if (p.residual) {
-            float a[16];
-            unpack8(*reinterpret_cast<const bf16x8*>(p.residual + off + c0), *reinterpret_cast<float(*)[8]>(&a[0]));
-            unpack8(*reinterpret_cast<const bf16x8*>(p.residual + off + c0 + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
+            float a[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(r_ptr + o), a);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += a[i];
+            for (int i = 0; i < 8; ++i) v[8 * u + i] += a[i];
           }
-          *reinterpret_cast<bf16x8*>(p.o + off + c0) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
-          *reinterpret_cast<bf16x8*>(p.o + off + c0 + 8) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
+          *reinterpret_cast<bf16x8*>(q_ptr + o) = pack8(*reinterpret_cast<float(*)[8]>(&v[8 * u]));
         }
+      }
+      ptx::fence_proxy_async();
+      softmax_bar_sync();
+      if (threadIdx.x == 64) {
+        for (int c = 0; c < kDC; ++c)
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::
+                           "l"(reinterpret_cast<uint64_t>(&mapO)), "r"(q_base + c * (128 * 128)), "r"(c * 64), "r"(q0), "r"(n)
+                       : "memory");
+        ptx::bulk_commit_group();
+        ptx::bulk_wait_read_all();
       }
     }
   }
@@ -353,7 +387,7 @@ int encode3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t 
 struct b200dm_attn_plan {
   b200dm_attn_desc desc;
   AttnParams p;
-  CUtensorMap mapQ, mapK, mapVt;
+  CUtensorMap mapQ, mapK, mapVt, mapO, mapR;
   int bkv;
   size_t smem;
   double flops;
@@ -370,7 +404,7 @@ static int launch_attn(const b200dm_attn_plan* pl, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid((pl->desc.lq + 127) / 128, pl->desc.batch);
-  B2_CHECK_CUDA(b2_launch(kern, grid, dim3(kThreads), Smem<D, BKV, NST, NPB>::kTotal, s, pl->mapQ, pl->mapK, pl->mapVt, pl->p));
+  B2_CHECK_CUDA(b2_launch(kern, grid, dim3(kThreads), Smem<D, BKV, NST, NPB>::kTotal, s, pl->mapQ, pl->mapK, pl->mapVt, pl->mapO, pl->mapR, pl->p));
   return B200DM_OK;
 }
 
@@ -389,6 +423,8 @@ extern "C" int b200dm_attention_plan_create(const b200dm_attn_desc* d, const voi
   int rc = encode3(&pl->mapQ, q, d->d, d->lq, d->batch, 64, 128);
   if (!rc) rc = encode3(&pl->mapK, k, d->d, d->lk, d->batch, 64, pl->bkv);
   if (!rc) rc = encode3(&pl->mapVt, vt, d->lk, d->d, d->batch, 64, d->d);
+  if (!rc) rc = encode3(&pl->mapO, o, d->d, d->lq, d->batch, 64, 128);
+  if (!rc) rc = encode3(&pl->mapR, residual ? residual : o, d->d, d->lq, d->batch, 64, 128);
   if (rc) { delete pl; return rc; }
   pl->p.batch = d->batch; pl->p.lq = d->lq; pl->p.lk = d->lk; pl->p.d = d->d;
   pl->p.scale_log2e = d->scale * 1.4426950408889634f;
