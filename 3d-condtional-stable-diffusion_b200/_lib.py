@@ -106,6 +106,8 @@ _SIGS = {
     "b200dm_program_add_softmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float]),
     "b200dm_program_add_update": (C.c_int, [C.c_void_p, C.POINTER(UpdateDesc)] + [C.c_void_p] * 5),
     "b200dm_program_add_step_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "b200dm_program_set_lane": (C.c_int, [C.c_void_p, C.c_int32]),
+    "b200dm_program_add_sync": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "b200dm_program_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200dm_program_num_launches": (C.c_int, [C.c_void_p]),
     "b200dm_program_num_ops": (C.c_int, [C.c_void_p]),

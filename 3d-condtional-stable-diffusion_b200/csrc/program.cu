@@ -2,14 +2,23 @@
 // call per U-Net forward / decode (the reference drives one eager TF op at a time from Python,
 // networks/dm3d.py:516-530).  Every launch goes to the caller's stream, so the whole program is
 // CUDA-graph capturable; timestep-dependent inputs are read through device pointers (t_dev).
+//
+// Lanes: independent branches of a block (the three branches of CrossAttentionBlock.call all read the same tensor,
+// conditional_dm3d.py:190-192) are recorded on side lanes = extra streams owned by the program, forked from / joined
+// to the caller's stream with events (b200dm_program_add_sync), so under graph capture they become parallel branches
+// and small kernels that fill a fraction of the 148 SMs overlap instead of queueing.
 #include <vector>
 #include <new>
 #include "common.cuh"
 
 namespace {
-enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN, OP_NORM_EX, OP_STATS_F32 };
+enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN, OP_NORM_EX, OP_STATS_F32, OP_SYNC };
+constexpr int kMaxLanes = 4;
 struct Op {
   OpKind kind;
+  int lane = 0;                 // 0 = the caller's stream
+  int to_lane = 0;              // OP_SYNC: lane that waits for everything recorded so far on `lane`
+  cudaEvent_t ev = nullptr;     // OP_SYNC
   b200dm_conv_plan* conv = nullptr;
   b200dm_attn_plan* attn = nullptr;
   b200dm_norm_desc nd{};
@@ -30,6 +39,9 @@ struct Op {
 
 struct b200dm_program {
   std::vector<Op> ops;
+  int cur_lane = 0;
+  cudaStream_t side[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
+  void push(Op& op) { op.lane = cur_lane; ops.push_back(op); }
 };
 
 extern "C" int b200dm_program_create(b200dm_program** out) {
@@ -44,13 +56,16 @@ extern "C" void b200dm_program_destroy(b200dm_program* p) {
   for (auto& op : p->ops)
     if (op.kind == OP_CONV) b200dm_conv_plan_destroy(op.conv);
     else if (op.kind == OP_ATTN) b200dm_attention_plan_destroy(op.attn);
+    else if (op.kind == OP_SYNC && op.ev) cudaEventDestroy(op.ev);
+  for (int i = 1; i < kMaxLanes; ++i)
+    if (p->side[i]) cudaStreamDestroy(p->side[i]);
   delete p;
 }
 
 extern "C" int b200dm_program_add_conv(b200dm_program* p, b200dm_conv_plan* plan) {
   B2_CHECK_ARG(p && plan, "program_add_conv: null argument");
   Op op; op.kind = OP_CONV; op.conv = plan;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
@@ -60,7 +75,7 @@ extern "C" int b200dm_program_add_norm_act_ex(b200dm_program* p, const b200dm_no
   B2_CHECK_ARG(p && d && x && a && b && y, "program_add_norm_act_ex: null argument");
   Op op; op.kind = OP_NORM_EX; op.ned = *d; op.p0 = x; op.p1 = a; op.p2 = b; op.p3 = mean_rstd; op.p4 = prelu_alpha; op.p5 = residual;
   op.out = y;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
@@ -69,14 +84,14 @@ extern "C" int b200dm_program_add_stats_f32(b200dm_program* p, const float* x, i
   B2_CHECK_ARG(p && x && mean_rstd && workspace, "program_add_stats_f32: null argument");
   Op op; op.kind = OP_STATS_F32; op.p0 = x; op.i1 = batch; op.i0 = per_sample; op.f0 = eps; op.out = mean_rstd; op.out2 = workspace;
   op.ws = ws_bytes; op.launches = 2;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
 extern "C" int b200dm_program_add_attention(b200dm_program* p, b200dm_attn_plan* plan) {
   B2_CHECK_ARG(p && plan, "program_add_attention: null argument");
   Op op; op.kind = OP_ATTN; op.attn = plan;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
@@ -84,7 +99,7 @@ extern "C" int b200dm_program_add_norm_act(b200dm_program* p, const b200dm_norm_
                                            const float* a, const float* b, const float* mean_rstd, void* y) {
   B2_CHECK_ARG(p && d && x0 && a && b && y, "program_add_norm_act: null argument");
   Op op; op.kind = OP_NORM; op.nd = *d; op.p0 = x0; op.p1 = x1; op.p2 = a; op.p3 = b; op.p4 = mean_rstd; op.out = y;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
@@ -93,7 +108,7 @@ extern "C" int b200dm_program_add_gn_stats(b200dm_program* p, const b200dm_norm_
   B2_CHECK_ARG(p && d && x && mean_rstd && workspace, "program_add_gn_stats: null argument");
   Op op; op.kind = OP_GNSTATS; op.nd = *d; op.p0 = x; op.f0 = eps; op.out = mean_rstd; op.out2 = workspace; op.ws = ws_bytes;
   op.launches = 2;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
@@ -103,7 +118,7 @@ extern "C" int b200dm_program_add_layernorm(b200dm_program* p, const void* x, in
   B2_CHECK_ARG(p && x && gammas && betas && ys && n_out >= 1 && n_out <= 3, "program_add_layernorm: bad argument");
   Op op; op.kind = OP_LN; op.p0 = x; op.i0 = rows; op.i1 = c; op.f0 = eps; op.i2 = n_out;
   for (int i = 0; i < n_out; ++i) { op.gam[i] = gammas[i]; op.bet[i] = betas[i]; op.ys[i] = ys[i]; }
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
@@ -111,7 +126,7 @@ extern "C" int b200dm_program_add_softmax(b200dm_program* p, const float* s, voi
                                           float scale) {
   B2_CHECK_ARG(p && s && p_bf16, "program_add_softmax: null argument");
   Op op; op.kind = OP_SOFTMAX; op.p0 = s; op.out = p_bf16; op.i0 = rows; op.i1 = cols; op.f0 = scale;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
@@ -119,13 +134,32 @@ extern "C" int b200dm_program_add_update(b200dm_program* p, const b200dm_update_
                                          const float* noise, float* x_prev, void* x_prev_bf16) {
   B2_CHECK_ARG(p && d && x_t && eps && x_prev, "program_add_update: null argument");
   Op op; op.kind = OP_UPDATE; op.ud = *d; op.p0 = x_t; op.p1 = eps; op.p2 = noise; op.out = x_prev; op.out2 = x_prev_bf16;
-  p->ops.push_back(op);
+  p->push(op);
   return B200DM_OK;
 }
 
 extern "C" int b200dm_program_add_step_advance(b200dm_program* p, int32_t* t_dev, int32_t delta) {
   B2_CHECK_ARG(p && t_dev, "program_add_step_advance: null argument");
   Op op; op.kind = OP_ADVANCE; op.out = t_dev; op.i1 = delta;
+  p->push(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_set_lane(b200dm_program* p, int32_t lane) {
+  B2_CHECK_ARG(p && lane >= 0 && lane < kMaxLanes, "program_set_lane: lane must be 0..%d", kMaxLanes - 1);
+  if (lane > 0 && !p->side[lane]) B2_CHECK_CUDA(cudaStreamCreateWithFlags(&p->side[lane], cudaStreamNonBlocking));
+  p->cur_lane = lane;
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_sync(b200dm_program* p, int32_t from_lane, int32_t to_lane) {
+  B2_CHECK_ARG(p && from_lane >= 0 && from_lane < kMaxLanes && to_lane >= 0 && to_lane < kMaxLanes && from_lane != to_lane,
+               "program_add_sync: bad lanes %d -> %d", from_lane, to_lane);
+  for (int l : {from_lane, to_lane})
+    if (l > 0 && !p->side[l]) B2_CHECK_CUDA(cudaStreamCreateWithFlags(&p->side[l], cudaStreamNonBlocking));
+  Op op; op.kind = OP_SYNC; op.launches = 0;
+  B2_CHECK_CUDA(cudaEventCreateWithFlags(&op.ev, cudaEventDisableTiming));
+  op.lane = from_lane; op.to_lane = to_lane;
   p->ops.push_back(op);
   return B200DM_OK;
 }
@@ -139,10 +173,21 @@ extern "C" int b200dm_program_num_launches(const b200dm_program* p) {
 
 static int run_op(Op& op, void* stream);
 
+static inline cudaStream_t lane_stream(b200dm_program* p, int lane, void* main) { return lane == 0 ? (cudaStream_t)main : p->side[lane]; }
+
+static int run_any(b200dm_program* p, Op& op, void* stream) {
+  if (op.kind == OP_SYNC) {
+    B2_CHECK_CUDA(cudaEventRecord(op.ev, lane_stream(p, op.lane, stream)));
+    B2_CHECK_CUDA(cudaStreamWaitEvent(lane_stream(p, op.to_lane, stream), op.ev, 0));
+    return B200DM_OK;
+  }
+  return run_op(op, (void*)lane_stream(p, op.lane, stream));
+}
+
 extern "C" int b200dm_program_run(b200dm_program* p, void* stream) {
   B2_CHECK_ARG(p, "program_run: null program");
   for (auto& op : p->ops) {
-    int rc = run_op(op, stream);
+    int rc = run_any(p, op, stream);
     if (rc != B200DM_OK) return rc;
   }
   return B200DM_OK;
@@ -158,8 +203,8 @@ extern "C" int b200dm_program_run_timed(b200dm_program* p, void* stream, float* 
   for (auto& e : ev) B2_CHECK_CUDA(cudaEventCreate(&e));
   B2_CHECK_CUDA(cudaEventRecord(ev[0], s));
   int rc = B200DM_OK;
-  for (size_t i = 0; i < p->ops.size() && rc == B200DM_OK; ++i) {
-    rc = run_op(p->ops[i], stream);
+  for (size_t i = 0; i < p->ops.size() && rc == B200DM_OK; ++i) {   // every lane's ops serially on the caller's stream
+    if (p->ops[i].kind != OP_SYNC) rc = run_op(p->ops[i], stream);
     cudaEventRecord(ev[i + 1], s);
   }
   cudaError_t e = cudaStreamSynchronize(s);
@@ -192,6 +237,7 @@ static int run_op(Op& op, void* stream) {
       case OP_NORM_EX:
         rc = b200dm_norm_act_ex(&op.ned, op.p0, (const float*)op.p1, (const float*)op.p2, (const float*)op.p3, op.p4, op.p5, op.out, stream);
         break;
+      case OP_SYNC: break;
       case OP_STATS_F32: rc = b200dm_stats_f32((const float*)op.p0, op.i1, op.i0, op.f0, (float*)op.out, op.out2, op.ws, stream); break;
     }
   }

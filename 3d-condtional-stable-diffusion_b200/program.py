@@ -151,6 +151,15 @@ class Program:
         self.bytes += nbytes
         self.log.append(("update", note, nbytes))
 
+    def set_lane(self, lane):
+        """Ops added from here on run on lane ``lane`` (0 = caller's stream; 1..3 = side streams of the program)."""
+        check(lib().b200dm_program_set_lane(self.h, lane))
+
+    def sync(self, from_lane, to_lane):
+        """Everything recorded so far on ``from_lane`` becomes a prerequisite of what follows on ``to_lane``."""
+        check(lib().b200dm_program_add_sync(self.h, from_lane, to_lane))
+        self.log.append(("sync", f"{from_lane}->{to_lane}", 0))
+
     def advance(self, t_dev, delta):
         check(lib().b200dm_program_add_step_advance(self.h, ptr(t_dev), delta))
         self.hold(t_dev)

@@ -156,6 +156,7 @@ class UNet:
         # norm pass, but measured SLOWER on B200 (cfg-2: 5.47 vs 5.08 ms/step): the extra stores lengthen the conv
         # epilogues, which are on the critical path, by more than the streaming pass costs.  Off unless B200DM_FUSE_NORMS=1.
         self.fuse_norms = os.environ.get("B200DM_FUSE_NORMS", "0") == "1"
+        self.lanes = os.environ.get("B200DM_LANES", "1") != "0"   # branch-parallel CrossAttentionBlock (program lanes)
         self.t_dev = t_dev if t_dev is not None else torch.zeros(2, dtype=torch.int32, device=dev)
         g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
 
@@ -169,12 +170,14 @@ class UNet:
         self.temb_table = temb
 
         def conv(x0, kname, cout, y=None, x1=None, k=3, stride=1, mode=L.CONV_DIRECT, act=None, bias=True, chan_bias=None,
-                 residual=None, y_dtype=torch.bfloat16, transposed_store=False, dense=False, out_affine=None, note=""):
+                 residual=None, y_dtype=torch.bfloat16, transposed_store=False, dense=False, out_affine=None, note="",
+                 kern=None):
             Bx, D, H, Wd, c0 = x0.shape
             c1 = x1.shape[-1] if x1 is not None else 0
             desc = ops.make_conv_desc(mode, Bx, (D, H, Wd), c0, c1, cout, k, stride, act, None, y_dtype,
                                       chan_bias_rows=1 if chan_bias is not None else 0, transposed_store=transposed_store)
-            kern = P[f"{kname}.kernel"]
+            if kern is None:
+                kern = P[f"{kname}.kernel"]
             if dense:  # Dense on voxels == 1^3 conv: (in,out) -> (1,1,1,in,out)
                 kern = kern.reshape(1, 1, 1, *kern.shape)
             wp = ops.pack_conv_weights(desc, kern).to(dev)
@@ -255,18 +258,39 @@ class UNet:
             bet = [g(f"{n}.norm{i}.beta") for i in (1, 2, 3)]
             ln = pr.layernorm(h, gam, bet, [pr.buf(h.shape) for _ in range(3)], 1e-3, note=f"{n}.ln")
             hf = h.view(B, Lq, c)
+            kc, vcT = pr.buf((B, Lq, c)), pr.buf((B, c, Lq))          # filled by set_context()
+            self.ctx_sites.append(dict(name=n, c=c, s=s, kc=kc, vcT=vcT))
+            if not self.lanes:
+                q1 = conv(ln[0], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
+                k1 = conv(ln[0], f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
+                v1T = conv(ln[0], f"{n}.value", c, k=1, dense=True, transposed_store=True)
+                t1 = attention_core(q1, k1, v1T, scale, hf, f"{n}.self")
+                q2 = conv(ln[1], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
+                t2 = attention_core(q2, kc, vcT, scale, t1, f"{n}.cross")
+                m = conv(ln[2], f"{n}.mlp0", 4 * c, k=1, dense=True, act="relu")
+                xs = conv(m, f"{n}.mlp1", c, k=1, dense=True, residual=t2.view(B, s, s, s, c))
+                # relu(proj_out(x)) + residual: act before the residual add
+                return conv(xs, f"{n}.proj_out", c, k=1, act="relu", residual=x)
+            # The three branches all read h (conditional_dm3d.py:190-192): self-attention on the caller's stream, cross
+            # attention on lane 1, the MLP on lane 2 (its second GEMM adds the cross branch), and proj_out sums the two
+            # partial results inside its K loop: proj_out(t1 + xs) = [t1 | xs] . [W; W]  (two K segments, no add pass).
+            pr.sync(0, 1)
+            pr.sync(0, 2)
             q1 = conv(ln[0], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
             k1 = conv(ln[0], f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
             v1T = conv(ln[0], f"{n}.value", c, k=1, dense=True, transposed_store=True)
             t1 = attention_core(q1, k1, v1T, scale, hf, f"{n}.self")
+            pr.set_lane(1)
             q2 = conv(ln[1], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
-            kc, vcT = pr.buf((B, Lq, c)), pr.buf((B, c, Lq))          # filled by set_context()
-            self.ctx_sites.append(dict(name=n, c=c, s=s, kc=kc, vcT=vcT))
-            t2 = attention_core(q2, kc, vcT, scale, t1, f"{n}.cross")
+            c2 = attention_core(q2, kc, vcT, scale, None, f"{n}.cross")
+            pr.set_lane(2)
             m = conv(ln[2], f"{n}.mlp0", 4 * c, k=1, dense=True, act="relu")
-            xs = conv(m, f"{n}.mlp1", c, k=1, dense=True, residual=t2.view(B, s, s, s, c))
-            # relu(proj_out(x)) + residual: act before the residual add
-            return conv(xs, f"{n}.proj_out", c, k=1, act="relu", residual=x)
+            pr.sync(1, 2)
+            xs = conv(m, f"{n}.mlp1", c, k=1, dense=True, residual=c2.view(B, s, s, s, c))
+            pr.set_lane(0)
+            pr.sync(2, 0)
+            w2 = torch.cat([P[f"{n}.proj_out.kernel"]] * 2, dim=3)
+            return conv(t1.view(B, s, s, s, c), f"{n}.proj_out", c, x1=xs, k=1, act="relu", residual=x, kern=w2)
 
         self.x_in = pr.buf((B, S, S, S, cfg.img_channels))
         self.eps = pr.buf((B, S, S, S, cfg.img_channels), torch.float32)
