@@ -179,8 +179,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (lane == 0) trace_ev(p, 0, tix, 44);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint64_t da = a_desc0 + (uint64_t)(s * (kStageBytes >> 4));
-          const uint64_t db = b_desc0 + (uint64_t)(s * (kStageBytes >> 4));
+          // swap_ab (BLOCK_N = 128, both tiles [128 rows][64 K]): the weight tile is the A operand -> D^T in TMEM
+          const uint64_t da = (p.swap_ab ? b_desc0 : a_desc0) + (uint64_t)(s * (kStageBytes >> 4));
+          const uint64_t db = (p.swap_ab ? a_desc0 : b_desc0) + (uint64_t)(s * (kStageBytes >> 4));
           ptx::tc_mma_f16(tmem_base, da, db, idesc, kb != kb0 ? 1u : 0u);
           ptx::tc_mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
           ptx::tc_mma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
@@ -249,7 +250,41 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mid_synced = true;
     } else {
       if (KSPLIT) { ptx::cluster_sync_all(); mid_synced = true; }   // acquire: every peer's partial tile is staged
-      if (BLOCK_N >= 64 && staged) {
+      if (BLOCK_N == 128 && staged && p.swap_ab) {
+        // ---- per-sample transposed output (V^T of the attention blocks) by operand swap: this thread's TMEM lane is
+        // output channel n_tile*128 + r, the 128 columns are the tile's voxels = 256 contiguous bytes of y[n][channel][:]
+        if (ok) {
+          const int co = n_tile * BLOCK_N + r;
+          const float bsv = (p.bias && co < p.c_out) ? __ldg(p.bias + co) : 0.f;
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+          const int vox0 = (d0 * p.m_h + h0) * p.m_w + w0;
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            uint8_t* stg = smem + g * kStageBytes;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t ra[16], rb[16];
+              ptx::tc_ld_32x32b_x16(trow + (uint32_t)(g * 64 + h * 32), ra);
+              ptx::tc_ld_32x32b_x16(trow + (uint32_t)(g * 64 + h * 32 + 16), rb);
+              ptx::tc_wait_ld();
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(ra[j]) + bsv; v[16 + j] = __uint_as_float(rb[j]) + bsv; }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<bf16x8*>(stg + (uint32_t)r * 128u + (uint32_t)(((h * 4 + u) ^ (r & 7)) << 4)) =
+                    pack8(*reinterpret_cast<float(*)[8]>(&v[8 * u]));
+            }
+            ptx::fence_proxy_async();
+            epilogue_bar_sync();
+            if (threadIdx.x == 64) {
+              ptx::tma_store_5d(&om.y[0], ptx::smem_u32(stg), vox0 + g * 64, n_tile * BLOCK_N, 0, 0, n0);
+              ptx::bulk_commit_group();
+            }
+          }
+          if (threadIdx.x == 64) ptx::bulk_wait_read_all();
+        }
+      } else if (BLOCK_N >= 64 && staged) {
         // ---- staged epilogue: 64-column groups -> bf16 SWIZZLE_128B tile in the (idle) pipeline stages -> one TMA store
         // per group.  Row-per-thread global stores touch 32 lines per instruction (measured ~1000 cycles per 16-column
         // chunk); the TMA store writes whole 128-byte rows and clips the ragged edges itself.
@@ -792,6 +827,22 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       p.tma_epi = 1;
     }
   }
+  // per-sample transposed store by operand swap (see the kernel): tiles of whole planes inside one sample, bias only
+  if (d->reserved[1] != 0 && !pl->halo && cl_m * cl_n == 1 && d->mode == B200DM_CONV_DIRECT && d->ksize == 1 && st == 1 &&
+      d->y_dtype == B200DM_BF16 && g.block_n == 128 && g.box_n == 1 && g.box_w == g.m_w && g.box_h == g.m_h && g.m_d % g.box_d == 0 &&
+      !residual && !prelu_alpha && !chan_bias && d->act == B200DM_ACT_NONE && d->reserved[0] == B200DM_ACT_NONE &&
+      !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0)) {
+    const cuuint64_t Lv = (cuuint64_t)g.m_w * g.m_h * g.m_d;
+    cuuint64_t dims[5] = {Lv, (cuuint64_t)d->c_out, 1, 1, (cuuint64_t)d->batch};
+    cuuint64_t strides[4] = {Lv * 2, Lv * d->c_out * 2, Lv * d->c_out * 2, Lv * d->c_out * 2};
+    cuuint32_t box[5] = {64, 128, 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (Lv % 8 == 0 && enc(&pl->om.y[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      p.swap_ab = 1;
+      p.tma_epi = 1;
+    }
+  }
   pl->smem = conv_smem_bytes(g.block_n, pl->nstage, p.tma_epi && residual);
   if (pl->smem > 232448) { p.tma_epi = 0; pl->smem = conv_smem_bytes(g.block_n, pl->nstage, false); }
   if (pl->halo) {
@@ -869,6 +920,7 @@ extern "C" int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float*
   B2_CHECK_ARG(p, "conv_plan_set_out_affine: null plan");
   B2_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_plan_set_out_affine: give both scale and shift, or neither");
   B2_CHECK_ARG(!scale || !p->p.prelu_alpha, "conv_plan_set_out_affine: not combinable with PReLU");
+  B2_CHECK_ARG(!scale || !p->p.swap_ab, "conv_plan_set_out_affine: not combinable with a transposed store");
   p->p.out_scale = scale;
   p->p.out_shift = shift;
   return B200DM_OK;

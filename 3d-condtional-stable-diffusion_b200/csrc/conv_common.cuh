@@ -16,6 +16,7 @@ struct ConvParams {
   int chan_bias_rows;
   int halo_td, halo_tiles_per_ntile, halo_ntn, halo_total_tiles;   // halo kernel only
   int tma_epi;                       // staged epilogue: bf16 tile -> swizzled smem -> TMA store (residual tile TMA-loaded)
+  int swap_ab;                       // transposed store by operand swap: D^T = W X^T (TMEM lane = channel, column = voxel)
   int epi_dbg;                       // tuning aid (B200DM_EPI_DBG): 1 = skip global stores, 2 = skip TMEM loads too
   int ksplit;                        // igemm split-K: cluster of ksplit CTAs per tile, each owns a K range (0/1 = off)
   int cl_m, cl_n;                    // igemm cluster: cl_m m-tiles share every B tile, cl_n n-tiles share every A tile

@@ -276,9 +276,13 @@ class UNet:
             # partial results inside its K loop: proj_out(t1 + xs) = [t1 | xs] . [W; W]  (two K segments, no add pass).
             pr.sync(0, 1)
             pr.sync(0, 2)
+            pr.sync(0, 3)
             q1 = conv(ln[0], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
             k1 = conv(ln[0], f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
+            pr.set_lane(3)
             v1T = conv(ln[0], f"{n}.value", c, k=1, dense=True, transposed_store=True)
+            pr.set_lane(0)
+            pr.sync(3, 0)
             t1 = attention_core(q1, k1, v1T, scale, hf, f"{n}.self")
             pr.set_lane(1)
             q2 = conv(ln[1], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)

@@ -174,10 +174,19 @@ def test_batched_gemm_and_transposed_store(cuda):
     desc = ops.make_conv_desc(_lib.CONV_DIRECT, B, (8, 8, 8), Cc, 0, Cc, 1, 1, y_dtype=torch.bfloat16, transposed_store=True)
     wp = ops.pack_conv_weights(desc, w).to(cuda)
     vt = torch.empty(B, Cc, L, dtype=torch.bfloat16, device=cuda)
-    ops.ConvPlan(desc, x.to(cuda, torch.bfloat16), wp, vt).run()
+    bv = _rand((Cc,), 6)
+    plan = ops.ConvPlan(desc, x.to(cuda, torch.bfloat16), wp, vt, bias=bv.to(cuda))
+    plan.run()
     _check_flag()
-    ref = O.conv3d(x, w).reshape(B, L, Cc).transpose(1, 2)
-    _close(vt, ref, tol=6e-3, what="transposed store")
+    ref = (O.conv3d(x, w) + bv).reshape(B, L, Cc).transpose(1, 2)
+    _close(vt, ref, tol=6e-3, what="transposed store (operand swap)")
+    # small volume (tile spans samples): the scalar transposed path
+    xs = _rand((B, 4, 4, 4, Cc), 7)
+    descs = ops.make_conv_desc(_lib.CONV_DIRECT, B, (4, 4, 4), Cc, 0, Cc, 1, 1, y_dtype=torch.bfloat16, transposed_store=True)
+    vts = torch.empty(B, Cc, 64, dtype=torch.bfloat16, device=cuda)
+    ops.ConvPlan(descs, xs.to(cuda, torch.bfloat16), ops.pack_conv_weights(descs, w).to(cuda), vts, bias=bv.to(cuda)).run()
+    _check_flag()
+    _close(vts, (O.conv3d(xs, w) + bv).reshape(B, 64, Cc).transpose(1, 2), tol=6e-3, what="transposed store (scalar path)")
     p = _r(torch.softmax(torch.randn(B, L, L, generator=torch.Generator().manual_seed(5)), -1))
     o = ops.batched_gemm(p.to(cuda, torch.bfloat16), vt)
     _check_flag()
