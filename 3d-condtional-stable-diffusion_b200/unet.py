@@ -247,6 +247,7 @@ class UNet:
             return conv(o, f"{n}.proj", c, k=1, dense=True, residual=nrm)   # returns BN(x) + proj (dm3d.py:63)
 
         self.ctx_sites = []
+        self._ctx_ids = None
 
         def xattn_block(b, x):  # CrossAttentionBlock.call (conditional_dm3d.py:186-195)
             n, c, s = b["name"], b["c"], b["s"]
@@ -330,16 +331,26 @@ class UNet:
         if ids.numel() == 1:
             ids = ids.expand(B)  # the reference feeds a batch-1 context (conditional_dm3d.py:552)
         assert ids.numel() == B
+        if getattr(self, "_ctx_ids", None) is not None and torch.equal(self._ctx_ids, ids):
+            return  # K_ctx / V_ctx^T of these class ids are already in the sites' buffers
         cemb = P["ctx.embedding"][ids].to(dev).contiguous()          # Embedding (conditional_dm3d.py:358)
         for site in self.ctx_sites:
             n, c, s = site["name"], site["c"], site["s"]
-            ctx = ops.dense_f32(cemb, P[f"{n}.ctxmlp.kernel"].to(dev), P[f"{n}.ctxmlp.bias"].to(dev), act_out="silu")
-            ctx = ops.cast(ctx, torch.bfloat16).view(B, s, s, s, c)
-            for wname, out, tr in (("key", site["kc"], False), ("value", site["vcT"], True)):
-                desc = ops.make_conv_desc(L.CONV_DIRECT, B, (s, s, s), c, 0, c, 1, 1, transposed_store=tr)
-                wp = ops.pack_conv_weights(desc, P[f"{n}.{wname}.kernel"].reshape(1, 1, 1, c, c)).to(dev)
-                ops.ConvPlan(desc, ctx, wp, out, bias=P[f"{n}.{wname}.bias"].to(dev)).run()
+            if "dev" not in site:   # device copies of the site's weights + the two projection plans, built once
+                ctxbuf = torch.empty(B, s, s, s, c, dtype=torch.bfloat16, device=dev)
+                plans = []
+                for wname, out, tr in (("key", site["kc"], False), ("value", site["vcT"], True)):
+                    desc = ops.make_conv_desc(L.CONV_DIRECT, B, (s, s, s), c, 0, c, 1, 1, transposed_store=tr)
+                    wp = ops.pack_conv_weights(desc, P[f"{n}.{wname}.kernel"].reshape(1, 1, 1, c, c)).to(dev)
+                    plans.append(ops.ConvPlan(desc, ctxbuf, wp, out, bias=P[f"{n}.{wname}.bias"].to(dev)))
+                site["dev"] = dict(w=P[f"{n}.ctxmlp.kernel"].to(dev), b=P[f"{n}.ctxmlp.bias"].to(dev), ctx=ctxbuf, plans=plans)
+            d = site["dev"]
+            ctx = ops.dense_f32(cemb, d["w"], d["b"], act_out="silu")     # ContextMLP (conditional_dm3d.py:310-318)
+            d["ctx"].copy_(ops.cast(ctx, torch.bfloat16).view(B, s, s, s, c))
+            for plan in d["plans"]:
+                plan.run()
         torch.cuda.synchronize(dev)
+        self._ctx_ids = ids.clone()
 
     # ---- call ---------------------------------------------------------------------------------------------
     def forward_inplace(self):
