@@ -19,11 +19,15 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 // ------------------------------------------------------------------ norm + act (+concat)
 // grid = (blocks_x, batch).  Prologue folds the per-(sample,channel) affine (a,b) into smem, then a
 // grid-stride loop over (voxel, channel-octet) of this sample: y = act(x*a + b).
-__global__ void __launch_bounds__(256) norm_act_kernel(b200dm_norm_desc d, const __nv_bfloat16* __restrict__ x0,
-                                                       const __nv_bfloat16* __restrict__ x1,
-                                                       const float* __restrict__ pa, const float* __restrict__ pb,
-                                                       const float* __restrict__ mean_rstd,
-                                                       __nv_bfloat16* __restrict__ y) {
+// The host sizes gridDim.x * 256 as a multiple of C/8 whenever it can, so a thread keeps ONE channel octet for the whole
+// pass: its 16 affine coefficients live in registers and the loop is loads / FMAs / stores with no index division
+// (ncu on the generic form: 169 warp instructions per 16-byte vector, issue-bound at 2.3 TB/s).
+template <int ACT>
+__global__ void __launch_bounds__(256, 4) norm_act_kernel(b200dm_norm_desc d, const __nv_bfloat16* __restrict__ x0,
+                                                          const __nv_bfloat16* __restrict__ x1,
+                                                          const float* __restrict__ pa, const float* __restrict__ pb,
+                                                          const float* __restrict__ mean_rstd,
+                                                          __nv_bfloat16* __restrict__ y) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sm[];
@@ -49,12 +53,39 @@ __global__ void __launch_bounds__(256) norm_act_kernel(b200dm_norm_desc d, const
   const __nv_bfloat16* s0 = x0 + (int64_t)n * d.voxels * d.c0;
   const __nv_bfloat16* s1 = x1 ? x1 + (int64_t)n * d.voxels * d.c1 : nullptr;
   __nv_bfloat16* yo = y + (int64_t)n * d.voxels * C;
-  const int act = d.act;
-  // 4 independent 16-byte vectors per thread per trip (loads issued before any use), 32-bit index arithmetic
-  // (total < 2^31 vectors per sample is checked on the host): the pass is a pure HBM stream.
-  constexpr int U = 4;
+  constexpr int U = 4;   // independent 16-byte vectors in flight per thread (loads issued before any use)
   const uint32_t tot32 = (uint32_t)total, stride = gridDim.x * blockDim.x;
-  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < tot32; i0 += stride * U) {
+  const uint32_t i00 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (stride % (uint32_t)c8n == 0) {
+    const uint32_t c8 = i00 % (uint32_t)c8n, dv = stride / (uint32_t)c8n, nvox = (uint32_t)d.voxels;
+    const float4 a0 = *reinterpret_cast<const float4*>(sa + (c8 << 3)), a1 = *reinterpret_cast<const float4*>(sa + (c8 << 3) + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + (c8 << 3)), b1 = *reinterpret_cast<const float4*>(sb + (c8 << 3) + 4);
+    const bool first = (int)c8 < c08;
+    const __nv_bfloat16* src = first ? s0 + (c8 << 3) : s1 + ((c8 - c08) << 3);
+    const uint32_t sstride = first ? d.c0 : d.c1;
+    __nv_bfloat16* dst = yo + (c8 << 3);
+    for (uint32_t v = i00 / (uint32_t)c8n; v < nvox; v += dv * U) {
+      bf16x8 pk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v + u * dv < nvox) pk[u] = ldg_bf16x8(reinterpret_cast<const bf16x8*>(src + (size_t)(v + u * dv) * sstride));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (v + u * dv >= nvox) break;
+        float f[8];
+        unpack8(pk[u], f);
+        f[0] = apply_act(fmaf(f[0], a0.x, b0.x), ACT); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), ACT);
+        f[2] = apply_act(fmaf(f[2], a0.z, b0.z), ACT); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), ACT);
+        f[4] = apply_act(fmaf(f[4], a1.x, b1.x), ACT); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), ACT);
+        f[6] = apply_act(fmaf(f[6], a1.z, b1.z), ACT); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), ACT);
+        *reinterpret_cast<bf16x8*>(dst + (size_t)(v + u * dv) * C) = pack8(f);
+      }
+    }
+    return;
+  }
+  // generic form (grid not aligned to the channel octets): 32-bit index arithmetic (total < 2^31 vectors per sample is
+  // checked on the host)
+  for (uint32_t i0 = i00; i0 < tot32; i0 += stride * U) {
     bf16x8 pk[U];
     uint32_t vv[U], cc[U];
 #pragma unroll
@@ -74,10 +105,10 @@ __global__ void __launch_bounds__(256) norm_act_kernel(b200dm_norm_desc d, const
       unpack8(pk[u], f);
       const float4 a0 = *reinterpret_cast<const float4*>(sa + (c8 << 3)), a1 = *reinterpret_cast<const float4*>(sa + (c8 << 3) + 4);
       const float4 b0 = *reinterpret_cast<const float4*>(sb + (c8 << 3)), b1 = *reinterpret_cast<const float4*>(sb + (c8 << 3) + 4);
-      f[0] = apply_act(fmaf(f[0], a0.x, b0.x), act); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), act);
-      f[2] = apply_act(fmaf(f[2], a0.z, b0.z), act); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), act);
-      f[4] = apply_act(fmaf(f[4], a1.x, b1.x), act); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), act);
-      f[6] = apply_act(fmaf(f[6], a1.z, b1.z), act); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), act);
+      f[0] = apply_act(fmaf(f[0], a0.x, b0.x), ACT); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), ACT);
+      f[2] = apply_act(fmaf(f[2], a0.z, b0.z), ACT); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), ACT);
+      f[4] = apply_act(fmaf(f[4], a1.x, b1.x), ACT); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), ACT);
+      f[6] = apply_act(fmaf(f[6], a1.z, b1.z), ACT); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), ACT);
       *reinterpret_cast<bf16x8*>(yo + (int64_t)vv[u] * C + (c8 << 3)) = pack8(f);
     }
   }
@@ -364,10 +395,26 @@ extern "C" int b200dm_norm_act_fwd(const b200dm_norm_desc* d, const void* x0, co
   const int C = d->c0 + d->c1;
   const int64_t items = d->voxels * (C >> 3);
   B2_CHECK_ARG(items < (1ll << 31), "norm_act_fwd: more than 2^31 16-byte vectors per sample");
-  int gx = grid_for((items * d->batch + 3) / 4, 256, 8);
+  // one resident wave (blocks per SM from the occupancy calculator), gridDim.x * 256 a multiple of C/8 when affordable
+  static int occ[3] = {0, 0, 0};
+  const int ai = d->act == B200DM_ACT_SILU ? 1 : (d->act == B200DM_ACT_RELU ? 2 : 0);
+  auto kern = ai == 1 ? norm_act_kernel<B200DM_ACT_SILU> : (ai == 2 ? norm_act_kernel<B200DM_ACT_RELU> : norm_act_kernel<B200DM_ACT_NONE>);
+  if (occ[ai] == 0) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, 2 * 512 * sizeof(float)) != cudaSuccess || o < 1) o = 4;
+    occ[ai] = o;
+  }
+  int gx = grid_for((items * d->batch + 3) / 4, 256, occ[ai]);
   gx = (gx + d->batch - 1) / d->batch;
   if (gx < 1) gx = 1;
-  B2_CHECK_CUDA(b2_launch(norm_act_kernel, dim3(gx, d->batch), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, 
+  {
+    const int c8n = C >> 3;
+    int g = c8n, r = 256;   // gcd(c8n, 256)
+    while (r) { const int t = g % r; g = r; r = t; }
+    const int m = c8n / g;   // gridDim.x must be a multiple of m for the fixed-octet path
+    if (m > 1 && (int64_t)gx * 256 < items) gx = (gx + m - 1) / m * m;
+  }
+  B2_CHECK_CUDA(b2_launch(kern, dim3(gx, d->batch), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream,
       *d, (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, a, b, mean_rstd, (__nv_bfloat16*)y));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
