@@ -743,7 +743,12 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     CUresult r;
     if (pl->halo) {
       const long long t1 = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
-      pl->halo_td = d->in_d >= 2 && t1 >= b2_num_sms() ? 2 : 1;
+      {  // planes per tile: 2 (weight stage shared by two planes, two MMA issuer warps) unless that costs a wave
+        const long long sms = b2_num_sms(), nt = g.n_pad / g.block_n;
+        const long long t_one = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * d->in_d * d->batch;
+        const long long cost2 = (t1 * nt + sms - 1) / sms * 2, cost1 = (t_one * nt + sms - 1) / sms;
+        pl->halo_td = d->in_d >= 2 && cost2 <= cost1 ? 2 : 1;
+      }
       halo_ring_config(g.block_n, &pl->halo_nb, &pl->halo_tps);
       // packed weights [n_pad rows][chunk*27 + tap][64] viewed as 3-D {64, rows, tap-chunks}: one box = TPS consecutive taps
       cuuint64_t dims3[3] = {64, (cuuint64_t)g.n_pad, (cuuint64_t)(g.ktot / 64)};
@@ -798,7 +803,8 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // staged (TMA-store) epilogue of the per-tap GEMM kernel: bf16 NDHWC output with whole 64-channel groups
   memset(&pl->om, 0, sizeof(pl->om));
   {
-    bool want = cl_m * cl_n == 1 && d->y_dtype == B200DM_BF16 && d->reserved[1] == 0 && !prelu_alpha &&
+    const bool f32 = d->y_dtype == B200DM_F32;   // fp32 output (the U-Net's eps): halo kernel only, 32-column groups
+    bool want = cl_m * cl_n == 1 && (!f32 || pl->halo) && d->reserved[1] == 0 && !prelu_alpha &&
                 d->c_out % 64 == 0 && g.block_n >= 64 && !(d->mode == B200DM_CONV_PARITY && residual);
     if (const char* e = getenv("B200DM_TMA_EPI")) { if (atoi(e) == 0) want = false; }
     if (want) {
@@ -807,12 +813,13 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       const cuuint64_t C = (cuuint64_t)d->c_out;
       auto encodeY = [&](CUtensorMap* m, const void* base) -> bool {
         cuuint64_t dims[5] = {C, (cuuint64_t)g.m_w, (cuuint64_t)g.m_h, (cuuint64_t)g.m_d, (cuuint64_t)d->batch};
-        cuuint64_t strides[4] = {C * 2 * ps, (cuuint64_t)g.out_w * C * 2 * ps, (cuuint64_t)g.out_h * g.out_w * C * 2 * ps,
-                                 (cuuint64_t)g.out_d * g.out_h * g.out_w * C * 2};
-        cuuint32_t box[5] = {64, (cuuint32_t)g.box_w, (cuuint32_t)g.box_h, (cuuint32_t)g.box_d, (cuuint32_t)g.box_n};
+        const cuuint64_t eb = f32 ? 4 : 2;
+        cuuint64_t strides[4] = {C * eb * ps, (cuuint64_t)g.out_w * C * eb * ps, (cuuint64_t)g.out_h * g.out_w * C * eb * ps,
+                                 (cuuint64_t)g.out_d * g.out_h * g.out_w * C * eb};
+        cuuint32_t box[5] = {f32 ? 32u : 64u, (cuuint32_t)g.box_w, (cuuint32_t)g.box_h, (cuuint32_t)g.box_d, (cuuint32_t)g.box_n};
         if (pl->halo) { box[1] = 8; box[2] = 16; box[3] = 1; box[4] = 1; }   // one output plane of the halo kernel's tile
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
-        return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
       };
       bool okm = true;

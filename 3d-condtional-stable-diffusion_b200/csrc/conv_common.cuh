@@ -228,6 +228,50 @@ __device__ __forceinline__ void conv_epilogue16_staged(const ConvParams& p, cons
   *reinterpret_cast<bf16x8*>(stg + o1) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
 }
 
+// fp32 form of the staged epilogue: 16 columns = 64 bytes = four 16-byte units of a [128 rows][128 B] tile that holds
+// 32 fp32 columns (c_local = 0 or 16 within the 32-column group); bias / scale / act / register residual as above.
+__device__ __forceinline__ void conv_epilogue16_staged_f32(const ConvParams& p, const uint32_t (&rr)[16], int r, int c_local,
+                                                           const float* bs, const float* sc, uint8_t* stg, bool has_rpre,
+                                                           const bf16x8* rpre) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+  if (sc) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+      v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+    }
+  }
+  if (bs) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (p.act != B200DM_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+  }
+  if (has_rpre) {
+    float a[16];
+    unpack8(rpre[0], *reinterpret_cast<float(*)[8]>(&a[0]));
+    unpack8(rpre[1], *reinterpret_cast<float(*)[8]>(&a[8]));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += a[j];
+  }
+  if (p.post_act != B200DM_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+  }
+  const int u0 = c_local >> 2, sw = r & 7;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<float4*>(stg + (uint32_t)r * 128u + (uint32_t)(((u0 + u) ^ sw) << 4)) =
+        make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+}
+
 // Stage bias[col] (+ chan_bias row `cbrow` when given) for columns [col_base, col_base + ncols) into shared memory.
 // With an output affine, dst_scale[c] = scale and dst[c] = scale * bias + shift.
 // Called by the epilogue threads (tid 0..nthreads-1); columns past c_out read as 0.

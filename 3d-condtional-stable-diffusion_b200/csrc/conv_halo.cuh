@@ -17,7 +17,7 @@
 //             MMA only 48, so one tap per round trip is issue-bound; three are not.
 //   TMEM      2 accumulator stages x TD x BLOCK_N columns: the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Warps (384 threads): 0 = slab producer, 1 = weight producer, 2 = TMEM owner + MMA issuer, 3 = idle, 4-11 = epilogue.
+// Warps (384 threads): 0 = slab producer, 1 = weight producer, 2 = TMEM owner + MMA issuer, 3 = second MMA issuer (TD = 2), 4-11 = epilogue.
 // Every role loop is warp-uniform; a single elected lane (elect.sync) issues TMA / tcgen05 instructions.
 #pragma once
 #include "conv_common.cuh"
@@ -62,6 +62,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   static_assert(TPS == 1 || TPS == 3, "taps per weight stage: 1 or 3");
   constexpr int kTapBytes = BLOCK_N * 128;
   constexpr int kBBytes = TPS * kTapBytes;
+  // MMA issuer warps: with TD = 2 each output plane (its own TMEM accumulator) is driven by its own warp.  Measured
+  // (clock64 timeline): one issuing thread spends ~280 cycles per weight stage on barrier waits / commits / descriptor
+  // arithmetic during which the shallow tcgen05 queue drains (59 cycles per N=64 MMA instead of the 48-cycle floor);
+  // two independent issuers hide each other's bookkeeping.
+  constexpr int kIssuers = TD == 2 ? 2 : 1;
   constexpr uint32_t kAccCols = TD * BLOCK_N;
   constexpr uint32_t kTmemCols = (2 * kAccCols) < 32 ? 32 : 2 * kAccCols;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two <= 512");
@@ -89,9 +94,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), 1); }
-    for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), 1); ptx::mbar_init(tmem_empty(s), 8); }
+    for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), kIssuers); }
+    for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), kIssuers); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
@@ -148,8 +153,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         if (++s == NB) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 2) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 2 || (warp == 3 && kIssuers == 2)) {
+    // ===================== MMA issuer(s) =====================
+    const int pl_lo = kIssuers == 2 ? warp - 2 : 0, pl_hi = kIssuers == 2 ? warp - 1 : TD;   // planes this warp drives
+    const bool tr = warp == 2 && lane == 0;
     // Descriptors are formed by ADDING 16-byte units to precomputed 64-bit bases (the 14-bit address field cannot
     // carry: smem < 256 KB); inside a stage every offset is a compile-time immediate.
     constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
@@ -160,10 +167,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     int ti = 0;
     for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step, ++it) {
       const uint32_t as = it & 1;
-      if (lane == 0) trace_ev(p, 0, ti, 1);
+      if (tr) trace_ev(p, 0, ti, 1);
       ok = ptx::mbar_wait(tmem_empty(as), ((it >> 1) & 1) ^ 1, p.dbg, 13);
       if (!ok) break;
-      if (lane == 0) trace_ev(p, 0, ti, 2);
+      if (tr) trace_ev(p, 0, ti, 2);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + as * kAccCols;
       for (int j = 0; j < nch && ok; ++j, q += TD + 2) {
@@ -175,7 +182,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             ok = ptx::mbar_wait(slab_full((q + kd + TD - 1) % NS), ((q + kd + TD - 1) / NS) & 1, p.dbg, 14);
           }
           if (!ok) break;
-          if (lane == 0) trace_ev(p, 0, ti, 3);
+          if (tr) trace_ev(p, 0, ti, 3);
           uint64_t a_pl[TD];
 #pragma unroll
           for (int pl = 0; pl < TD; ++pl) a_pl[pl] = a_desc0 + (uint64_t)(((q + pl + kd) % NS) * (kSlabBytes >> 4));
@@ -195,6 +202,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                   const uint32_t first = (kw != 0) ? 1u : (first_kd | (kh != 0 ? 1u : 0u));
 #pragma unroll
                   for (int pl = 0; pl < TD; ++pl) {
+                    if (pl < pl_lo || pl >= pl_hi) continue;
                     const uint64_t da = a_pl[pl] + (uint64_t)(kh * 80 + kw * 8);   // (kh*10+kw) rows of 128 B in 16-B units
                     const uint64_t db = db0 + (uint64_t)(u * (kTapBytes >> 4));
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da, db, idesc, first);
@@ -210,7 +218,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
           }
           if (!ok) break;
-          if (lane == 0) trace_ev(p, 0, ti, 4);
+          if (tr) trace_ev(p, 0, ti, 4);
           // slab pl is last used at kd = min(pl, 2)
           if (ptx::elect_one()) {
             if (kd < 2) ptx::tc_commit(slab_empty((q + kd) % NS));
@@ -279,7 +287,41 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         stage_bias(p, bs, scs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128, 256);
         epilogue_bar_sync256();
       }
-      if constexpr (STAGED) {
+      if (STAGED && p.y_f32) {
+        // fp32 output (eps of the U-Net): 32-column groups of 128-byte rows; the staging area (two 16 KB slots) holds one
+        // group per column half, so BLOCK_N = 128 takes two rounds per plane
+        constexpr int kRounds = kHalfCols / 32;
+#pragma unroll
+        for (int pl = 0; pl < TD; ++pl) {
+          const int od = t.d0 + pl;
+          if (od >= p.out_d) break;   // CTA-uniform
+          uint8_t* stg = stg_base + half * 16384;
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N + cbase;
+#pragma unroll
+          for (int rd = 0; rd < kRounds; ++rd) {
+            if (warp == 4 && lane == 0) ptx::bulk_wait_read_all();   // the previous round's stores have left the staging
+            epilogue_bar_sync256();
+            uint32_t ra[16], rb[16];
+            ptx::tc_ld_32x32b_x16(taddr + rd * 32, ra);
+            ptx::tc_ld_32x32b_x16(taddr + rd * 32 + 16, rb);
+            ptx::tc_wait_ld();
+            conv_epilogue16_staged_f32(p, ra, r, 0, has_bs ? bs + cbase + rd * 32 : nullptr, has_sc ? scs + cbase + rd * 32 : nullptr,
+                                       stg, pre, rpre[pl][2 * rd]);
+            conv_epilogue16_staged_f32(p, rb, r, 16, has_bs ? bs + cbase + rd * 32 + 16 : nullptr,
+                                       has_sc ? scs + cbase + rd * 32 + 16 : nullptr, stg, pre, rpre[pl][2 * rd + 1]);
+            ptx::fence_proxy_async();
+            epilogue_bar_sync256();
+            if (warp == 4 && lane == 0) {
+              for (int h = 0; h < 2; ++h) {
+                const int col = t.n_tile * BLOCK_N + h * kHalfCols + rd * 32;
+                if (col < p.c_out) ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + h * 16384), col, t.w0, t.h0, od, t.n);
+              }
+              ptx::bulk_commit_group();
+            }
+          }
+        }
+        nstore = 0;   // (buffer rotation is a bf16-path notion)
+      } else if constexpr (STAGED) {
         // bf16 plane tile -> swizzled smem -> one TMA store per 64-channel group (whole 128-byte rows, edges clipped by
         // the TMA unit) instead of row-per-thread 16-byte stores that touch 32 lines per instruction
         constexpr int kNG = BLOCK_N / 64, kBufs = stage_bufs(BLOCK_N);

@@ -23,7 +23,7 @@ _lib.check(_lib.lib().b200dm_conv_plan_set_trace(plan.h, C.c_void_p(tr.data_ptr(
 plan.run()
 torch.cuda.synchronize()
 t = tr.cpu().view(4, 2048)
-names = {1: "tile:begin", 2: "tile:tmem_empty ok", 3: "kd:slabs ready", 4: "kd:issued", 10: "epi:wait", 11: "epi:tmem_full ok", 12: "epi:done"}
+names = {1: "tile:begin", 2: "tile:tmem_empty ok", 3: "kd:slabs ready", 4: "kd:issued", 5: "b?", 6: "b:waited", 7: "b:pre", 10: "epi:wait", 11: "epi:tmem_full ok", 12: "epi:done"}
 t0 = min(int(v) >> 8 for v in t[0] if int(v) != 0)
 for region, label in ((0, "MMA"), (1, "EPI"), (2, "SLAB")):
     prev = None
@@ -36,5 +36,5 @@ for region, label in ((0, "MMA"), (1, "EPI"), (2, "SLAB")):
         out.append(f"{names.get(tag, 'slab'+str(tag-20))}@{clk}" + (f"(+{clk-prev})" if prev is not None else ""))
         prev = clk
     print(label, len(out))
-    for i in range(0, min(len(out), 60), 6):
+    for i in range(0, min(len(out), int(os.environ.get('NEV', '60'))), 6):
         print("   ", "  ".join(out[i:i + 6]))
