@@ -33,8 +33,9 @@ constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 
 // CMODE 0: plain; 1: cluster with TMA-multicast operands (experiment); 2: split-K cluster (K range per CTA, partial
 // accumulators reduced through distributed shared memory by the cluster's first CTA).
+// (two-stage instantiations: registers capped so that four CTAs share an SM -- see conv_plan_create)
 template <int BLOCK_N, int NSTAGE, int CMODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, NSTAGE == 2 ? 4 : 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvOutMaps om, const ConvParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
@@ -800,6 +801,9 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // pipeline depth 4; measured on B200: a deeper ring (6 stages at BLOCK_N=128, 8 below) does not help at BLOCK_N=128 (the
   // operand stream is bandwidth-, not latency-bound) and hurts below 128, where 4 stages let two CTAs share an SM
   pl->nstage = 4;
+  // short K loops (1^3 convs: 1-3 k-blocks) never fill four stages; two stages let 3-4 CTAs share an SM, which hides the
+  // per-CTA prologue / TMA latency / epilogue of these HBM-bound launches
+  if ((g.nch0 + g.nch1) * g.ntaps <= 3 && g.block_n >= 64 && cl_m * cl_n == 1 && !getenv("B200DM_IGEMM_NO2")) pl->nstage = 2;
   // staged (TMA-store) epilogue of the per-tap GEMM kernel: bf16 NDHWC output with whole 64-channel groups
   memset(&pl->om, 0, sizeof(pl->om));
   {
@@ -881,6 +885,12 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
       case 32: return dispatch_halo<32, 4, 3>(pl, s);
       case 64: return dispatch_halo<64, 3, 3>(pl, s);
       case 128: return dispatch_halo<128, 4, 1>(pl, s);
+    }
+  }
+  if (pl->nstage == 2) {
+    switch (pl->g.block_n) {
+      case 64: return launch_conv<64, 2>(pl, s);
+      case 128: return launch_conv<128, 2>(pl, s);
     }
   }
   switch (pl->g.block_n) {
