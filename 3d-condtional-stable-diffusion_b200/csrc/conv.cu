@@ -804,6 +804,13 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // short K loops (1^3 convs: 1-3 k-blocks) never fill four stages; two stages let 3-4 CTAs share an SM, which hides the
   // per-CTA prologue / TMA latency / epilogue of these HBM-bound launches
   if ((g.nch0 + g.nch1) * g.ntaps <= 3 && g.block_n >= 64 && cl_m * cl_n == 1 && !getenv("B200DM_IGEMM_NO2")) pl->nstage = 2;
+  // grids of several waves: two stages x three co-resident CTAs keep more operand bytes in flight per SM than one CTA with
+  // four stages, and hide every CTA's prologue / epilogue (measured: 16^3 128->128 parity conv 123 -> 77 us, 8^3 MLP GEMM
+  // 17.5 -> 12.7 us; a single-wave split-K grid gets slower, so it keeps four stages)
+  if (!pl->halo && (long long)pl->grid.x * pl->grid.y * pl->grid.z >= 2LL * b2_num_sms() && g.block_n >= 64 && p.ksplit <= 1 &&
+      cl_m * cl_n == 1 && !getenv("B200DM_IGEMM_NO2"))
+    pl->nstage = 2;
+  if (const char* e = getenv("B200DM_IGEMM_STAGES")) { if (atoi(e) == 2 && g.block_n >= 64 && cl_m * cl_n == 1) pl->nstage = 2; if (atoi(e) == 4) pl->nstage = 4; }
   // staged (TMA-store) epilogue of the per-tap GEMM kernel: bf16 NDHWC output with whole 64-channel groups
   memset(&pl->om, 0, sizeof(pl->om));
   {
