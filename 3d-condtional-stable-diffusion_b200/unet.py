@@ -171,7 +171,7 @@ class UNet:
 
         def conv(x0, kname, cout, y=None, x1=None, k=3, stride=1, mode=L.CONV_DIRECT, act=None, bias=True, chan_bias=None,
                  residual=None, y_dtype=torch.bfloat16, transposed_store=False, dense=False, out_affine=None, note="",
-                 kern=None):
+                 kern=None, bias_t=None):
             Bx, D, H, Wd, c0 = x0.shape
             c1 = x1.shape[-1] if x1 is not None else 0
             desc = ops.make_conv_desc(mode, Bx, (D, H, Wd), c0, c1, cout, k, stride, act, None, y_dtype,
@@ -184,7 +184,8 @@ class UNet:
             if y is None:
                 od, oh, ow = ops.conv_out_shape(mode, (D, H, Wd), stride)
                 y = pr.buf((Bx, cout, od * oh * ow) if transposed_store else (Bx, od, oh, ow, cout), y_dtype)
-            return pr.conv(desc, x0, wp, y, x1=x1, bias=g(f"{kname}.bias") if bias else None, chan_bias=chan_bias,
+            bias_dev = None if not bias else (bias_t.to(dev).contiguous() if bias_t is not None else g(f"{kname}.bias"))
+            return pr.conv(desc, x0, wp, y, x1=x1, bias=bias_dev, chan_bias=chan_bias,
                            t_dev=self.t_dev if chan_bias is not None else None, residual=residual, out_affine=out_affine,
                            note=note or kname)
 
@@ -253,8 +254,13 @@ class UNet:
             n, c, s = b["name"], b["c"], b["s"]
             Lq = s ** 3
             scale = float(c) ** -0.5
-            nrm, _ = bn_act(x, f"{n}.norm", None)
-            h = conv(nrm, f"{n}.proj_in", c, k=1, act="relu")
+            # inference BatchNorm followed by the 1^3 proj_in conv is one affine map: fold it into proj_in's kernel and bias
+            # (W' = diag(a) W, b' = b + shift . W; conditional_dm3d.py:187-188) -- no normalisation pass
+            sc_n, sh_n = ops.bn_fold(g(f"{n}.norm.gamma"), g(f"{n}.norm.beta"), g(f"{n}.norm.mean"), g(f"{n}.norm.var"), 1e-3)
+            w_in = P[f"{n}.proj_in.kernel"].reshape(c, c)
+            w_fold = (sc_n.cpu()[:, None] * w_in).reshape(1, 1, 1, c, c)
+            b_fold = P[f"{n}.proj_in.bias"] + sh_n.cpu() @ w_in
+            h = conv(x, f"{n}.proj_in", c, k=1, act="relu", kern=w_fold, bias_t=b_fold)
             gam = [g(f"{n}.norm{i}.gamma") for i in (1, 2, 3)]
             bet = [g(f"{n}.norm{i}.beta") for i in (1, 2, 3)]
             ln = pr.layernorm(h, gam, bet, [pr.buf(h.shape) for _ in range(3)], 1e-3, note=f"{n}.ln")
