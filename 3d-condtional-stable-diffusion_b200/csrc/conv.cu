@@ -482,6 +482,7 @@ struct b200dm_conv_plan {
   int nstage;
   double flops;
   bool halo = false;
+  bool pair = false;   // halo kernel on 8 x 8 planes: 8w x 8h x 2d tiles from pair slabs (conv_halo.cuh)
   int halo_td = 1, halo_nb = 4, halo_tps = 1;
 };
 
@@ -640,6 +641,19 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
   return B200DM_OK;
 }
 
+constexpr int kHaloNSPair = 4;   // pair slabs are 25 KB; three per channel chunk are live
+
+static int launch_halo_pair(const b200dm_conv_plan* pl, cudaStream_t s) {
+  auto kern = halo::conv_halo_kernel<64, 1, kHaloNSPair, 3, 3, true, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    attr_set = true;
+  }
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
+  return B200DM_OK;
+}
+
 // weight-ring depth / taps per stage by BLOCK_N (smem: 6 slabs x 23 KB + NB x TPS x BLOCK_N x 128 B <= 227 KB)
 static void halo_ring_config(int block_n, int* nb, int* tps) {
   if (block_n >= 128) { *nb = 4; *tps = 1; }
@@ -657,8 +671,8 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 
 static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const bool st = pl->p.tma_epi != 0;
-  const int ns = st ? kHaloNSStaged : kHaloNS;
-  return 1024 + (size_t)ns * halo::kSlabBytes + (size_t)pl->halo_nb * pl->halo_tps * pl->g.block_n * 128 +
+  const int ns = pl->pair ? kHaloNSPair : (st ? kHaloNSStaged : kHaloNS);
+  return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) + (size_t)pl->halo_nb * pl->halo_tps * pl->g.block_n * 128 +
          (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
 }
 
@@ -688,6 +702,12 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // halo-reuse kernel: 3^3 stride-1 convs on volumes that fill its 8w x 16h tile (use_halo = -1 forces it off)
   pl->halo = d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w >= 8 && d->in_h >= 16 &&
              d->reserved[1] == 0 && d->use_halo >= 0;
+  // 8 x 8 planes (the U-Net's deepest level): pair-slab tiles, 64 output channels per CTA so that >= 128 CTAs share the
+  // weight stream; bf16 staged output only
+  pl->pair = !pl->halo && d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w == 8 && d->in_h == 8 &&
+             d->in_d >= 2 && d->reserved[1] == 0 && d->use_halo >= 0 && d->y_dtype == B200DM_BF16 && d->c_out % 64 == 0 &&
+             !prelu_alpha && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) && !getenv("B200DM_NO_PAIR");
+  if (pl->pair) { pl->halo = true; g.block_n = 64; pl->g.block_n = 64; }
   // igemm cluster (see the kernel): cl_n n-tiles share A, cl_m m-tiles share B; B200DM_CLUSTER="m,n" switches it on.
   int cl_m = 1, cl_n = 1, a_split_dim = 0, a_split_ext = 0;
   if (!pl->halo && st == 1) {
@@ -717,7 +737,12 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)d->in_w * C * 2, (cuuint64_t)d->in_h * d->in_w * C * 2,
                              (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)(g.box_w * st), (cuuint32_t)(g.box_h * st), (cuuint32_t)(g.box_d * st), (cuuint32_t)g.box_n};
-    if (pl->halo) { box[1] = 10; box[2] = 18; box[3] = 1; box[4] = 1; }   // one halo d-plane slab
+    if (pl->pair) {   // dims listed as (C, W, D, H, N): the box {64, 10, 2, 10, 1} lands as rows [h][d][w]
+      dims[2] = (cuuint64_t)d->in_d; dims[3] = (cuuint64_t)d->in_h;
+      const cuuint64_t sh = strides[1], sd = strides[2];
+      strides[1] = sd; strides[2] = sh;
+      box[1] = 10; box[2] = 2; box[3] = 10; box[4] = 1;
+    } else if (pl->halo) { box[1] = 10; box[2] = 18; box[3] = 1; box[4] = 1; }   // one halo d-plane slab
     else if (cl_n > 1) box[a_split_dim] = (cuuint32_t)a_split_ext;          // this CTA's share of the multicast A tile
 
     cuuint32_t es[5] = {1, (cuuint32_t)st, (cuuint32_t)st, (cuuint32_t)st, 1};
@@ -749,6 +774,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
         const long long t_one = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * d->in_d * d->batch;
         const long long cost2 = (t1 * nt + sms - 1) / sms * 2, cost1 = (t_one * nt + sms - 1) / sms;
         pl->halo_td = d->in_d >= 2 && cost2 <= cost1 ? 2 : 1;
+        if (pl->pair) pl->halo_td = 2;   // d step of a pair tile (the kernel runs with one accumulator, TD = 1)
       }
       halo_ring_config(g.block_n, &pl->halo_nb, &pl->halo_tps);
       // packed weights [n_pad rows][chunk*27 + tap][64] viewed as 3-D {64, rows, tap-chunks}: one box = TPS consecutive taps
@@ -828,7 +854,12 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
         cuuint64_t strides[4] = {C * eb * ps, (cuuint64_t)g.out_w * C * eb * ps, (cuuint64_t)g.out_h * g.out_w * C * eb * ps,
                                  (cuuint64_t)g.out_d * g.out_h * g.out_w * C * eb};
         cuuint32_t box[5] = {f32 ? 32u : 64u, (cuuint32_t)g.box_w, (cuuint32_t)g.box_h, (cuuint32_t)g.box_d, (cuuint32_t)g.box_n};
-        if (pl->halo) { box[1] = 8; box[2] = 16; box[3] = 1; box[4] = 1; }   // one output plane of the halo kernel's tile
+        if (pl->pair) {   // (C, W, D, H, N) order, one 8w x 2d x 8h tile
+          dims[2] = (cuuint64_t)g.m_d; dims[3] = (cuuint64_t)g.m_h;
+          const cuuint64_t sh = strides[1], sd = strides[2];
+          strides[1] = sd; strides[2] = sh;
+          box[1] = 8; box[2] = 2; box[3] = 8; box[4] = 1;
+        } else if (pl->halo) { box[1] = 8; box[2] = 16; box[3] = 1; box[4] = 1; }   // one output plane of the halo kernel's tile
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
         return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -865,7 +896,8 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   if (pl->smem > 232448) { p.tma_epi = 0; pl->smem = conv_smem_bytes(g.block_n, pl->nstage, false); }
   if (pl->halo) {
     const int td = pl->halo_td;
-    p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td; p.tiles_n = d->batch;
+    p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = pl->pair ? (d->in_h + 7) / 8 : (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td;
+    p.tiles_n = d->batch;
     const long long per = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
     p.halo_td = td; p.halo_tiles_per_ntile = (int)per; p.halo_ntn = ntiles; p.halo_total_tiles = (int)(per * ntiles);
     int ctas = b2_num_sms();
@@ -886,6 +918,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
 extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
+  if (pl->pair) return launch_halo_pair(pl, s);
   if (pl->halo) {
     switch (pl->g.block_n) {
       case 16: return dispatch_halo<16, 4, 3>(pl, s);
@@ -925,6 +958,7 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   B2_CHECK_ARG(p && y_extra && scale && shift, "conv_plan_add_output: null argument");
   B2_CHECK_ARG(p->desc.c_out % 16 == 0 && p->desc.reserved[1] == 0, "conv_plan_add_output: needs c_out %% 16 == 0 and a plain (non-transposed) store");
   B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
+  if (p->pair) { b200dm_set_error("conv_plan_add_output: not available on pair-slab (8 x 8 plane) plans"); return B200DM_ERR_UNSUPPORTED; }
   if (p->p.tma_epi) { p->p.tma_epi = 0; p->smem = p->halo ? halo_smem_bytes(p) : conv_smem_bytes(p->g.block_n, p->nstage, false); }
   if (!p->p.y2) { p->p.y2 = (__nv_bfloat16*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (__nv_bfloat16*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }

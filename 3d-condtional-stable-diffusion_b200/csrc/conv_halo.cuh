@@ -39,12 +39,13 @@ struct Tile {
   int w0, h0, d0, n, n_tile;
 };
 
+template <bool PAIR = false>
 __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int id) {
   Tile t;
   t.n_tile = id / p.halo_tiles_per_ntile;
   int r = id - t.n_tile * p.halo_tiles_per_ntile;
   t.w0 = (r % p.tiles_w) * 8; r /= p.tiles_w;
-  t.h0 = (r % p.tiles_h) * 16; r /= p.tiles_h;
+  t.h0 = (r % p.tiles_h) * (PAIR ? 8 : 16); r /= p.tiles_h;
   t.d0 = (r % p.tiles_d) * p.halo_td; r /= p.tiles_d;
   t.n = r;
   return t;
@@ -54,12 +55,20 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int id) {
 constexpr int stage_bufs(int block_n) { return block_n == 64 ? 2 : 1; }
 constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs(block_n) * (block_n / 64) * 16384 : 0; }
 
-template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED>
+// PAIR (small planes, 8 x 8: the 8^3 level of the U-Net): the tile is 8 w x 8 h x 2 d.  The activation tensor map lists
+// its dims as (C, W, D, H, N), so one box {64, 10, 2, 10, 1} lands in smem as rows [h][d][w]: the 16 eight-row groups of
+// the M = 128 operand (group = h * 2 + d) are again a uniform 10 rows apart, the (kh, kw) tap shift is (kh * 20 + kw) rows,
+// and each kd tap reads its own pair slab (planes d0 + kd - 1, d0 + kd).  TD = 1; staged epilogue only.
+template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const ConvParams p) {
   static_assert(!STAGED || BLOCK_N >= 64, "staged epilogue works on whole 64-channel groups");
   static_assert(TPS == 1 || TPS == 3, "taps per weight stage: 1 or 3");
+  static_assert(!PAIR || (STAGED && TD == 1), "pair-slab tiles: one accumulator, staged epilogue");
+  constexpr int kSlabBytes = PAIR ? 25 * 1024 : halo::kSlabBytes;   // 200 (pair) / 180 rows of 128 B, 1 KB-rounded
+  constexpr int kSlabTx = PAIR ? 200 * 128 : halo::kSlabTx;
+  constexpr int kKhUnits = PAIR ? 160 : 80;                          // one kh step in 16-byte units (20 / 10 rows)
   constexpr int kTapBytes = BLOCK_N * 128;
   constexpr int kBBytes = TPS * kTapBytes;
   // MMA issuer warps: with TD = 2 each output plane (its own TMEM accumulator) is driven by its own warp.  Measured
@@ -118,7 +127,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     bool ok = true;
     int ti = 0;
     for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step) {
-      const Tile t = decode_tile(p, id);
+      const Tile t = decode_tile<PAIR>(p, id);
       for (int j = 0; j < nch && ok; ++j) {
         const CUtensorMap* map = j < p.nch0 ? &mapA0 : &mapA1;
         const int c0 = (j < p.nch0 ? j : j - p.nch0) * 64;
@@ -128,7 +137,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (lane == 0) trace_ev(p, 2, ti, 20 + pl);
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(slab_full(s), kSlabTx);
-            ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.h0 - 1, t.d0 - 1 + pl, t.n);
+            if (PAIR) ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.d0 - 1 + pl, t.h0 - 1, t.n);
+            else ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.h0 - 1, t.d0 - 1 + pl, t.n);
           }
           __syncwarp();
           if (++s == NS) { s = 0; ph ^= 1; }
@@ -140,7 +150,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     uint32_t s = 0, ph = 1;
     bool ok = true;
     for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step) {
-      const Tile t = decode_tile(p, id);
+      const Tile t = decode_tile<PAIR>(p, id);
       const int row0 = t.n_tile * BLOCK_N;
       for (int kb = 0; kb < nch * 27; kb += TPS) {
         ok = ptx::mbar_wait(b_empty(s), ph, p.dbg, 12);
@@ -203,7 +213,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
                   for (int pl = 0; pl < TD; ++pl) {
                     if (pl < pl_lo || pl >= pl_hi) continue;
-                    const uint64_t da = a_pl[pl] + (uint64_t)(kh * 80 + kw * 8);   // (kh*10+kw) rows of 128 B in 16-B units
+                    const uint64_t da = a_pl[pl] + (uint64_t)(kh * kKhUnits + kw * 8);   // (kh*10+kw) rows of 128 B in 16-B units
                     const uint64_t db = db0 + (uint64_t)(u * (kTapBytes >> 4));
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da, db, idesc, first);
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 2, db + 2, idesc, 1u);
@@ -243,13 +253,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const bool active = BLOCK_N >= 32 || half == 0;
     const int cbase = BLOCK_N >= 32 ? half * kHalfCols : 0;
     const int r = qd * 32 + lane;
-    const int iw = r & 7, ih = r >> 3;
+    const int iw = r & 7, ih = PAIR ? (r >> 4) : (r >> 3), idp = PAIR ? ((r >> 3) & 1) : 0;   // PAIR: row group = h * 2 + d
     const int64_t vox_per = (int64_t)p.out_d * p.out_h * p.out_w;
     uint32_t it = 0;
     int ti = 0;
     uint32_t nstore = 0;   // staged epilogue: plane stores issued so far (selects the staging buffer)
     for (int id = first_tile; id < p.halo_total_tiles; id += tile_step, ++it) {
-      const Tile t = decode_tile(p, id);
+      const Tile t = decode_tile<PAIR>(p, id);
       const uint32_t as = it & 1;
       const int ow = t.w0 + iw, oh = t.h0 + ih;
       const int colt = t.n_tile * BLOCK_N + cbase;       // first output channel of this warp
@@ -259,7 +269,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       if (pre) {
 #pragma unroll
         for (int pl = 0; pl < TD; ++pl) {
-          const int od = t.d0 + pl;
+          const int od = t.d0 + pl + idp;
           if (ow < p.out_w && oh < p.out_h && od < p.out_d) {
             const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;
             const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + ((int64_t)t.n * vox_per + vox) * p.c_out + colt);
@@ -353,8 +363,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (warp == 4 && lane == 0) {
             for (int g = 0; g < kNG; ++g)
               if (t.n_tile * BLOCK_N + g * 64 < p.c_out)
-                ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.n_tile * BLOCK_N + g * 64,
-                                  t.w0, t.h0, od, t.n);
+                if (PAIR) ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.n_tile * BLOCK_N + g * 64,
+                                            t.w0, od, t.h0, t.n);
+                else ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.n_tile * BLOCK_N + g * 64,
+                                       t.w0, t.h0, od, t.n);
             ptx::bulk_commit_group();
           }
           ++nstore;

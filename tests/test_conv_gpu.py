@@ -75,6 +75,23 @@ def test_conv3_bf16_out_and_epilogue(cuda):
     _close(y, ref, tol=6e-3, what="conv3 + bias + temb + silu + residual (bf16 out)")
 
 
+def test_conv3_pair_slab_tiles(cuda):
+    """8 x 8 planes (the U-Net's 8^3 level): pair-slab halo tiles, two K segments, odd depth (ragged last pair)."""
+    from b200dm import ops
+    for (B, D, c0, c1, cout) in ((2, 8, 256, 256, 256), (1, 5, 64, 0, 64)):
+        x0 = _rand((B, D, 8, 8, c0), 1)
+        x1 = _rand((B, D, 8, 8, c1), 6) if c1 else None
+        w = _rand((3, 3, 3, c0 + c1, cout), 2, 1.0 / np.sqrt(27 * (c0 + c1)))
+        b = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+        res = _rand((B, D, 8, 8, cout), 5)
+        xin = x0 if x1 is None else torch.cat([x0, x1], -1)
+        ref = O.conv3d(xin, w, b) + res
+        y = ops.conv3d(x0.to(cuda, torch.bfloat16), w, bias=b.to(cuda), residual=res.to(cuda, torch.bfloat16),
+                       x1=None if x1 is None else x1.to(cuda, torch.bfloat16))
+        _check_flag()
+        _close(y, ref, tol=6e-3, what=f"pair-slab conv3 B{B} D{D} {c0}+{c1}->{cout}")
+
+
 def test_conv3_two_segments(cuda):
     from b200dm import ops
     B, S, c0, c1, cout = 2, 8, 64, 32, 64
