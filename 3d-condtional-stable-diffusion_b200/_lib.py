@@ -90,6 +90,7 @@ _SIGS = {
     "b200dm_conv_plan_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200dm_conv_plan_set_out_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200dm_conv_plan_add_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "b200dm_conv_plan_set_side_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b200dm_conv_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b200dm_attention_plan_create": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 5 + [C.POINTER(C.c_void_p)]),
     "b200dm_attention_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -47,7 +47,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const bool staged = BLOCK_N >= 64 && CMODE != 1 && p.tma_epi != 0;
   const bool staged_res = staged && p.residual != nullptr;
   uint8_t* res_smem = smem + NSTAGE * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(res_smem + (staged_res ? kResBytes : 0));
+  const bool side_on = BLOCK_N >= 64 && CMODE == 0 && p.side != 0 && blockIdx.y == 0;   // n-tile 0 writes the side output
+  uint8_t* side_smem = res_smem + (staged_res ? kResBytes : 0);                         // [128 rows][128 B] staging + affine table
+  float* side_tab = reinterpret_cast<float*>(side_smem + 16384);                        // [2][side_c]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(side_smem + (p.side ? 16384 + 2 * p.side_c * 4 : 0));
   // bars[0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2NSTAGE] tmem_full, [2NSTAGE+1] residual tile; then tmem ptr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 3);   // (+3 keeps bias_s 16-byte aligned)
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [2][BLOCK_N]: bias (+temb), output-affine scale
@@ -89,7 +92,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t rank_m = CLUSTER ? ptx::cluster_ctaid_x() : 0u, rank_n = CLUSTER ? ptx::cluster_ctaid_y() : 0u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), cl_m * cl_n); }
+    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), cl_m * cl_n + (side_on ? 1u : 0u)); }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
@@ -227,6 +230,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     if (has_bs) {
       stage_bias(p, bias_s, scale_s, n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 64);
       epilogue_bar_sync();
+    }
+    if (BLOCK_N >= 64 && CMODE == 0 && side_on) {
+      // ---- side output: every A tile (one 64-channel chunk of x or skip, 1^3 conv => k-block == chunk) is read back from
+      // shared memory, normalised (+ swish) and TMA-stored at its channel offset of the concatenated tensor; the stage is
+      // released to the producer only after these 128 threads are done with it (empty barrier count 2)
+      const int et = threadIdx.x - 64;
+      for (int c = et; c < p.side_c; c += 128) { side_tab[c] = __ldg(p.side_scale + c); side_tab[p.side_c + c] = __ldg(p.side_shift + c); }
+      epilogue_bar_sync();
+      uint32_t ss = 0, sph = 0;
+      for (int kb = 0; kb < nkb_all; ++kb) {
+        if (!ptx::mbar_wait(full_bar(ss), sph, p.dbg, 5)) break;
+        const int cbase = kb < p.nch0 ? kb * 64 : p.nch0 * 64 + (kb - p.nch0) * 64;   // (c0 % 64 == 0 whenever c1 > 0)
+        if (kb > 0) {   // the previous chunk's store has finished reading the staging tile
+          if (et == 0) ptx::bulk_wait_read_all();
+          epilogue_bar_sync();
+        }
+        const uint8_t* arow = smem + ss * kStageBytes + (uint32_t)r * 128u;
+        uint8_t* srow = side_smem + (uint32_t)r * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t o = (uint32_t)((j ^ (r & 7)) << 4);
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(arow + o), f);
+          const int c = cbase + j * 8;
+          if (c < p.side_c) {   // (side_c % 8 == 0)
+            const float4 a0 = *reinterpret_cast<const float4*>(side_tab + c), a1 = *reinterpret_cast<const float4*>(side_tab + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(side_tab + p.side_c + c), b1 = *reinterpret_cast<const float4*>(side_tab + p.side_c + c + 4);
+            f[0] = apply_act(fmaf(f[0], a0.x, b0.x), p.side_act); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), p.side_act);
+            f[2] = apply_act(fmaf(f[2], a0.z, b0.z), p.side_act); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), p.side_act);
+            f[4] = apply_act(fmaf(f[4], a1.x, b1.x), p.side_act); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), p.side_act);
+            f[6] = apply_act(fmaf(f[6], a1.z, b1.z), p.side_act); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), p.side_act);
+          }
+          *reinterpret_cast<bf16x8*>(srow + o) = pack8(f);
+        }
+        ptx::fence_proxy_async();
+        epilogue_bar_sync();
+        if (et == 0) {
+          ptx::tma_store_5d(&om.s, ptx::smem_u32(side_smem), cbase, w0, h0, d0, n0);
+          ptx::bulk_commit_group();
+          ptx::mbar_arrive(empty_bar(ss));
+        }
+        if (++ss == NSTAGE) { ss = 0; sph ^= 1; }
+      }
+      if (et == 0) ptx::bulk_wait_read_all();
     }
     if (warp == 2 && lane == 0) trace_ev(p, 1, tix, 45);
     const bool ok = ptx::mbar_wait(tmem_full_bar, 0, p.dbg, 3);
@@ -568,13 +615,13 @@ extern "C" int b200dm_conv_pack_weights(const b200dm_conv_desc* d, const float* 
   return B200DM_OK;
 }
 
-static size_t conv_smem_bytes(int block_n, int nstage, bool staged_res) {
-  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (staged_res ? (size_t)block_n * 256 : 0) + (2 * nstage + 3) * 8 + 16 +
-         2 * block_n * 4;
+static size_t conv_smem_bytes(int block_n, int nstage, bool staged_res, int side_c = 0) {
+  return 1024 + (size_t)nstage * (kABytes + block_n * 128) + (staged_res ? (size_t)block_n * 256 : 0) +
+         (side_c > 0 ? 16384 + (size_t)2 * side_c * 4 : 0) + (2 * nstage + 3) * 8 + 16 + 2 * block_n * 4;
 }
 
 static size_t conv_smem_attr(int block_n, int nstage) {   // opt-in ceiling of one kernel instantiation
-  const size_t v = conv_smem_bytes(block_n, nstage, true);
+  const size_t v = conv_smem_bytes(block_n, nstage, true, 1024);
   return v > 232448 ? 232448 : v;
 }
 
@@ -963,6 +1010,34 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   if (!p->p.y2) { p->p.y2 = (__nv_bfloat16*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (__nv_bfloat16*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
   else { b200dm_set_error("conv_plan_add_output: at most two extra outputs"); return B200DM_ERR_UNSUPPORTED; }
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_conv_plan_set_side_norm(b200dm_conv_plan* pl, void* y_side, const float* scale, const float* shift, int32_t act) {
+  B2_CHECK_ARG(pl && y_side && scale && shift, "conv_plan_set_side_norm: null argument");
+  const b200dm_conv_desc* d = &pl->desc;
+  const int C = d->c0 + d->c1;
+  if (pl->halo || !pl->p.tma_epi || pl->p.swap_ab || pl->p.ksplit > 1 || pl->p.cl_m * pl->p.cl_n != 1 || d->mode != B200DM_CONV_DIRECT ||
+      d->ksize != 1 || d->stride != 1 || pl->g.block_n < 64 || (d->c1 > 0 && d->c0 % 64 != 0) || C % 8 != 0 || C > 1024 ||
+      ((uintptr_t)y_side & 15) != 0) {
+    b200dm_set_error("conv_plan_set_side_norm: only on staged 1^3 stride-1 convs (c0 %% 64 == 0 when c1 > 0)");
+    return B200DM_ERR_UNSUPPORTED;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->in_d, (cuuint64_t)d->batch};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)d->in_w * C * 2, (cuuint64_t)d->in_h * d->in_w * C * 2,
+                           (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)pl->g.box_w, (cuuint32_t)pl->g.box_h, (cuuint32_t)pl->g.box_d, (cuuint32_t)pl->g.box_n};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  if (!enc || enc(&pl->om.s, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, y_side, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    b200dm_set_error("conv_plan_set_side_norm: cuTensorMapEncodeTiled failed");
+    return B200DM_ERR_CUDA;
+  }
+  const size_t smem = conv_smem_bytes(pl->g.block_n, pl->nstage, pl->p.residual != nullptr, C);
+  if (smem > conv_smem_attr(pl->g.block_n, pl->nstage)) { b200dm_set_error("conv_plan_set_side_norm: shared memory"); return B200DM_ERR_UNSUPPORTED; }
+  pl->smem = smem;
+  pl->p.side = 1; pl->p.side_act = act; pl->p.side_c = C; pl->p.side_scale = scale; pl->p.side_shift = shift;
   return B200DM_OK;
 }
 

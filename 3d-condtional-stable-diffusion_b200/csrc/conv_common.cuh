@@ -16,6 +16,11 @@ struct ConvParams {
   int chan_bias_rows;
   int halo_td, halo_tiles_per_ntile, halo_ntn, halo_total_tiles;   // halo kernel only
   int tma_epi;                       // staged epilogue: bf16 tile -> swizzled smem -> TMA store (residual tile TMA-loaded)
+  // side output of a 1^3 conv (ResidualBlock shortcut): act(side_scale[c] * x + side_shift[c]) of the conv's own INPUT
+  // channels (both K segments, concatenated), written while the A tiles sit in shared memory -- the block's norm1 +
+  // swish pass (dm3d.py:235-236) without a second read of x / skip
+  int side, side_act, side_c;
+  const float* side_scale; const float* side_shift;
   int swap_ab;                       // transposed store by operand swap: D^T = W X^T (TMEM lane = channel, column = voxel)
   int epi_dbg;                       // tuning aid (B200DM_EPI_DBG): 1 = skip global stores, 2 = skip TMEM loads too
   int ksplit;                        // igemm split-K: cluster of ksplit CTAs per tile, each owns a K range (0/1 = off)
@@ -42,6 +47,7 @@ struct ConvParams {
 struct ConvOutMaps {
   CUtensorMap y[8];
   CUtensorMap r;
+  CUtensorMap s;   // side output (see ConvParams::side)
 };
 
 // timeline regions (each kTraceRegion entries): 0 = MMA issuer, 1 = epilogue warp 4, 2 = slab producer, 3 = weight producer

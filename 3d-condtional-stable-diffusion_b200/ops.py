@@ -237,6 +237,15 @@ class ConvPlan:
         self.keep = self.keep + (y_extra, scale, shift)
         return y_extra
 
+    def set_side_norm(self, y_side, scale, shift, act=None):
+        """1^3 conv only: also write act(scale*x + shift) of the conv's own input channels (x0|x1) to ``y_side``.
+        Returns False when the plan cannot (caller runs a norm pass instead)."""
+        rc = lib().b200dm_conv_plan_set_side_norm(self.h, ptr(y_side), ptr(scale), ptr(shift), L.ACT[act])
+        if rc != 0:
+            return False
+        self.keep = self.keep + (y_side, scale, shift)
+        return True
+
     def run(self):
         check(lib().b200dm_conv_plan_run(self.h, stream()))
         return self.y

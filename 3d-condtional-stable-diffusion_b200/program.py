@@ -39,9 +39,10 @@ class Program:
 
     # -- ops
     def conv(self, desc, x0, w_packed, y, x1=None, bias=None, chan_bias=None, t_dev=None, residual=None,
-             prelu_alpha=None, out_affine=None, note=""):
+             prelu_alpha=None, out_affine=None, note="", side=None):
         plan = ops.ConvPlan(desc, x0, w_packed, y, x1=x1, bias=bias, chan_bias=chan_bias, t_dev=t_dev,
                             residual=residual, prelu_alpha=prelu_alpha, out_affine=out_affine)
+        self.side_ok = side is not None and plan.set_side_norm(*side)   # (y_side, scale, shift, act)
         self.flops += plan.flops
         check(lib().b200dm_program_add_conv(self.h, plan.h))
         plan.release()

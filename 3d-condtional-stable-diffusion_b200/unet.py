@@ -156,6 +156,10 @@ class UNet:
         # norm pass, but measured SLOWER on B200 (cfg-2: 5.47 vs 5.08 ms/step): the extra stores lengthen the conv
         # epilogues, which are on the critical path, by more than the streaming pass costs.  Off unless B200DM_FUSE_NORMS=1.
         self.fuse_norms = os.environ.get("B200DM_FUSE_NORMS", "0") == "1"
+        # norm1 as a side output of the 1^3 shortcut conv (b200dm_conv_plan_set_side_norm): measured SLOWER on B200 (cfg-2:
+        # 3.35 vs 3.15 ms/step) -- one-tile CTAs serialise load -> transform -> store, while the stand-alone pass is a
+        # pipelined HBM stream at 4.9 TB/s.  Off unless B200DM_SIDE_NORM=1 (kept, tested, for a persistent variant).
+        self.side_norm = os.environ.get("B200DM_SIDE_NORM", "0") == "1"
         self.lanes = os.environ.get("B200DM_LANES", "1") != "0"   # branch-parallel CrossAttentionBlock (program lanes)
         self.t_dev = t_dev if t_dev is not None else torch.zeros(2, dtype=torch.int32, device=dev)
         g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
@@ -171,7 +175,7 @@ class UNet:
 
         def conv(x0, kname, cout, y=None, x1=None, k=3, stride=1, mode=L.CONV_DIRECT, act=None, bias=True, chan_bias=None,
                  residual=None, y_dtype=torch.bfloat16, transposed_store=False, dense=False, out_affine=None, note="",
-                 kern=None, bias_t=None):
+                 kern=None, bias_t=None, side=None):
             Bx, D, H, Wd, c0 = x0.shape
             c1 = x1.shape[-1] if x1 is not None else 0
             desc = ops.make_conv_desc(mode, Bx, (D, H, Wd), c0, c1, cout, k, stride, act, None, y_dtype,
@@ -187,7 +191,7 @@ class UNet:
             bias_dev = None if not bias else (bias_t.to(dev).contiguous() if bias_t is not None else g(f"{kname}.bias"))
             return pr.conv(desc, x0, wp, y, x1=x1, bias=bias_dev, chan_bias=chan_bias,
                            t_dev=self.t_dev if chan_bias is not None else None, residual=residual, out_affine=out_affine,
-                           note=note or kname)
+                           note=note or kname, side=side)
 
         def bgemm(a, b, y_dtype, residual=None, note=""):
             Bx, M, K = a.shape
@@ -217,15 +221,24 @@ class UNet:
         def resblock(b, x, skip):
             n, w = b["name"], b["cout"]
             cin = b["cin"] + b["cskip"]
+            h = None
             if cin != w:
-                res = conv(x, f"{n}.shortcut", w, x1=skip, k=1)
+                # the 1^3 shortcut conv reads exactly the tensor(s) norm1 normalises: it writes swish(BN(x|skip)) from its
+                # A tiles as a side output, so the block needs no separate norm pass (falls back to one if the plan cannot)
+                sc1, sh1 = ops.bn_fold(g(f"{n}.norm1.gamma"), g(f"{n}.norm1.beta"), g(f"{n}.norm1.mean"), g(f"{n}.norm1.var"), 1e-3)
+                hbuf = pr.buf((*x.shape[:-1], cin))
+                res = conv(x, f"{n}.shortcut", w, x1=skip, k=1, side=(hbuf, sc1, sh1, "silu") if self.side_norm else None)
+                if pr.side_ok:
+                    h, h1 = hbuf, None
+                    pr.outputs[f"{n}.norm1"] = hbuf
             elif skip is None:
                 res = x
             else:  # concat whose width equals w: materialise it once (identity affine)
                 one, zero = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
                 res = pr.norm_act(x, one, zero, pr.buf((*x.shape[:-1], cin)), x1=skip, note=f"{n}.concat")
             table = ops.dense_f32(temb, g(f"{n}.temb.kernel"), g(f"{n}.temb.bias"), act_in="silu")  # (T, w)
-            h, h1 = bn_act(x, f"{n}.norm1", "silu", x1=skip)
+            if h is None:
+                h, h1 = bn_act(x, f"{n}.norm1", "silu", x1=skip)
             # conv1 + temb -> BN(norm2) -> swish (dm3d.py:237-244): conv1's output has no other reader, so norm2 and the
             # activation run in conv1's epilogue on the fp32 accumulator (one HBM pass and one bf16 rounding fewer)
             sc2, sh2 = ops.bn_fold(g(f"{n}.norm2.gamma"), g(f"{n}.norm2.beta"), g(f"{n}.norm2.mean"), g(f"{n}.norm2.var"), 1e-3)

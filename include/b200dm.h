@@ -234,6 +234,11 @@ int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float* scale, con
  * (dm3d.py:235-236 norm1 of the next ResidualBlock, the skip-connection half of an up-path norm1, dm3d.py:46 the
  * attention block's norm, dm3d.py:371-372 the output norm), so those tensors are never re-read by a separate pass. */
 int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, const float* scale, const float* shift, int32_t act);
+/* Side output of a 1^3 stride-1 conv (the ResidualBlock shortcut, dm3d.py:226-227,250): y_side = act(scale[c] * x[c] + shift[c])
+ * over the conv's own INPUT channels (x0 | x1 concatenated, bf16, same voxel grid), written from the A tiles while they sit
+ * in shared memory -- the block's norm1 + swish (dm3d.py:235-236) without a second pass over x / skip.  Returns
+ * B200DM_ERR_UNSUPPORTED when the plan cannot do it (the caller then runs b200dm_norm_act_fwd). */
+int b200dm_conv_plan_set_side_norm(b200dm_conv_plan* p, void* y_side, const float* scale, const float* shift, int32_t act);
 /* which kernel / tile configuration the plan launches (profiling): halo 1 = persistent halo-reuse kernel */
 int b200dm_conv_plan_info(const b200dm_conv_plan* p, int32_t* halo, int32_t* block_n, int32_t* ksplit);
 /* tuning aid: device int64[4*2048] receiving CTA 0's per-role timeline ((clock64 << 8) | tag); NULL switches it off */

@@ -92,6 +92,28 @@ def test_conv3_pair_slab_tiles(cuda):
         _close(y, ref, tol=6e-3, what=f"pair-slab conv3 B{B} D{D} {c0}+{c1}->{cout}")
 
 
+def test_conv1_side_norm_output(cuda):
+    """1^3 shortcut conv with the block's norm1 + swish written as a side output from the A tiles (two K segments)."""
+    from b200dm import ops, _lib
+    B, S, c0, c1, cout = 2, 8, 64, 32, 64
+    x0, x1 = _rand((B, S, S, S, c0), 1), _rand((B, S, S, S, c1), 2)
+    w = _rand((1, 1, 1, c0 + c1, cout), 3, 1.0 / np.sqrt(c0 + c1))
+    b = torch.randn(cout, generator=torch.Generator().manual_seed(4))
+    sc = torch.rand(c0 + c1, generator=torch.Generator().manual_seed(5)) + 0.5
+    sh = torch.randn(c0 + c1, generator=torch.Generator().manual_seed(6)) * 0.1
+    desc = ops.make_conv_desc(_lib.CONV_DIRECT, B, (S, S, S), c0, c1, cout, 1, 1)
+    y = torch.empty(B, S, S, S, cout, dtype=torch.bfloat16, device=cuda)
+    hs = torch.zeros(B, S, S, S, c0 + c1, dtype=torch.bfloat16, device=cuda)
+    plan = ops.ConvPlan(desc, x0.to(cuda, torch.bfloat16), ops.pack_conv_weights(desc, w).to(cuda), y, x1=x1.to(cuda, torch.bfloat16),
+                        bias=b.to(cuda))
+    assert plan.set_side_norm(hs, sc.to(cuda), sh.to(cuda), "silu")
+    plan.run()
+    _check_flag()
+    xin = torch.cat([x0, x1], -1)
+    _close(y, O.conv3d(xin, w, b), tol=6e-3, what="1^3 conv with side output")
+    _close(hs, O.swish(xin * sc + sh), tol=6e-3, what="side output swish(scale*x+shift)")
+
+
 def test_conv3_two_segments(cuda):
     from b200dm import ops
     B, S, c0, c1, cout = 2, 8, 64, 32, 64
