@@ -529,6 +529,7 @@ struct b200dm_conv_plan {
   int nstage;
   double flops;
   bool halo = false;
+  bool wide = false;   // halo kernel, BLOCK_N = 128, staged: 3-tap weight stages x 2, 4 slabs (see conv_plan_create)
   bool pair = false;   // halo kernel on 8 x 8 planes: 8w x 8h x 2d tiles from pair slabs (conv_halo.cuh)
   int halo_td = 1, halo_nb = 4, halo_tps = 1;
 };
@@ -689,6 +690,19 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 }
 
 constexpr int kHaloNSPair = 4;   // pair slabs are 25 KB; three per channel chunk are live
+constexpr int kHaloNSWide = 4;
+
+template <int TD>
+static int launch_halo_wide(const b200dm_conv_plan* pl, cudaStream_t s) {
+  auto kern = halo::conv_halo_kernel<128, TD, kHaloNSWide, 2, 3, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    attr_set = true;
+  }
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
+  return B200DM_OK;
+}
 
 static int launch_halo_pair(const b200dm_conv_plan* pl, cudaStream_t s) {
   auto kern = halo::conv_halo_kernel<64, 1, kHaloNSPair, 3, 3, true, true>;
@@ -718,7 +732,7 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 
 static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const bool st = pl->p.tma_epi != 0;
-  const int ns = pl->pair ? kHaloNSPair : (st ? kHaloNSStaged : kHaloNS);
+  const int ns = pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : (st ? kHaloNSStaged : kHaloNS));
   return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) + (size_t)pl->halo_nb * pl->halo_tps * pl->g.block_n * 128 +
          (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
 }
@@ -941,6 +955,19 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   }
   pl->smem = conv_smem_bytes(g.block_n, pl->nstage, p.tma_epi && residual);
   if (pl->smem > 232448) { p.tma_epi = 0; pl->smem = conv_smem_bytes(g.block_n, pl->nstage, false); }
+  // BLOCK_N = 128 with the staged epilogue: one-tap weight stages hold only 8 MMAs (4 per issuer warp) and the per-stage
+  // barrier round trip (~200 cycles) made those convs issue-bound (45 % of the MMA floor); 3-tap stages x 2 fit once the
+  // slab ring is the 4 slabs a channel chunk needs (the next chunk's slab i reloads as soon as slab i is released).
+  if (pl->halo && !pl->pair && g.block_n == 128 && p.tma_epi && !getenv("B200DM_NO_WIDE")) {
+    cuuint64_t dims3[3] = {64, (cuuint64_t)g.n_pad, (cuuint64_t)(g.ktot / 64)};
+    cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
+    cuuint32_t box3[3] = {64, 128, 3};
+    cuuint32_t es3[3] = {1, 1, 1};
+    if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B wide) failed"); return B200DM_ERR_CUDA; }
+    pl->wide = true; pl->halo_nb = 2; pl->halo_tps = 3;
+  }
   if (pl->halo) {
     const int td = pl->halo_td;
     p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = pl->pair ? (d->in_h + 7) / 8 : (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td;
@@ -971,7 +998,9 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
       case 16: return dispatch_halo<16, 4, 3>(pl, s);
       case 32: return dispatch_halo<32, 4, 3>(pl, s);
       case 64: return dispatch_halo<64, 3, 3>(pl, s);
-      case 128: return dispatch_halo<128, 4, 1>(pl, s);
+      case 128:
+        if (pl->wide) return pl->halo_td == 2 ? launch_halo_wide<2>(pl, s) : launch_halo_wide<1>(pl, s);
+        return dispatch_halo<128, 4, 1>(pl, s);
     }
   }
   if (pl->nstage == 2) {
@@ -1005,7 +1034,7 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   B2_CHECK_ARG(p && y_extra && scale && shift, "conv_plan_add_output: null argument");
   B2_CHECK_ARG(p->desc.c_out % 16 == 0 && p->desc.reserved[1] == 0, "conv_plan_add_output: needs c_out %% 16 == 0 and a plain (non-transposed) store");
   B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
-  if (p->pair) { b200dm_set_error("conv_plan_add_output: not available on pair-slab (8 x 8 plane) plans"); return B200DM_ERR_UNSUPPORTED; }
+  if (p->pair || p->wide) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo plans"); return B200DM_ERR_UNSUPPORTED; }
   if (p->p.tma_epi) { p->p.tma_epi = 0; p->smem = p->halo ? halo_smem_bytes(p) : conv_smem_bytes(p->g.block_n, p->nstage, false); }
   if (!p->p.y2) { p->p.y2 = (__nv_bfloat16*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (__nv_bfloat16*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
