@@ -393,9 +393,36 @@ class VQVAE:
         self.quantizer = VectorQuantizer(num_embeddings, embedding_dim, layout="DK")
 
     def load_weights(self, path):
-        p = Wt.load_npz(path)
-        self.decoder.set_weights({k[len("decoder."):]: v for k, v in p.items() if k.startswith("decoder.")})
-        self.quantizer.set_embeddings(p["quantizer.embeddings"])
+        _load_first_stage(self, path)
+
+
+def _load_first_stage(model, path):
+    """.npz of canonical names, or the prefix of a TensorFlow checkpoint of the reference's first-stage trainer
+    (``vqvae_trainer.load_weights(ckpt)``, dm3d.py:408-414).  In the object graph the decoder is a subclassed model that
+    holds ``self.blocks`` (a Sequential, or a list in vqgan_attn_cp), so its variables sit under
+    ``decoder/blocks/layer_with_weights-<n>/...`` in layer order, and the codebook under ``quantizer/embeddings``."""
+    import os as _os
+    if not str(path).endswith(".npz") and _os.path.exists(str(path) + ".index"):
+        from . import tf_checkpoint as T
+        variables = T.read_checkpoint(str(path))
+        groups = T.keras_layer_variables(variables, "decoder/blocks")
+        if not groups:   # list-tracked blocks: decoder/blocks/<i>/...
+            import re as _re
+            pat = _re.compile(r"decoder/blocks/(\d+)/(?:layer_with_weights-\d+/)?([A-Za-z_0-9]+)/\.ATTRIBUTES/VARIABLE_VALUE$")
+            g = {}
+            for k, v in variables.items():
+                m = pat.match(k)
+                if m:
+                    g.setdefault(int(m.group(1)), {})[m.group(2)] = v
+            groups = sorted(g.items())
+        model.decoder.set_weights(T.assign_by_creation_order(model.decoder.spec, groups))
+        emb = [v for k, v in variables.items() if k.startswith("quantizer/embeddings") and k.endswith("VARIABLE_VALUE")]
+        if emb:
+            model.quantizer.set_embeddings(emb[0])
+        return
+    p = Wt.load_npz(path)
+    model.decoder.set_weights({k[len("decoder."):]: v for k, v in p.items() if k.startswith("decoder.")})
+    model.quantizer.set_embeddings(p["quantizer.embeddings"])
 
 
 class VQGAN:
@@ -419,6 +446,4 @@ class VQGAN:
         self.quantizer = VectorQuantizer(num_embeddings, embedding_dim, layout="DK" if variant == "vqgan" else "KD")
 
     def load_weights(self, path):
-        p = Wt.load_npz(path)
-        self.decoder.set_weights({k[len("decoder."):]: v for k, v in p.items() if k.startswith("decoder.")})
-        self.quantizer.set_embeddings(p["quantizer.embeddings"])
+        _load_first_stage(self, path)

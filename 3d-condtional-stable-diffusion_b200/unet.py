@@ -136,8 +136,15 @@ class UNet:
         self._params = {k: torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).float().cpu() for k, v in params.items()}
         self.prog = None
 
-    def load_weights(self, path):
-        self.set_weights(Wt.load_npz(path))
+    def load_weights(self, path, name_map=None):
+        """``path``: a flat .npz of canonical names, or the prefix of a TensorFlow checkpoint written by the reference's
+        ``save_weights`` (``<path>.index`` + ``<path>.data-*``, read without TensorFlow: tf_checkpoint.py)."""
+        import os as _os
+        if not str(path).endswith(".npz") and _os.path.exists(str(path) + ".index"):
+            from . import tf_checkpoint as T
+            self.set_weights(T.load_keras_checkpoint(str(path), self.spec, root="network", name_map=name_map))
+        else:
+            self.set_weights(Wt.load_npz(path))
 
     def count_params(self):
         return sum(int(np.prod(s)) for _, s, _ in self.spec)

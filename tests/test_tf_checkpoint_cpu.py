@@ -1,0 +1,122 @@
+"""TensorFlow tensor-bundle checkpoints: format restatement pinned by published known answers, a writer ->
+reader round trip, and the object-graph-key -> canonical-name assignment for the U-Net.  TensorFlow itself is absent."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import b200dm
+from b200dm import tf_checkpoint as T
+
+
+def test_crc32c_known_answers():
+    # RFC 3720 B.4 test vectors for CRC32C (Castagnoli)
+    assert T.crc32c(b"\x00" * 32) == 0x8A9136AA
+    assert T.crc32c(b"\xff" * 32) == 0x62A8AB43
+    assert T.crc32c(bytes(range(32))) == 0x46DD794E
+    assert T.crc32c(b"123456789") == 0xE3069283
+    # tensorflow/core/lib/hash/crc32c.h: Mask(crc) = rotr(crc, 15) + 0xa282ead8
+    assert T.mask_crc(0) == 0xA282EAD8
+
+
+def test_varint_and_proto_roundtrip():
+    for v in (0, 1, 127, 128, 300, 2 ** 31, 2 ** 40 + 5):
+        assert T._get_varint(T._put_varint(v), 0) == (v, len(T._put_varint(v)))
+    msg = T._field(1, 0, T._put_varint(1)) + T._field(4, 0, T._put_varint(1 << 33)) + T._field(6, 5, struct.pack("<I", 0xDEADBEEF))
+    m = T._parse_proto(msg)
+    assert m[1] == [1] and m[4] == [1 << 33] and m[6] == [0xDEADBEEF]
+
+
+def test_write_read_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    # enough keys that the index spans several data blocks and exercises key prefix compression
+    vars_ = {f"network/layer_with_weights-{i}/kernel/.ATTRIBUTES/VARIABLE_VALUE": rng.standard_normal((3, 3, 3, 4, 8)).astype(np.float32)
+             for i in range(60)}
+    vars_.update({f"network/layer_with_weights-{i}/bias/.ATTRIBUTES/VARIABLE_VALUE": rng.standard_normal((8,)).astype(np.float32) for i in range(60)})
+    vars_["step/.ATTRIBUTES/VARIABLE_VALUE"] = np.array(7, dtype=np.int64)
+    prefix = str(tmp_path / "ckpt" / "dm-3")
+    T.write_checkpoint(prefix, vars_)
+    assert os.path.exists(prefix + ".index") and os.path.exists(prefix + ".data-00000-of-00001")
+    raw = open(prefix + ".index", "rb").read()
+    assert struct.unpack("<Q", raw[-8:])[0] == T.MAGIC            # LevelDB table magic (table/format.h kTableMagicNumber)
+    header, entries = T.read_index(prefix + ".index")
+    assert header == dict(num_shards=1, endianness=0) and len(entries) == len(vars_)
+    got = T.read_checkpoint(prefix, verify=True)
+    assert set(got) == set(vars_)
+    for k, v in vars_.items():
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v)
+
+
+def test_corruption_is_detected(tmp_path):
+    prefix = str(tmp_path / "c")
+    T.write_checkpoint(prefix, {"a/.ATTRIBUTES/VARIABLE_VALUE": np.arange(8, dtype=np.float32)})
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    raw[3] ^= 0x40
+    open(prefix + ".index", "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        T.read_index(prefix + ".index")
+    with pytest.raises(ValueError):
+        T.read_index(prefix + ".data-00000-of-00001")   # not a table at all
+
+
+def test_unet_weights_from_object_graph_checkpoint(tmp_path):
+    """Save a small U-Net's weights under Keras object-graph keys, reload through the canonical names."""
+    net = b200dm.build_model(8, 8, [64, 128, 256], [False, False, True, True])
+    params = net.params
+    # one checkpoint layer per weighted Keras layer, numbered in the construction order of param_spec
+    layers, cur = [], None
+    for name, shape, _ in net.spec:
+        stem, leaf = name.rsplit(".", 1)
+        if cur is None or cur[0] != stem:
+            cur = (stem, [])
+            layers.append(cur)
+        cur[1].append((name, leaf))
+    vars_ = {}
+    for n, (stem, tensors) in enumerate(layers):
+        for name, leaf in tensors:
+            attr = T._ATTR_OF_LEAF.get(leaf, leaf)
+            vars_[f"network/layer_with_weights-{n}/{attr}/.ATTRIBUTES/VARIABLE_VALUE"] = params[name].numpy()
+    vars_["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"] = np.array(3, dtype=np.int64)
+    prefix = str(tmp_path / "dm3d-1")
+    T.write_checkpoint(prefix, vars_, checksum_limit=1 << 14)
+    loaded = T.load_keras_checkpoint(prefix, net.spec, root="network")
+    assert set(loaded) == set(params)
+    for k in params:
+        assert np.array_equal(loaded[k], params[k].numpy()), k
+    net2 = b200dm.build_model(8, 8, [64, 128, 256], [False, False, True, True])
+    net2.load_weights(prefix)                      # same call the reference makes (dm3d.py:408-414)
+    assert all(np.array_equal(net2.params[k].numpy(), params[k].numpy()) for k in params)
+    # a checkpoint of a different architecture is rejected with the offending shapes
+    net3 = b200dm.build_model(8, 16, [64, 128, 256], [False, False, True, True])
+    with pytest.raises(ValueError):
+        T.load_keras_checkpoint(prefix, net3.spec)
+
+
+def test_first_stage_weights_from_checkpoint(tmp_path):
+    """vqvae_trainer.load_weights(ckpt): decoder blocks (Sequential order) + quantizer codebook from object-graph keys."""
+    vq = b200dm.VQVAE(1, 1, (32, 64), 1, (32, 64), num_embeddings=16, embedding_dim=8, latent_size=4)
+    spec = vq.decoder.spec
+    rng = np.random.default_rng(1)
+    layers, cur = [], None
+    for name, shape, _ in spec:
+        stem, leaf = name.rsplit(".", 1)
+        if cur is None or cur[0] != stem:
+            cur = (stem, [])
+            layers.append(cur)
+        cur[1].append((name, leaf, shape))
+    vars_, want = {}, {}
+    for n, (stem, tensors) in enumerate(layers):
+        for name, leaf, shape in tensors:
+            a = rng.standard_normal(shape).astype(np.float32)
+            want[name] = a
+            vars_[f"decoder/blocks/layer_with_weights-{n}/{T._ATTR_OF_LEAF.get(leaf, leaf)}/.ATTRIBUTES/VARIABLE_VALUE"] = a
+    cb = rng.standard_normal((8, 16)).astype(np.float32)           # monai codebook layout (D, K)
+    vars_["quantizer/embeddings/.ATTRIBUTES/VARIABLE_VALUE"] = cb
+    vars_["quantizer/codebooks_used/.ATTRIBUTES/VARIABLE_VALUE"] = np.zeros(16, dtype=np.int32)
+    prefix = str(tmp_path / "vqvae-5")
+    T.write_checkpoint(prefix, vars_, checksum_limit=1 << 14)
+    vq.load_weights(prefix)
+    for k, a in want.items():
+        assert np.array_equal(vq.decoder.params[k].numpy(), a), k
+    assert np.array_equal(np.asarray(vq.quantizer.embeddings), cb)
