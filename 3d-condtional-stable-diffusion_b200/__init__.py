@@ -7,4 +7,4 @@ the top-level shim:  ``import b200dm``.
 from . import _lib, ops, weights  # noqa: F401
 from .unet import build_model, UNet, param_spec  # noqa: F401
 from .diffusion import DiffusionModel, ConditionalDiffusionModel, Betas  # noqa: F401
-from .first_stage import VQVAE, VQGAN, VectorQuantizer, MonaiDecoder, AttnCpDecoder, VqganFamilyDecoder  # noqa: F401
+from .first_stage import VQVAE, VQGAN, VectorQuantizer, MonaiDecoder, MonaiEncoder, AttnCpDecoder, VqganFamilyDecoder  # noqa: F401

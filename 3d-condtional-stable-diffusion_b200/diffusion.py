@@ -232,6 +232,21 @@ class DiffusionModel:
             st["delta"] = -1 if st["graph"] is None else st["delta"]
         return st["x"].clone()
 
+    def encode(self, images):
+        """``latents, _ = self.quantizer(self.encoder(images))`` -- the first line of the reference's train_step
+        (dm3d.py / conditional_dm3d.py:478): volumes (B,S,S,S,1) -> quantised latents (B,s,s,s,D) fp32 on the device."""
+        latents, _ = self.quantizer(self.encoder(images))
+        return latents
+
+    def q_sample(self, latents, t, noise):
+        """Forward diffusion of train_step (conditional_dm3d.py:484-490): sqrt(abar_t) * latents + sqrt(1 - abar_t) * noise,
+        t (B,) int.  A host-side helper over the fp32 schedule tables (not on the sampling path)."""
+        t = torch.as_tensor(t).long().reshape(-1).cpu()
+        h = self.b.host
+        sqb = torch.from_numpy(h["sqrt_alpha_bar"])[t].reshape(-1, 1, 1, 1, 1).to(latents.device, torch.float32)
+        osqb = torch.from_numpy(h["sqrt_one_minus_alpha_bar"])[t].reshape(-1, 1, 1, 1, 1).to(latents.device, torch.float32)
+        return sqb * latents.float() + osqb * noise.to(latents.device, torch.float32)
+
     def decode(self, latents, quantize=False):
         """latents -> volumes through the first-stage decoder; ``quantize=True`` snaps latents to the codebook first
         (extension: the reference's test() decodes un-quantized latents, dm3d.py:541)."""

@@ -5,7 +5,8 @@ Mirrors the attribute surface the reference's DiffusionModel uses (``.encoder / 
     MonaiDecoder  (family D1)  networks/vqvae3d_monai.py:309-391 + VQVAEResidualUnit :218-234
     AttnCpDecoder (family D5)  networks/vqgan_attn_cp.py:339-427 + VQVAEResidualUnit :250-276
     VQVAE / VQGAN              networks/vqvae3d_monai.py:394-457 / vqgan_attn_cp.py:569-590 (constructor surface)
-The encoder is not on the sampling path and is not built: ``.encoder`` raises.
+    MonaiEncoder  (8f.2)       networks/vqvae3d_monai.py:237-306 (volumes -> pre-quantisation latents; front half of train_step)
+The other families' encoders are not built: their ``.encoder`` raises.
 """
 from __future__ import annotations
 
@@ -100,11 +101,11 @@ class _DecoderBase:
         return sum(int(np.prod(s)) for _, s, _ in self.spec)
 
     def _conv(self, pr, x0, kernel, bias, cout, k=3, mode=L.CONV_DIRECT, act=None, post_act=None, residual=None,
-              prelu_alpha=None, y_dtype=torch.bfloat16, transposed=False, note=""):
+              prelu_alpha=None, y_dtype=torch.bfloat16, transposed=False, note="", stride=1):
         B, D, H, W, c0 = x0.shape
-        desc = ops.make_conv_desc(mode, B, (D, H, W), c0, 0, cout, k, 1, act, post_act, y_dtype)
+        desc = ops.make_conv_desc(mode, B, (D, H, W), c0, 0, cout, k, stride, act, post_act, y_dtype)
         wp = ops.pack_conv_weights(desc, kernel, transposed).to(self.device)
-        od, oh, ow = ops.conv_out_shape(mode, (D, H, W), 1)
+        od, oh, ow = ops.conv_out_shape(mode, (D, H, W), stride)
         y = pr.buf((B, od, oh, ow, cout), y_dtype)
         return pr.conv(desc, x0, wp, y, bias=bias.to(self.device).contiguous(), residual=residual,
                        prelu_alpha=prelu_alpha, note=note)
@@ -171,6 +172,75 @@ class MonaiDecoder(_DecoderBase):
         self.out = x
         torch.cuda.synchronize(dev)
         return self
+
+
+class MonaiEncoder(_DecoderBase):
+    """vqvae3d_monai.Encoder (:237-306): per level Conv3D(c_i, k4, s2, 'same') ReLU, R x VQVAEResidualUnit; Conv3(->D) PReLU.
+    volumes (B,S,S,S,in) -> pre-quantisation latents (B,s,s,s,D) fp32, s = S / 2^levels.  The input's channels are zero-padded
+    to 8 (one 16-byte NDHWC vector) together with the first kernel's C_in."""
+
+    def __init__(self, in_channels, out_channels, num_channels, num_res_layers, num_res_channels, in_size,
+                 downsample_parameters=None, dropout=None):
+        self.cin, self.out_channels, self.R, self.in_size = in_channels, out_channels, num_res_layers, in_size
+        self.ch, self.rch = list(num_channels), list(num_res_channels)
+        if downsample_parameters is not None:
+            for dp in downsample_parameters:
+                if tuple(dp[:3]) != (2, 4, 1) or dp[3] not in ("same", 1):
+                    raise NotImplementedError(f"downsample_parameters {dp}: only (stride 2, kernel 4, dilation 1, 'same') is built")
+        sp, s, cin = [], in_size, in_channels
+        for i, c in enumerate(self.ch):
+            s //= 2
+            sp += [(f"level.{i}.down.kernel", (4, 4, 4, cin, c), "glorot"), (f"level.{i}.down.bias", (c,), "zeros")]
+            for j in range(self.R):
+                n, rc = f"level.{i}.res.{j}", self.rch[i]
+                sp += [(f"{n}.conv1.kernel", (3, 3, 3, c, rc), "glorot"), (f"{n}.conv1.bias", (rc,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, rc, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros"),
+                       (f"{n}.norm.gamma", (c,), "ones"), (f"{n}.norm.beta", (c,), "zeros"),
+                       (f"{n}.norm.mean", (c,), "zeros"), (f"{n}.norm.var", (c,), "ones"),
+                       (f"{n}.prelu.alpha", (s, s, s, c), "zeros")]
+            cin = c
+        sp += [("head.kernel", (3, 3, 3, cin, out_channels), "glorot"), ("head.bias", (out_channels,), "zeros"),
+               ("head.prelu.alpha", (s, s, s, out_channels), "zeros")]
+        self.spec = sp
+        super().__init__()
+
+    def compile(self, batch, in_size=None):
+        L.require_gpu()
+        assert in_size in (None, self.in_size), "per-voxel PReLU alphas lock the encoder to its build resolution"
+        P = self.params
+        self.device = dev = torch.device("cuda", torch.cuda.current_device())
+        pr = self.prog = Program(dev)
+        S = self.in_size
+        cpad = -(-self.cin // 8) * 8
+        self.z_in = pr.buf((batch, S, S, S, cpad))
+        self.z_in.zero_()
+        alpha = lambda n: P[n].to(dev, torch.bfloat16).contiguous()  # noqa: E731
+        x = self.z_in
+        for i, c in enumerate(self.ch):
+            w = P[f"level.{i}.down.kernel"]
+            if i == 0 and cpad != self.cin:
+                w = torch.cat([w, torch.zeros(4, 4, 4, cpad - self.cin, c)], dim=3)
+            x = self._conv(pr, x, w, P[f"level.{i}.down.bias"], c, k=4, stride=2, act="relu", note=f"level.{i}.down")
+            for j in range(self.R):
+                n = f"level.{i}.res.{j}"
+                h = self._conv(pr, x, P[f"{n}.conv1.kernel"], P[f"{n}.conv1.bias"], self.rch[i], act="relu", note=f"{n}.conv1")
+                scale = P[f"{n}.norm.gamma"] * torch.rsqrt(P[f"{n}.norm.var"] + 1e-3)   # BN (inference) folded into conv2
+                shift = P[f"{n}.norm.beta"] - P[f"{n}.norm.mean"] * scale
+                x = self._conv(pr, h, P[f"{n}.conv2.kernel"] * scale, P[f"{n}.conv2.bias"] * scale + shift, c,
+                               prelu_alpha=alpha(f"{n}.prelu.alpha"), residual=x, post_act="relu", note=f"{n}.conv2")
+        self.out = self._conv(pr, x, P["head.kernel"], P["head.bias"], self.out_channels, prelu_alpha=alpha("head.prelu.alpha"),
+                              y_dtype=torch.float32, note="head")
+        torch.cuda.synchronize(dev)
+        return self
+
+    def __call__(self, volumes):
+        """encoder(volumes (B,S,S,S,in) fp32|bf16) -> latents (B,s,s,s,D) fp32."""
+        if self.prog is None or volumes.shape[0] != self.z_in.shape[0]:
+            self.compile(volumes.shape[0], volumes.shape[1])
+        v = volumes.to(self.device)
+        self.z_in[..., :self.cin].copy_(v if v.dtype == torch.bfloat16 else ops.cast(v.contiguous().float(), torch.bfloat16))
+        self.prog.run()
+        return self.out.clone()
 
 
 class AttnCpDecoder(_DecoderBase):
@@ -387,7 +457,8 @@ class VQVAE:
         self.num_res_layers, self.num_res_channels, self.num_gpus = num_res_layers, tuple(num_res_channels), num_gpus
         if latent_size is None:
             latent_size = 128 // (2 ** len(num_channels))
-        self.encoder = _NoEncoder()
+        self.encoder = MonaiEncoder(in_channels, embedding_dim, num_channels, num_res_layers, num_res_channels,
+                                    latent_size * (2 ** len(num_channels)), downsample_parameters, dropout)
         self.decoder = MonaiDecoder(embedding_dim, out_channels, num_channels, num_res_layers, num_res_channels, latent_size,
                                     upsample_parameters, dropout, output_act, kernel_resize)
         self.quantizer = VectorQuantizer(num_embeddings, embedding_dim, layout="DK")

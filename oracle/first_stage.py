@@ -104,6 +104,45 @@ class MonaiDecoder:
         return x
 
 
+# ------------------------------------------------------------------ encoder (monai)
+class MonaiEncoder:
+    """vqvae3d_monai.Encoder (:237-306): per level Conv3D(c_i, k=4, strides=2, 'same') ReLU, R x VQVAEResidualUnit (:218-234);
+    then Conv3D(embedding_dim, 3, 'same') PReLU.  Dropout is an inference no-op.  PReLU alphas are per voxel (d,h,w,c)."""
+
+    def __init__(self, in_channels, out_channels, num_channels, num_res_layers, num_res_channels, in_size):
+        self.cin, self.cout, self.ch, self.rch = in_channels, out_channels, list(num_channels), list(num_res_channels)
+        self.R, self.s0 = num_res_layers, in_size
+
+    def spec(self):
+        sp, s, cin = [], self.s0, self.cin
+        for i, c in enumerate(self.ch):
+            s //= 2
+            sp += [(f"level.{i}.down.kernel", (4, 4, 4, cin, c), "glorot"), (f"level.{i}.down.bias", (c,), "zeros")]
+            for j in range(self.R):
+                n, rc = f"level.{i}.res.{j}", self.rch[i]
+                sp += [(f"{n}.conv1.kernel", (3, 3, 3, c, rc), "glorot"), (f"{n}.conv1.bias", (rc,), "zeros"),
+                       (f"{n}.conv2.kernel", (3, 3, 3, rc, c), "glorot"), (f"{n}.conv2.bias", (c,), "zeros"),
+                       (f"{n}.norm.gamma", (c,), "ones"), (f"{n}.norm.beta", (c,), "zeros"),
+                       (f"{n}.norm.mean", (c,), "zeros"), (f"{n}.norm.var", (c,), "ones"),
+                       (f"{n}.prelu.alpha", (s, s, s, c), "zeros")]
+            cin = c
+        sp += [("head.kernel", (3, 3, 3, cin, self.cout), "glorot"), ("head.bias", (self.cout,), "zeros"),
+               ("head.prelu.alpha", (s, s, s, self.cout), "zeros")]
+        return sp
+
+    def forward(self, P, x, emu: Emu = EXACT):
+        x = emu.a(x)
+        for i in range(len(self.ch)):
+            x = emu.a(torch.relu(ops.conv3d(x, emu.w(P[f"level.{i}.down.kernel"]), P[f"level.{i}.down.bias"], stride=2)))
+            for j in range(self.R):
+                n = f"level.{i}.res.{j}"
+                h = emu.a(torch.relu(ops.conv3d(x, emu.w(P[f"{n}.conv1.kernel"]), P[f"{n}.conv1.bias"])))
+                h = ops.conv3d(h, emu.w(P[f"{n}.conv2.kernel"]), P[f"{n}.conv2.bias"])
+                h = ops.batchnorm_infer(h, P[f"{n}.norm.gamma"], P[f"{n}.norm.beta"], P[f"{n}.norm.mean"], P[f"{n}.norm.var"])
+                x = emu.a(torch.relu(x + ops.prelu(h, P[f"{n}.prelu.alpha"])))
+        return ops.prelu(ops.conv3d(x, emu.w(P["head.kernel"]), P["head.bias"]), P["head.prelu.alpha"])
+
+
 # ------------------------------------------------------------------ decoder D5 (vqgan_attn_cp)
 class AttnCpDecoder:
     """vqgan_attn_cp.Decoder: Conv1(D->c_top) GN(min(D,32)) SiLU; [ConvT(k4,s2,c_i) 2xResUnit]x(L-1); Conv3(->out).

@@ -146,6 +146,40 @@ def test_monai_decoder(cuda):
     assert r_e <= 8e-3 and r_x <= 3e-2
 
 
+def test_monai_encoder_and_quantize(cuda):
+    """volumes -> Encoder (k4 s2 'same' convs, ResUnits, per-voxel PReLU) -> quantizer: the front half of train_step
+    (conditional_dm3d.py:478: latents, _ = self.quantizer(self.encoder(images)))."""
+    import b200dm
+    enc = b200dm.MonaiEncoder(1, 8, (32, 64), 1, (32, 64), 16)
+    oe = OF.MonaiEncoder(1, 8, (32, 64), 1, (32, 64), 16)
+    P = OI.make_params(oe.spec(), 6, "stress")
+    enc.set_weights(P)
+    vol = OI.normal((2, 16, 16, 16, 1), 12)
+    z = enc(vol.to(cuda))
+    assert tuple(z.shape) == (2, 4, 4, 4, 8) and z.dtype == torch.float32
+    r_e, r_x = rel(z, oe.forward(P, vol, Emu(True))), rel(z, oe.forward(P, vol))
+    print(f"monai encoder: rel-L2 vs emu {r_e:.3e}, vs fp32 {r_x:.3e}")
+    assert r_e <= 8e-3 and r_x <= 3e-2
+    # quantise the SAME latents on both sides: indices bit-exact (the encoder's own rounding noise is tested above)
+    vq = b200dm.VectorQuantizer(64, 8, layout="DK")
+    cb = OI.codebook(64, 8, "DK", seed=3)
+    vq.set_embeddings(cb)
+    q, idx, _ = vq.quantize(z)
+    q_ref, idx_ref, _, _ = OF.quantize(z.cpu(), cb, "DK")
+    assert torch.equal(idx.cpu(), idx_ref) and torch.equal(q.cpu(), q_ref)
+    # train_step's forward half through the model surface: encode -> q_sample (conditional_dm3d.py:478-490)
+    dm = b200dm.DiffusionModel(4, 64, 8, None, types.SimpleNamespace(timesteps=50, num_gpus=1, kernel_resize=False, bs=2))
+    dm.vqvae_trainer.encoder, dm.encoder = enc, enc
+    dm.vqvae_trainer.quantizer, dm.quantizer = vq, vq
+    lat = dm.encode(vol.to(cuda))
+    assert torch.equal(lat.cpu(), q_ref)
+    t, nz = torch.tensor([3, 40]), OI.normal(tuple(lat.shape), 13)
+    b = OBetas(50)
+    want = torch.from_numpy(b.sqrt_alpha_bar)[t].reshape(-1, 1, 1, 1, 1) * q_ref + \
+        torch.from_numpy(b.sqrt_one_minus_alpha_bar)[t].reshape(-1, 1, 1, 1, 1) * nz
+    assert torch.allclose(dm.q_sample(lat, t, nz).cpu(), want, atol=1e-6)
+
+
 def test_attn_cp_decoder_and_quantize(cuda):
     import b200dm
     K, D = 256, 64

@@ -101,6 +101,23 @@ def test_monai_vqvae_param_count_matches_reference_log():
     tr, nt = OF.monai_vqvae_param_count(1, 1, (32, 64, 128), 3, (32, 64, 128), 256, 64, img_size=128)
     assert tr == 75_593_473
     assert nt == 2_688
+    # the same number from the encoder / decoder weight tables the oracle and the product are built from
+    enc = OF.MonaiEncoder(1, 64, (32, 64, 128), 3, (32, 64, 128), 128)
+    dec = OF.MonaiDecoder(64, 1, (32, 64, 128), 3, (32, 64, 128), 16)
+    stats = lambda n: n.endswith(".mean") or n.endswith(".var")  # noqa: E731
+    tr2 = sum(int(np.prod(s)) for sp in (enc.spec(), dec.spec()) for n, s, _ in sp if not stats(n)) + 64 * 256
+    nt2 = sum(int(np.prod(s)) for sp in (enc.spec(), dec.spec()) for n, s, _ in sp if stats(n))
+    assert (tr2, nt2) == (75_593_473, 2_688)
+
+
+def test_monai_encoder_shapes_and_product_spec_agree():
+    import b200dm
+    oe = OF.MonaiEncoder(1, 8, (32, 64), 1, (32, 64), 16)
+    P = OI.make_params(oe.spec(), 6, "stress")
+    z = oe.forward(P, OI.normal((1, 16, 16, 16, 1), 12))
+    assert tuple(z.shape) == (1, 4, 4, 4, 8)
+    pe = b200dm.MonaiEncoder(1, 8, (32, 64), 1, (32, 64), 16)
+    assert [(n, tuple(s)) for n, s, _ in pe.spec] == [(n, tuple(s)) for n, s, _ in oe.spec()]
 
 
 def test_unet_param_counts_are_stable():
