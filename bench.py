@@ -268,6 +268,12 @@ def run_ours(args):
                             "traffic": None, "launches": len(sel), "avg_launch_ms": h_ms / max(1, len(sel)),
                             "algorithmic_gflop_per_launch_avg": h_fl / 1e9 / max(1, len(sel)), "share_of_step": h_ms / tot_ms,
                             "timing": "CUDA events around every launch on the launching stream (b200dm_program_run_timed)"}
+        try:   # ncu dram__bytes_(read+write) of representative launches (one --set full capture each; profiles/)
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1d_traffic.json")) as f:
+                line["roofline"]["traffic_samples"] = json.load(f)["samples"]
+            line["roofline"]["traffic_note"] = "traffic is null for the 36-launch aggregate; per-launch ncu samples are listed in traffic_samples"
+        except OSError:
+            pass
         sel, t_ms, t_fl = agg(("conv_halo", "conv", "attn"))
         line["roofline_all_tensor_kernels"] = {"kernels": "conv_halo_kernel + conv_igemm_kernel (1^3 / strided / parity convs, GEMMs) + flash_attn_kernel",
                                                "bound": "tensor", "achieved": t_fl / (t_ms * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
@@ -278,6 +284,35 @@ def run_ours(args):
             line["roofline_hbm_kernels"] = {"kernels": "norm_act / layernorm (fused elementwise passes left in the step)", "bound": "hbm",
                                             "achieved": e_by / (e_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                             "frac": e_by / (e_ms * 1e-3) / 1e9 / pk["hbm"], "launches": len(sel), "share_of_step": e_ms / tot_ms}
+        # the two HBM-bound kernels that move the bytes: the fused posterior update (largest pass of the step) and the largest
+        # BN+swish(+concat) pass -- each timed alone with CUDA events on its stream (tiny launches dominate the aggregate above)
+        net0 = nets[0]
+        xs = st["x"][:st["chain_batch"]]
+        reset(T - 1)
+
+        def upd():
+            L.check(L.lib().b200dm_ddpm_update(ctypes.byref(st["descs"][0]), L.ptr(xs), L.ptr(net0.eps), None, L.ptr(xs), L.ptr(net0.x_in), L.stream()))
+
+        for _ in range(3):
+            upd()
+        torch.cuda.synchronize()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(10):
+            upd()
+        u1.record()
+        torch.cuda.synchronize()
+        u_ms = u0.elapsed_time(u1) / 10
+        u_bytes = xs.numel() * (4.0 + 4.0 + 4.0 + 2.0)
+        line["roofline_update_kernel"] = {"kernel": "update_kernel (fused DDPM posterior + Philox noise): x_t fp32 + eps fp32 -> x_{t-1} fp32 + bf16 copy",
+                                          "bound": "hbm", "achieved": u_bytes / (u_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                          "frac": u_bytes / (u_ms * 1e-3) / 1e9 / pk["hbm"], "algorithmic_bytes_per_launch": u_bytes,
+                                          "avg_launch_ms": u_ms, "working_set": "940 MB per launch (> 126 MB L2)"}
+        big = max((r for r in rows if r[0] == "norm_act"), key=lambda r: r[2], default=None)
+        if big is not None:
+            line["roofline_largest_norm_pass"] = {"kernel": f"norm_act_kernel ({big[1]})", "bound": "hbm", "achieved": big[2] / (big[3] * 1e-3) / 1e9,
+                                                  "peak": pk["hbm"], "unit": "GB/s", "frac": big[2] / (big[3] * 1e-3) / 1e9 / pk["hbm"],
+                                                  "algorithmic_bytes_per_launch": big[2], "avg_launch_ms": big[3]}
         if world == 1 and not args.no_cpu:
             r = oracle_cpu_rate(3, 1, budget_s=25.0)
             line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
