@@ -13,7 +13,7 @@
 
 namespace {
 enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN, OP_NORM_EX, OP_STATS_F32, OP_SYNC };
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 6;
 struct Op {
   OpKind kind;
   int lane = 0;                 // 0 = the caller's stream
@@ -40,7 +40,7 @@ struct Op {
 struct b200dm_program {
   std::vector<Op> ops;
   int cur_lane = 0;
-  cudaStream_t side[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
+  cudaStream_t side[kMaxLanes] = {};   // [0] unused
   void push(Op& op) { op.lane = cur_lane; ops.push_back(op); }
 };
 
