@@ -186,10 +186,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           // swap_ab (BLOCK_N = 128, both tiles [128 rows][64 K]): the weight tile is the A operand -> D^T in TMEM
           const uint64_t da = (p.swap_ab ? b_desc0 : a_desc0) + (uint64_t)(s * (kStageBytes >> 4));
           const uint64_t db = (p.swap_ab ? a_desc0 : b_desc0) + (uint64_t)(s * (kStageBytes >> 4));
+          // a ragged last chunk of a K segment (e.g. C_in = 32 or 8) issues only the K=16 steps that hold real channels
+          const int chunk = kb / p.ntaps;
+          const int ksn = chunk == p.nch0 - 1 ? p.ksteps0_last : (chunk == p.nch0 + p.nch1 - 1 && p.nch1 > 0 ? p.ksteps1_last : 4);
           ptx::tc_mma_f16(tmem_base, da, db, idesc, kb != kb0 ? 1u : 0u);
-          ptx::tc_mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
-          ptx::tc_mma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
-          ptx::tc_mma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
+          if (ksn > 1) ptx::tc_mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
+          if (ksn > 2) ptx::tc_mma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
+          if (ksn > 3) ptx::tc_mma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
           if (CLUSTER) ptx::tc_commit_mc(empty_bar(s), (uint16_t)((1u << (cl_m * cl_n)) - 1u));
           else ptx::tc_commit(empty_bar(s));
         }
@@ -862,6 +865,8 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   p.tiles_w = (g.m_w + g.box_w - 1) / g.box_w; p.tiles_h = (g.m_h + g.box_h - 1) / g.box_h;
   p.tiles_d = (g.m_d + g.box_d - 1) / g.box_d; p.tiles_n = (d->batch + g.box_n - 1) / g.box_n;
   p.nch0 = g.nch0; p.nch1 = g.nch1; p.ntaps = g.ntaps; p.ksize = d->ksize; p.stride = st; p.pad = g.pad;
+  p.ksteps0_last = ((d->c0 - (g.nch0 - 1) * 64) + 15) / 16;
+  p.ksteps1_last = d->c1 > 0 ? ((d->c1 - (g.nch1 - 1) * 64) + 15) / 16 : 4;
   p.c_out = d->c_out; p.n_pad = d->mode == B200DM_CONV_BATCHED_GEMM ? d->c_out : g.n_pad;
   p.act = d->act; p.post_act = d->reserved[0]; p.y_f32 = d->y_dtype == B200DM_F32; p.transposed_store = d->reserved[1];
   p.chan_bias_rows = d->chan_bias_rows;

@@ -11,6 +11,7 @@ struct ConvParams {
   int box_w, box_h, box_d, box_n;    // product == 128
   int tiles_w, tiles_h, tiles_d, tiles_n;
   int nch0, nch1, ntaps, ksize, stride, pad;
+  int ksteps0_last, ksteps1_last;    // K=16 MMA steps that hold real channels in the LAST 64-channel chunk of each segment (1..4)
   int c_out, n_pad;
   int act, post_act, y_f32, transposed_store;
   int chan_bias_rows;

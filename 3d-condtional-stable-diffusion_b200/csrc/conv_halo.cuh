@@ -197,6 +197,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
           for (int pl = 0; pl < TD; ++pl) a_pl[pl] = a_desc0 + (uint64_t)(((q + pl + kd) % NS) * (kSlabBytes >> 4));
           const uint32_t first_kd = (j | kd) != 0 ? 1u : 0u;
+          // a ragged last chunk (C_in = 32: half of the 64-channel chunk is TMA zero fill) issues only the K=16 steps that
+          // hold real channels
+          const int ks = j == p.nch0 - 1 ? p.ksteps0_last : (j == nch - 1 && p.nch1 > 0 ? p.ksteps1_last : 4);
 #pragma unroll 1
           for (int kh = 0; kh < 3 && ok; ++kh) {
 #pragma unroll
@@ -216,9 +219,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                     const uint64_t da = a_pl[pl] + (uint64_t)(kh * kKhUnits + kw * 8);   // (kh*10+kw) rows of 128 B in 16-B units
                     const uint64_t db = db0 + (uint64_t)(u * (kTapBytes >> 4));
                     ptx::tc_mma_f16(acc + pl * BLOCK_N, da, db, idesc, first);
-                    ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 2, db + 2, idesc, 1u);
-                    ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 4, db + 4, idesc, 1u);
-                    ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 6, db + 6, idesc, 1u);
+                    if (ks > 1) ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 2, db + 2, idesc, 1u);
+                    if (ks > 2) ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 4, db + 4, idesc, 1u);
+                    if (ks > 3) ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 6, db + 6, idesc, 1u);
                   }
                 }
                 ptx::tc_commit(b_empty(sb));
