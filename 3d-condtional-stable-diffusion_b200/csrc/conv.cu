@@ -177,6 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const uint64_t b_desc0 = ptx::make_smem_desc(smem_base + kABytes, 16, 1024, ptx::kLayoutSw128);
       bool ok = true;
       uint32_t s = 0, phase = 0;
+      int mchunk = kb0 / p.ntaps, mtap = kb0 % p.ntaps;
       for (int kb = kb0; kb < kb1 && ok; ++kb) {
         ok = ptx::mbar_wait(full_bar(s), phase, p.dbg, 2);
         if (!ok) break;
@@ -187,8 +188,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const uint64_t da = (p.swap_ab ? b_desc0 : a_desc0) + (uint64_t)(s * (kStageBytes >> 4));
           const uint64_t db = (p.swap_ab ? a_desc0 : b_desc0) + (uint64_t)(s * (kStageBytes >> 4));
           // a ragged last chunk of a K segment (e.g. C_in = 32 or 8) issues only the K=16 steps that hold real channels
-          const int chunk = kb / p.ntaps;
-          const int ksn = chunk == p.nch0 - 1 ? p.ksteps0_last : (chunk == p.nch0 + p.nch1 - 1 && p.nch1 > 0 ? p.ksteps1_last : 4);
+          const int ksn = mchunk == p.nch0 - 1 ? p.ksteps0_last : (mchunk == p.nch0 + p.nch1 - 1 && p.nch1 > 0 ? p.ksteps1_last : 4);
           ptx::tc_mma_f16(tmem_base, da, db, idesc, kb != kb0 ? 1u : 0u);
           if (ksn > 1) ptx::tc_mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
           if (ksn > 2) ptx::tc_mma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
@@ -198,6 +198,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
         __syncwarp();
         if (++s == NSTAGE) { s = 0; phase ^= 1; }
+        if (++mtap == p.ntaps) { mtap = 0; ++mchunk; }
       }
       if (ptx::elect_one()) ptx::tc_commit(tmem_full_bar);
       __syncwarp();
