@@ -13,7 +13,7 @@
 
 namespace {
 enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN, OP_NORM_EX, OP_STATS_F32, OP_SYNC };
-constexpr int kMaxLanes = 6;
+constexpr int kMaxLanes = 10;
 struct Op {
   OpKind kind;
   int lane = 0;                 // 0 = the caller's stream

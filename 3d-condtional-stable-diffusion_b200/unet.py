@@ -162,6 +162,8 @@ class UNet:
         # Producer-side normalisation (conv epilogues write the consumers' BN(+swish) copies as extra outputs) removes every
         # norm pass, but measured SLOWER on B200 (cfg-2: 5.47 vs 5.08 ms/step): the extra stores lengthen the conv
         # epilogues, which are on the critical path, by more than the streaming pass costs.  Off unless B200DM_FUSE_NORMS=1.
+        self._wcache = {}
+        self._lane_base, self._half = 0, (0, batch)
         self.fuse_norms = os.environ.get("B200DM_FUSE_NORMS", "0") == "1"
         # norm1 as a side output of the 1^3 shortcut conv (b200dm_conv_plan_set_side_norm): measured SLOWER on B200 (cfg-2:
         # 3.35 vs 3.15 ms/step) -- one-tile CTAs serialise load -> transform -> store, while the stand-alone pass is a
@@ -187,11 +189,15 @@ class UNet:
             c1 = x1.shape[-1] if x1 is not None else 0
             desc = ops.make_conv_desc(mode, Bx, (D, H, Wd), c0, c1, cout, k, stride, act, None, y_dtype,
                                       chan_bias_rows=1 if chan_bias is not None else 0, transposed_store=transposed_store)
+            kern_key = None if kern is None else "override"
             if kern is None:
                 kern = P[f"{kname}.kernel"]
             if dense:  # Dense on voxels == 1^3 conv: (in,out) -> (1,1,1,in,out)
                 kern = kern.reshape(1, 1, 1, *kern.shape)
-            wp = ops.pack_conv_weights(desc, kern).to(dev)
+            wkey = (kname, mode, k, stride, c0, c1, cout, transposed_store, dense, kern_key)
+            wp = self._wcache.get(wkey)
+            if wp is None:   # (the two batch halves of the deep phase share one packed copy)
+                wp = self._wcache[wkey] = ops.pack_conv_weights(desc, kern).to(dev)
             if y is None:
                 od, oh, ow = ops.conv_out_shape(mode, (D, H, Wd), stride)
                 y = pr.buf((Bx, cout, od * oh * ow) if transposed_store else (Bx, od, oh, ow, cout), y_dtype)
@@ -270,6 +276,7 @@ class UNet:
         def attn_block(b, x):  # AttentionBlock.call (dm3d.py:39-63)
             n, c, s = b["name"], b["c"], b["s"]
             Lq = s ** 3
+            B = x.shape[0]
             nrm, _ = bn_act(x, f"{n}.norm", None)
             q = conv(nrm, f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
             kk = conv(nrm, f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
@@ -279,10 +286,22 @@ class UNet:
 
         self.ctx_sites = []
         self._ctx_ids = None
+        sites = {}
+
+        def ctx_site(n, c, s):
+            """K_ctx / V_ctx^T buffers of one attention site for the WHOLE batch (filled by set_context); the caller gets
+            the rows of the batch range it is building."""
+            if n not in sites:
+                Lq = s ** 3
+                sites[n] = dict(name=n, c=c, s=s, kc=pr.buf((batch, Lq, c)), vcT=pr.buf((batch, c, Lq)))
+                self.ctx_sites.append(sites[n])
+            lo, hi = self._half
+            return sites[n]["kc"][lo:hi], sites[n]["vcT"][lo:hi]
 
         def xattn_block(b, x):  # CrossAttentionBlock.call (conditional_dm3d.py:186-195)
             n, c, s = b["name"], b["c"], b["s"]
             Lq = s ** 3
+            B, lb = x.shape[0], self._lane_base
             scale = float(c) ** -0.5
             # inference BatchNorm followed by the 1^3 proj_in conv is one affine map: fold it into proj_in's kernel and bias
             # (W' = diag(a) W, b' = b + shift . W; conditional_dm3d.py:187-188) -- no normalisation pass
@@ -295,8 +314,7 @@ class UNet:
             bet = [g(f"{n}.norm{i}.beta") for i in (1, 2, 3)]
             ln = pr.layernorm(h, gam, bet, [pr.buf(h.shape) for _ in range(3)], 1e-3, note=f"{n}.ln")
             hf = h.view(B, Lq, c)
-            kc, vcT = pr.buf((B, Lq, c)), pr.buf((B, c, Lq))          # filled by set_context()
-            self.ctx_sites.append(dict(name=n, c=c, s=s, kc=kc, vcT=vcT))
+            kc, vcT = ctx_site(n, c, s)
             if not self.lanes:
                 q1 = conv(ln[0], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
                 k1 = conv(ln[0], f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
@@ -311,25 +329,25 @@ class UNet:
             # The three branches all read h (conditional_dm3d.py:190-192): self-attention on the caller's stream, cross
             # attention on lane 1, the MLP on lane 2 (its second GEMM adds the cross branch), and proj_out sums the two
             # partial results inside its K loop: proj_out(t1 + xs) = [t1 | xs] . [W; W]  (two K segments, no add pass).
-            pr.sync(0, 1)
-            pr.sync(0, 2)
-            pr.sync(0, 3)
+            pr.sync(lb, lb + 1)
+            pr.sync(lb, lb + 2)
+            pr.sync(lb, lb + 3)
             q1 = conv(ln[0], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
             k1 = conv(ln[0], f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
-            pr.set_lane(3)
+            pr.set_lane(lb + 3)
             v1T = conv(ln[0], f"{n}.value", c, k=1, dense=True, transposed_store=True)
-            pr.set_lane(0)
-            pr.sync(3, 0)
+            pr.set_lane(lb)
+            pr.sync(lb + 3, lb)
             t1 = attention_core(q1, k1, v1T, scale, hf, f"{n}.self")
-            pr.set_lane(1)
+            pr.set_lane(lb + 1)
             q2 = conv(ln[1], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
             c2 = attention_core(q2, kc, vcT, scale, None, f"{n}.cross")
-            pr.set_lane(2)
+            pr.set_lane(lb + 2)
             m = conv(ln[2], f"{n}.mlp0", 4 * c, k=1, dense=True, act="relu")
-            pr.sync(1, 2)
+            pr.sync(lb + 1, lb + 2)
             xs = conv(m, f"{n}.mlp1", c, k=1, dense=True, residual=c2.view(B, s, s, s, c))
-            pr.set_lane(0)
-            pr.sync(2, 0)
+            pr.set_lane(lb)
+            pr.sync(lb + 2, lb)
             w2 = torch.cat([P[f"{n}.proj_out.kernel"]] * 2, dim=3)
             return conv(t1.view(B, s, s, s, c), f"{n}.proj_out", c, x1=xs, k=1, act="relu", residual=x, kern=w2)
 
@@ -365,31 +383,70 @@ class UNet:
                 self.shadow_norms[id(t)] = dict(name=nm, y=y)
             pr.set_lane(0)
 
-        x, skips, skip_ids = None, [], []
+        st = dict(x=None, skips=[], ids=[])
         self._npush = 1   # push index 0 is the input conv's output
-        for b in self.blocks:
+
+        def do_block(b, st, y_out=None):
             k = b["kind"]
-            if not shadow_done and k == "res" and b["s"] == deepest:
-                shadow_pass(skips, skip_ids)
-                shadow_done = True
             if k == "in":
-                x = conv(self.x_in, "in", b["cout"])
-                skips.append(x); skip_ids.append(len(skip_ids))
+                st["x"] = conv(self.x_in, "in", b["cout"])
+                st["skips"].append(st["x"]); st["ids"].append(0)
             elif k == "res":
+                skip = None
                 if b.get("pop"):
-                    skip_ids.pop()
-                x = resblock(b, x, skips.pop() if b.get("pop") else None)
+                    st["ids"].pop()
+                    skip = st["skips"].pop()
+                st["x"] = resblock(b, st["x"], skip)
             elif k == "attn":
-                x = xattn_block(b, x) if cfg.conditional else attn_block(b, x)
+                st["x"] = xattn_block(b, st["x"]) if cfg.conditional else attn_block(b, st["x"])
             elif k == "push":
-                skips.append(x); skip_ids.append(self._npush); self._npush += 1
+                st["skips"].append(st["x"]); st["ids"].append(self._npush); self._npush += 1
             elif k == "down":
-                x = conv(x, b["name"], b["c"], stride=2)
+                st["x"] = conv(st["x"], b["name"], b["c"], stride=2)
             elif k == "up":
-                x = conv(x, b["name"], b["c"], mode=L.CONV_PARITY)
+                st["x"] = conv(st["x"], b["name"], b["c"], mode=L.CONV_PARITY, y=y_out)
             elif k == "out":
-                h, _ = bn_act(x, "out.norm", "silu")
+                h, _ = bn_act(st["x"], "out.norm", "silu")
                 conv(h, "out.conv", b["cout"], y=self.eps, y_dtype=torch.float32)
+
+        # Deep phase = the blocks at the coarsest resolution (8^3 in cfg-2) up to and including the upsample conv that leaves it.
+        # B200DM_SPLIT_DEEP=1 records it twice, once per half of the batch, on two independent lane sets (0-3 and 5-8), as
+        # parallel branches of the step graph.  Measured on B200 (cfg-2): 3.23 vs 3.09 ms/step -- SLOWER: the phase's kernels
+        # are bound by their own latency (one tile per CTA either way), so halving the batch halves no kernel's duration and
+        # doubles the launches.  Off by default; kept (and parity-tested) because it is the scaffold for per-sample
+        # persistent kernels at this level.
+        blocks = self.blocks
+        deep = [i for i, b in enumerate(blocks) if b.get("s") == deepest and b["kind"] in ("res", "attn", "up")]
+        i0, i1 = (deep[0], deep[-1] + 1) if deep else (len(blocks), len(blocks))
+        split = (os.environ.get("B200DM_SPLIT_DEEP", "0") == "1" and self.lanes and batch >= 4 and batch % 2 == 0 and deep
+                 and blocks[i1 - 1]["kind"] == "up")
+        i = 0
+        while i < len(blocks):
+            b = blocks[i]
+            if not shadow_done and b["kind"] == "res" and b["s"] == deepest:
+                shadow_pass(st["skips"], st["ids"])
+                shadow_done = True
+            if split and i == i0:
+                up = blocks[i1 - 1]
+                s_out = 2 * up["s"]
+                full = pr.buf((batch, s_out, s_out, s_out, up["c"]))
+                npush0, after = self._npush, None
+                pr.sync(0, 5)
+                for (lo, hi), lb in (((0, batch // 2), 0), ((batch // 2, batch), 5)):
+                    self._lane_base, self._half, self._npush = lb, (lo, hi), npush0
+                    pr.set_lane(lb)
+                    sh = dict(x=st["x"][lo:hi], skips=[t[lo:hi] for t in st["skips"]], ids=list(st["ids"]))
+                    for j in range(i0, i1):
+                        do_block(blocks[j], sh, y_out=full[lo:hi] if j == i1 - 1 else None)
+                    after = sh
+                self._lane_base, self._half = 0, (0, batch)
+                pr.set_lane(0)
+                pr.sync(5, 0)
+                st = dict(x=full, skips=st["skips"][:len(after["skips"])], ids=after["ids"])
+                i = i1
+                continue
+            do_block(b, st)
+            i += 1
         torch.cuda.synchronize(dev)
         return self
 

@@ -294,7 +294,7 @@ int b200dm_program_add_update(b200dm_program* p, const b200dm_update_desc* d, co
                               const void* eps, const float* noise_or_null, float* x_prev,
                               void* x_prev_bf16_or_null);
 int b200dm_program_add_step_advance(b200dm_program* p, int32_t* t_dev, int32_t delta);
-/* Lanes: ops added after set_lane(l) run on lane l (0 = the caller's stream, 1..5 = streams owned by the program);
+/* Lanes: ops added after set_lane(l) run on lane l (0 = the caller's stream, 1..9 = streams owned by the program);
  * add_sync(a, b) makes everything recorded so far on lane a a prerequisite of what follows on lane b (event record /
  * wait: a fork when a = 0, a join when b = 0).  Every side lane must be joined back to lane 0 before the program ends.
  * Used for the three independent branches of CrossAttentionBlock.call (conditional_dm3d.py:190-192). */

@@ -97,6 +97,32 @@ def test_unet_cond_forward(cuda):
     assert rel(y2[1:], y[1:].cpu()) < 1e-6 and rel(y2[:1], y[:1].cpu()) > 1e-4
 
 
+def test_unet_cond_forward_split_deep_phase(cuda):
+    """B200DM_SPLIT_DEEP=1 (batch >= 4): the coarsest-resolution phase is recorded per batch half on two lane sets (parallel
+    graph branches); the result must equal the oracle and the default program bit for bit."""
+    import os
+    S, C_lat, B = 8, 16, 4
+    x = OI.normal((B, S, S, S, C_lat), 1)
+    ctx = torch.tensor([0, 1, 1, 0])
+    tt = torch.full((B,), 33)
+    os.environ["B200DM_SPLIT_DEEP"] = "1"
+    try:
+        net, ou, P = _unet_pair(S, C_lat, True)
+        net.compile(B, 50)
+        assert any(note == "0->5" for kind, note, _ in net.prog.log if kind == "sync"), "deep phase was not split"
+        y = net([x.to(cuda), tt, ctx])
+    finally:
+        del os.environ["B200DM_SPLIT_DEEP"]
+    r_e = rel(y, ou.forward(P, x, tt, ctx=ctx, emu=Emu(True)))
+    print(f"cond, split deep phase: rel-L2 vs bf16-emulating oracle {r_e:.3e}")
+    assert r_e <= 2.5e-2
+    net1, _, _ = _unet_pair(S, C_lat, True)
+    net1.compile(B, 50)
+    assert not any(note == "0->5" for kind, note, _ in net1.prog.log if kind == "sync")
+    y1 = net1([x.to(cuda), tt, ctx])
+    assert torch.equal(y.cpu(), y1.cpu())
+
+
 def test_full_chain_injected_noise(cuda):
     """T-step DDPM chain, same x_T and per-step noise on both sides."""
     import b200dm
