@@ -172,9 +172,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
     const uint64_t a_desc0 = ptx::make_smem_desc(slab_base, 16, 1280, ptx::kLayoutSw128);
     const uint64_t b_desc0 = ptx::make_smem_desc(bring_base, 16, 1024, ptx::kLayoutSw128);
-    uint32_t q = 0, it = 0, sb = 0, bph = 0;
+    // Ring positions are carried incrementally (qs = slab slot of the chunk's first slab, qph = its phase bit): the
+    // issuing thread is the pacing resource, and the integer divisions / modulos of a closed-form index cost ~200 cycles
+    // per kd step during which the shallow MMA queue drains.
+    uint32_t it = 0, sb = 0, bph = 0, qs = 0, qph = 0;
     bool ok = true;
     int ti = 0;
+    auto slot = [&](uint32_t i, uint32_t& ph) -> uint32_t {   // ring slot / phase of slab i of the current chunk (i < NS)
+      uint32_t idx = qs + i;
+      const bool wrap = idx >= (uint32_t)NS;
+      ph = qph ^ (wrap ? 1u : 0u);
+      return wrap ? idx - NS : idx;
+    };
     for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step, ++it) {
       const uint32_t as = it & 1;
       if (tr) trace_ev(p, 0, ti, 1);
@@ -183,23 +192,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       if (tr) trace_ev(p, 0, ti, 2);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + as * kAccCols;
-      for (int j = 0; j < nch && ok; ++j, q += TD + 2) {
+      for (int j = 0; j < nch && ok; ++j) {
+        // a ragged last chunk (C_in = 32: half of the 64-channel chunk is TMA zero fill) issues only the K=16 steps that
+        // hold real channels
+        const int ks = j == p.nch0 - 1 ? p.ksteps0_last : (j == nch - 1 && p.nch1 > 0 ? p.ksteps1_last : 4);
 #pragma unroll 1
         for (int kd = 0; kd < 3 && ok; ++kd) {
+          uint32_t ph;
           if (kd == 0) {
-            for (int pl = 0; pl < TD && ok; ++pl) ok = ptx::mbar_wait(slab_full((q + pl) % NS), ((q + pl) / NS) & 1, p.dbg, 14);
+            for (int pl = 0; pl < TD && ok; ++pl) { const uint32_t sl = slot(pl, ph); ok = ptx::mbar_wait(slab_full(sl), ph, p.dbg, 14); }
           } else {
-            ok = ptx::mbar_wait(slab_full((q + kd + TD - 1) % NS), ((q + kd + TD - 1) / NS) & 1, p.dbg, 14);
+            const uint32_t sl = slot(kd + TD - 1, ph);
+            ok = ptx::mbar_wait(slab_full(sl), ph, p.dbg, 14);
           }
           if (!ok) break;
           if (tr) trace_ev(p, 0, ti, 3);
           uint64_t a_pl[TD];
 #pragma unroll
-          for (int pl = 0; pl < TD; ++pl) a_pl[pl] = a_desc0 + (uint64_t)(((q + pl + kd) % NS) * (kSlabBytes >> 4));
+          for (int pl = 0; pl < TD; ++pl) a_pl[pl] = a_desc0 + (uint64_t)(slot(pl + kd, ph) * (uint32_t)(kSlabBytes >> 4));
           const uint32_t first_kd = (j | kd) != 0 ? 1u : 0u;
-          // a ragged last chunk (C_in = 32: half of the 64-channel chunk is TMA zero fill) issues only the K=16 steps that
-          // hold real channels
-          const int ks = j == p.nch0 - 1 ? p.ksteps0_last : (j == nch - 1 && p.nch1 > 0 ? p.ksteps1_last : 4);
+          // slab released by this kd step: slab kd (last used at kd = min(index, 2)); after kd = 2 also slabs 3 .. TD+1
+          const uint32_t rel0 = slot(kd, ph), rel1 = TD == 2 ? slot(3, ph) : 0u;
 #pragma unroll 1
           for (int kh = 0; kh < 3 && ok; ++kh) {
 #pragma unroll
@@ -225,6 +238,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                   }
                 }
                 ptx::tc_commit(b_empty(sb));
+                if (kh == 2 && g == 3 / TPS - 1) {   // last stage of this kd step: release its slab(s) in the same breath
+                  ptx::tc_commit(slab_empty(rel0));
+                  if (kd == 2 && TD == 2) ptx::tc_commit(slab_empty(rel1));
+                }
               }
               __syncwarp();
               if (++sb == NB) { sb = 0; bph ^= 1; }
@@ -232,14 +249,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
           if (!ok) break;
           if (tr) trace_ev(p, 0, ti, 4);
-          // slab pl is last used at kd = min(pl, 2)
-          if (ptx::elect_one()) {
-            if (kd < 2) ptx::tc_commit(slab_empty((q + kd) % NS));
-            else
-              for (int pl = 2; pl < TD + 2; ++pl) ptx::tc_commit(slab_empty((q + pl) % NS));
-          }
-          __syncwarp();
         }
+        qs += TD + 2;
+        if (qs >= (uint32_t)NS) { qs -= NS; qph ^= 1; }
       }
       if (ptx::elect_one()) ptx::tc_commit(tmem_full(as));
       __syncwarp();
