@@ -12,8 +12,9 @@ TensorFlow 2.12 / Keras 2.  TensorFlow is not installed in this environment and 
 (SURVEY.md F2/F3, section 8c).  The restatement below therefore follows the reference *source*
 (every function cites the file:line it restates) and the documented Keras op semantics;
 the only reference-derived pins are the Keras parameter count logged in
-``experiments/vqvae3d-scaled-monai-B8-AUG-all-T-KR.output:23-25`` (tests/test_param_count.py)
-and the closed-form schedule identities of ``Betas`` (tests/test_schedule.py).
+``experiments/vqvae3d-scaled-monai-B8-AUG-all-T-KR.output:23-25`` (reproduced from the encoder + decoder weight tables)
+and the closed-form schedule identities of ``Betas`` (both in tests/test_oracle_cpu.py), next to the Random123
+known-answer vectors for Philox4x32-10.
 
 Arithmetic: PyTorch-CPU fp32 (``dtype=torch.float64`` for an independent high-precision
 check).  ``Emu`` (oracle.ops) optionally rounds to bf16 at exactly the points where the
