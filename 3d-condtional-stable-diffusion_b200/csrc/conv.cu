@@ -533,6 +533,7 @@ struct b200dm_conv_plan {
   int nstage;
   double flops;
   bool halo = false;
+  bool cg2 = false;    // halo kernel, BLOCK_N = 64, two planes, staged: CTA pairs (cta_group::2), see conv_halo.cuh
   bool wide = false;   // halo kernel, BLOCK_N = 128, staged: 3-tap weight stages x 2, 4 slabs (see conv_plan_create)
   bool pair = false;   // halo kernel on 8 x 8 planes: 8w x 8h x 2d tiles from pair slabs (conv_halo.cuh)
   int halo_td = 1, halo_nb = 4, halo_tps = 1;
@@ -696,6 +697,25 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 constexpr int kHaloNSPair = 4;   // pair slabs are 25 KB; three per channel chunk are live
 constexpr int kHaloNSWide = 4;
 
+static int launch_halo_cg2(const b200dm_conv_plan* pl, cudaStream_t s) {
+  auto kern = halo::conv_halo_kernel<64, 2, kHaloNSStaged, 3, 3, true, false, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = pl->grid; cfg.blockDim = dim3(halo::kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
+  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
+  return B200DM_OK;
+}
+
 template <int TD>
 static int launch_halo_wide(const b200dm_conv_plan* pl, cudaStream_t s) {
   auto kern = halo::conv_halo_kernel<128, TD, kHaloNSWide, 2, 3, true>;
@@ -737,7 +757,8 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const bool st = pl->p.tma_epi != 0;
   const int ns = pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : (st ? kHaloNSStaged : kHaloNS));
-  return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) + (size_t)pl->halo_nb * pl->halo_tps * pl->g.block_n * 128 +
+  return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) +
+         (size_t)pl->halo_nb * pl->halo_tps * (pl->cg2 ? pl->g.block_n / 2 : pl->g.block_n) * 128 +
          (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
 }
 
@@ -974,6 +995,20 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B wide) failed"); return B200DM_ERR_CUDA; }
     pl->wide = true; pl->halo_nb = 2; pl->halo_tps = 3;
   }
+  // CTA pairs for the C_out-tile-64 two-plane convs (the 32^3-level ResidualBlock convs): needs an even tile count per n-tile
+  if (pl->halo && !pl->pair && g.block_n == 64 && p.tma_epi && pl->halo_td == 2 && !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
+    const long long per = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
+    if (per % 2 == 0 && per * (g.n_pad / 64) >= 2) {
+      cuuint64_t dims3[3] = {64, (cuuint64_t)g.n_pad, (cuuint64_t)(g.ktot / 64)};
+      cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
+      cuuint32_t box3[3] = {64, 32, 3};   // this CTA's half of the 64 rows of a 3-tap weight stage
+      cuuint32_t es3[3] = {1, 1, 1};
+      if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B cg2) failed"); return B200DM_ERR_CUDA; }
+      pl->cg2 = true;
+    }
+  }
   if (pl->halo) {
     const int td = pl->halo_td;
     p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = pl->pair ? (d->in_h + 7) / 8 : (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td;
@@ -982,6 +1017,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     p.halo_td = td; p.halo_tiles_per_ntile = (int)per; p.halo_ntn = ntiles; p.halo_total_tiles = (int)(per * ntiles);
     int ctas = b2_num_sms();
     if (ctas > p.halo_total_tiles) ctas = p.halo_total_tiles;
+    if (pl->cg2) ctas &= ~1;   // whole pairs
     pl->grid = dim3((unsigned)ctas, 1, 1);
     pl->smem = halo_smem_bytes(pl);
   }
@@ -999,6 +1035,7 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
   if (pl->pair) return launch_halo_pair(pl, s);
+  if (pl->cg2) return launch_halo_cg2(pl, s);
   if (pl->halo) {
     switch (pl->g.block_n) {
       case 16: return dispatch_halo<16, 4, 3>(pl, s);
@@ -1040,7 +1077,7 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   B2_CHECK_ARG(p && y_extra && scale && shift, "conv_plan_add_output: null argument");
   B2_CHECK_ARG(p->desc.c_out % 16 == 0 && p->desc.reserved[1] == 0, "conv_plan_add_output: needs c_out %% 16 == 0 and a plain (non-transposed) store");
   B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
-  if (p->pair || p->wide) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo plans"); return B200DM_ERR_UNSUPPORTED; }
+  if (p->pair || p->wide || p->cg2) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo plans"); return B200DM_ERR_UNSUPPORTED; }
   if (p->p.tma_epi) { p->p.tma_epi = 0; p->smem = p->halo ? halo_smem_bytes(p) : conv_smem_bytes(p->g.block_n, p->nstage, false); }
   if (!p->p.y2) { p->p.y2 = (__nv_bfloat16*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (__nv_bfloat16*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }

@@ -59,7 +59,11 @@ constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs
 // its dims as (C, W, D, H, N), so one box {64, 10, 2, 10, 1} lands in smem as rows [h][d][w]: the 16 eight-row groups of
 // the M = 128 operand (group = h * 2 + d) are again a uniform 10 rows apart, the (kh, kw) tap shift is (kh * 20 + kw) rows,
 // and each kd tap reads its own pair slab (planes d0 + kd - 1, d0 + kd).  TD = 1; staged epilogue only.
-template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED, bool PAIR = false>
+// CG2 (cta_group::2): a cluster of two CTAs works on two consecutive tiles of the same n-tile.  Each CTA stages its own slabs
+// and HALF of every weight stage (BLOCK_N / 2 rows); the leader's issuer warps run M = 256 MMAs over both CTAs' shared memory
+// and TMEM.  Per CTA and MMA that is 4 KB of A + 1 KB of B instead of 4 + 2, and half the weight fill traffic -- the two terms
+// that put the one-CTA main loop on the shared-memory roofline.
+template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED, bool PAIR = false, bool CG2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const ConvParams p) {
@@ -69,7 +73,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   constexpr int kSlabBytes = PAIR ? 25 * 1024 : halo::kSlabBytes;   // 200 (pair) / 180 rows of 128 B, 1 KB-rounded
   constexpr int kSlabTx = PAIR ? 200 * 128 : halo::kSlabTx;
   constexpr int kKhUnits = PAIR ? 160 : 80;                          // one kh step in 16-byte units (20 / 10 rows)
-  constexpr int kTapBytes = BLOCK_N * 128;
+  static_assert(!CG2 || (TD == 2 && STAGED && !PAIR && BLOCK_N >= 64), "CTA-pair variant: two planes, staged epilogue");
+  constexpr int kBRows = CG2 ? BLOCK_N / 2 : BLOCK_N;   // weight rows of one tap staged by THIS CTA
+  constexpr int kTapBytes = kBRows * 128;
   constexpr int kBBytes = TPS * kTapBytes;
   // MMA issuer warps: with TD = 2 each output plane (its own TMEM accumulator) is driven by its own warp.  Measured
   // (clock64 timeline): one issuing thread spends ~280 cycles per weight stage on barrier waits / commits / descriptor
@@ -101,22 +107,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   pdl_launch_dependents();
   const int nch = p.nch0 + p.nch1;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  const uint32_t crank = CG2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), kIssuers); }
     for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), kIssuers); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), 8); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), CG2 ? 16 : 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
     if (STAGED) ptx::prefetch_tmap(&mapY);
   }
   if (warp == 2) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), kTmemCols);
-    ptx::tmem_relinquish();
+    if (CG2) { ptx::tmem_alloc_cg2(ptx::smem_u32(tmem_ptr_smem), kTmemCols); ptx::tmem_relinquish_cg2(); }
+    else { ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG2) ptx::cluster_sync_all();   // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();   // set-up above overlaps the previous kernel's tail
@@ -136,9 +145,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (!ok) break;
           if (lane == 0) trace_ev(p, 2, ti, 20 + pl);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(slab_full(s), kSlabTx);
-            if (PAIR) ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.d0 - 1 + pl, t.h0 - 1, t.n);
-            else ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.h0 - 1, t.d0 - 1 + pl, t.n);
+            if (CG2) {   // both CTAs' slabs complete on the LEADER's barrier, which expects both transfers
+              if (leader) ptx::mbar_expect_tx(slab_full(s), 2 * kSlabTx);
+              ptx::tma_load_5d_cg2(slab_base + s * kSlabBytes, map, ptx::mapa_shared(slab_full(s), 0), c0, t.w0 - 1, t.h0 - 1,
+                                   t.d0 - 1 + pl, t.n);
+            } else {
+              ptx::mbar_expect_tx(slab_full(s), kSlabTx);
+              if (PAIR) ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.d0 - 1 + pl, t.h0 - 1, t.n);
+              else ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.h0 - 1, t.d0 - 1 + pl, t.n);
+            }
           }
           __syncwarp();
           if (++s == NS) { s = 0; ph ^= 1; }
@@ -156,8 +171,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         ok = ptx::mbar_wait(b_empty(s), ph, p.dbg, 12);
         if (!ok) break;
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(b_full(s), kBBytes);
-          tma_load_3d(bring_base + s * kBBytes, &mapB, b_full(s), 0, row0, kb);
+          if (CG2) {   // this CTA's half of the rows; completion on the leader's barrier
+            if (leader) ptx::mbar_expect_tx(b_full(s), 2 * kBBytes);
+            ptx::tma_load_3d_cg2(bring_base + s * kBBytes, &mapB, ptx::mapa_shared(b_full(s), 0), 0, row0 + (int)crank * kBRows, kb);
+          } else {
+            ptx::mbar_expect_tx(b_full(s), kBBytes);
+            tma_load_3d(bring_base + s * kBBytes, &mapB, b_full(s), 0, row0, kb);
+          }
         }
         __syncwarp();
         if (++s == NB) { s = 0; ph ^= 1; }
@@ -169,7 +189,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const bool tr = warp == 2 && lane == 0;
     // Descriptors are formed by ADDING 16-byte units to precomputed 64-bit bases (the 14-bit address field cannot
     // carry: smem < 256 KB); inside a stage every offset is a compile-time immediate.
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(CG2 ? 256 : 128, BLOCK_N);
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accum) {
+      if (CG2) ptx::tc_mma_f16_cg2(d, da, db, idesc, accum); else ptx::tc_mma_f16(d, da, db, idesc, accum);
+    };
+    auto commit = [&](uint32_t bar) { if (CG2) ptx::tc_commit_cg2(bar, (uint16_t)3); else ptx::tc_commit(bar); };
     const uint64_t a_desc0 = ptx::make_smem_desc(slab_base, 16, 1280, ptx::kLayoutSw128);
     const uint64_t b_desc0 = ptx::make_smem_desc(bring_base, 16, 1024, ptx::kLayoutSw128);
     // Ring positions are carried incrementally (qs = slab slot of the chunk's first slab, qph = its phase bit): the
@@ -184,7 +208,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       ph = qph ^ (wrap ? 1u : 0u);
       return wrap ? idx - NS : idx;
     };
-    for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step, ++it) {
+    for (int id = first_tile; id < p.halo_total_tiles && ok && leader; id += tile_step, ++it) {
       const uint32_t as = it & 1;
       if (tr) trace_ev(p, 0, ti, 1);
       ok = ptx::mbar_wait(tmem_empty(as), ((it >> 1) & 1) ^ 1, p.dbg, 13);
@@ -231,16 +255,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                     if (pl < pl_lo || pl >= pl_hi) continue;
                     const uint64_t da = a_pl[pl] + (uint64_t)(kh * kKhUnits + kw * 8);   // (kh*10+kw) rows of 128 B in 16-B units
                     const uint64_t db = db0 + (uint64_t)(u * (kTapBytes >> 4));
-                    ptx::tc_mma_f16(acc + pl * BLOCK_N, da, db, idesc, first);
-                    if (ks > 1) ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 2, db + 2, idesc, 1u);
-                    if (ks > 2) ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 4, db + 4, idesc, 1u);
-                    if (ks > 3) ptx::tc_mma_f16(acc + pl * BLOCK_N, da + 6, db + 6, idesc, 1u);
+                    mma(acc + pl * BLOCK_N, da, db, first);
+                    if (ks > 1) mma(acc + pl * BLOCK_N, da + 2, db + 2, 1u);
+                    if (ks > 2) mma(acc + pl * BLOCK_N, da + 4, db + 4, 1u);
+                    if (ks > 3) mma(acc + pl * BLOCK_N, da + 6, db + 6, 1u);
                   }
                 }
-                ptx::tc_commit(b_empty(sb));
+                commit(b_empty(sb));
                 if (kh == 2 && g == 3 / TPS - 1) {   // last stage of this kd step: release its slab(s) in the same breath
-                  ptx::tc_commit(slab_empty(rel0));
-                  if (kd == 2 && TD == 2) ptx::tc_commit(slab_empty(rel1));
+                  commit(slab_empty(rel0));
+                  if (kd == 2 && TD == 2) commit(slab_empty(rel1));
                 }
               }
               __syncwarp();
@@ -253,7 +277,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         qs += TD + 2;
         if (qs >= (uint32_t)NS) { qs -= NS; qph ^= 1; }
       }
-      if (ptx::elect_one()) ptx::tc_commit(tmem_full(as));
+      if (ptx::elect_one()) commit(tmem_full(as));
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -418,15 +442,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       ptx::tc_fence_before();
       __syncwarp();
       if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 12);
-      if (lane == 0) ptx::mbar_arrive(tmem_empty(as));
+      if (lane == 0) {
+        if (CG2) ptx::mbar_arrive_cluster(ptx::mapa_shared(tmem_empty(as), 0));   // the leader's issuers own the accumulators
+        else ptx::mbar_arrive(tmem_empty(as));
+      }
     }
     if (STAGED && warp == 4 && lane == 0) ptx::bulk_wait_read_all();   // smem must outlive the last store's reads
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory / write its TMEM until here
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (CG2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
