@@ -697,8 +697,9 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 constexpr int kHaloNSPair = 4;   // pair slabs are 25 KB; three per channel chunk are live
 constexpr int kHaloNSWide = 4;
 
+template <int BLOCK_N, int TD, int NS, int NB, bool PAIR>
 static int launch_halo_cg2(const b200dm_conv_plan* pl, cudaStream_t s) {
-  auto kern = halo::conv_halo_kernel<64, 2, kHaloNSStaged, 3, 3, true, false, true>;
+  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, NS, NB, 3, true, PAIR, true>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -756,7 +757,7 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 
 static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const bool st = pl->p.tma_epi != 0;
-  const int ns = pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : (st ? kHaloNSStaged : kHaloNS));
+  const int ns = pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : (st ? kHaloNSStaged : kHaloNS));   // (cg2: 5, or 4 for pair slabs)
   return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) +
          (size_t)pl->halo_nb * pl->halo_tps * (pl->cg2 ? pl->g.block_n / 2 : pl->g.block_n) * 128 +
          (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
@@ -995,18 +996,21 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B wide) failed"); return B200DM_ERR_CUDA; }
     pl->wide = true; pl->halo_nb = 2; pl->halo_tps = 3;
   }
-  // CTA pairs for the C_out-tile-64 two-plane convs (the 32^3-level ResidualBlock convs): needs an even tile count per n-tile
-  if (pl->halo && !pl->pair && g.block_n == 64 && p.tma_epi && pl->halo_td == 2 && !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
-    const long long per = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
-    if (per % 2 == 0 && per * (g.n_pad / 64) >= 2) {
+  // CTA pairs (cta_group::2) for every staged halo configuration with 64- or 128-channel tiles: needs an even tile count per
+  // n-tile so that the two CTAs of a pair always work on the same n-tile and run the same number of tiles
+  if (pl->halo && (g.block_n == 64 || g.block_n == 128) && p.tma_epi && (pl->pair || pl->halo_td == 2 || g.block_n == 128) &&
+      !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
+    const int td = pl->halo_td;   // (pair: d step 2)
+    const long long per = (long long)((d->in_w + 7) / 8) * (pl->pair ? (d->in_h + 7) / 8 : (d->in_h + 15) / 16) * ((d->in_d + td - 1) / td) * d->batch;
+    if (per % 2 == 0) {
       cuuint64_t dims3[3] = {64, (cuuint64_t)g.n_pad, (cuuint64_t)(g.ktot / 64)};
       cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
-      cuuint32_t box3[3] = {64, 32, 3};   // this CTA's half of the 64 rows of a 3-tap weight stage
+      cuuint32_t box3[3] = {64, (cuuint32_t)(g.block_n / 2), 3};   // this CTA's half of the rows of a 3-tap weight stage
       cuuint32_t es3[3] = {1, 1, 1};
       if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B cg2) failed"); return B200DM_ERR_CUDA; }
-      pl->cg2 = true;
+      pl->cg2 = true; pl->wide = false; pl->halo_nb = 3; pl->halo_tps = 3;
     }
   }
   if (pl->halo) {
@@ -1034,8 +1038,12 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
 extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
+  if (pl->cg2) {
+    if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);
+    if (pl->g.block_n == 64) return launch_halo_cg2<64, 2, kHaloNSStaged, 3, false>(pl, s);
+    return pl->halo_td == 2 ? launch_halo_cg2<128, 2, kHaloNSStaged, 3, false>(pl, s) : launch_halo_cg2<128, 1, kHaloNSStaged, 3, false>(pl, s);
+  }
   if (pl->pair) return launch_halo_pair(pl, s);
-  if (pl->cg2) return launch_halo_cg2(pl, s);
   if (pl->halo) {
     switch (pl->g.block_n) {
       case 16: return dispatch_halo<16, 4, 3>(pl, s);

@@ -73,7 +73,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   constexpr int kSlabBytes = PAIR ? 25 * 1024 : halo::kSlabBytes;   // 200 (pair) / 180 rows of 128 B, 1 KB-rounded
   constexpr int kSlabTx = PAIR ? 200 * 128 : halo::kSlabTx;
   constexpr int kKhUnits = PAIR ? 160 : 80;                          // one kh step in 16-byte units (20 / 10 rows)
-  static_assert(!CG2 || (TD == 2 && STAGED && !PAIR && BLOCK_N >= 64), "CTA-pair variant: two planes, staged epilogue");
+  static_assert(!CG2 || (STAGED && BLOCK_N >= 64), "CTA-pair variant: staged epilogue");
   constexpr int kBRows = CG2 ? BLOCK_N / 2 : BLOCK_N;   // weight rows of one tap staged by THIS CTA
   constexpr int kTapBytes = kBRows * 128;
   constexpr int kBBytes = TPS * kTapBytes;
@@ -147,8 +147,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (ptx::elect_one()) {
             if (CG2) {   // both CTAs' slabs complete on the LEADER's barrier, which expects both transfers
               if (leader) ptx::mbar_expect_tx(slab_full(s), 2 * kSlabTx);
-              ptx::tma_load_5d_cg2(slab_base + s * kSlabBytes, map, ptx::mapa_shared(slab_full(s), 0), c0, t.w0 - 1, t.h0 - 1,
-                                   t.d0 - 1 + pl, t.n);
+              if (PAIR) ptx::tma_load_5d_cg2(slab_base + s * kSlabBytes, map, ptx::mapa_shared(slab_full(s), 0), c0, t.w0 - 1,
+                                             t.d0 - 1 + pl, t.h0 - 1, t.n);
+              else ptx::tma_load_5d_cg2(slab_base + s * kSlabBytes, map, ptx::mapa_shared(slab_full(s), 0), c0, t.w0 - 1, t.h0 - 1,
+                                        t.d0 - 1 + pl, t.n);
             } else {
               ptx::mbar_expect_tx(slab_full(s), kSlabTx);
               if (PAIR) ptx::tma_load_5d(slab_base + s * kSlabBytes, map, slab_full(s), c0, t.w0 - 1, t.d0 - 1 + pl, t.h0 - 1, t.n);
