@@ -697,9 +697,9 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 constexpr int kHaloNSPair = 4;   // pair slabs are 25 KB; three per channel chunk are live
 constexpr int kHaloNSWide = 4;
 
-template <int BLOCK_N, int TD, int NS, int NB, bool PAIR>
+template <int BLOCK_N, int TD, int NS, int NB, bool PAIR, bool STAGED = true>
 static int launch_halo_cg2(const b200dm_conv_plan* pl, cudaStream_t s) {
-  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, NS, NB, 3, true, PAIR, true>;
+  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, NS, NB, 3, STAGED, PAIR, true>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -998,7 +998,8 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   }
   // CTA pairs (cta_group::2) for every staged halo configuration with 64- or 128-channel tiles: needs an even tile count per
   // n-tile so that the two CTAs of a pair always work on the same n-tile and run the same number of tiles
-  if (pl->halo && (g.block_n == 64 || g.block_n == 128) && p.tma_epi && (pl->pair || pl->halo_td == 2 || g.block_n == 128) &&
+  const bool cg2_n32 = g.block_n == 32 && !p.tma_epi && !pl->pair && pl->halo_td == 2 && !p.y2;   // the U-Net's input conv (direct stores)
+  if (pl->halo && (((g.block_n == 64 || g.block_n == 128) && p.tma_epi && (pl->pair || pl->halo_td == 2 || g.block_n == 128)) || cg2_n32) &&
       !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
     const int td = pl->halo_td;   // (pair: d step 2)
     const long long per = (long long)((d->in_w + 7) / 8) * (pl->pair ? (d->in_h + 7) / 8 : (d->in_h + 15) / 16) * ((d->in_d + td - 1) / td) * d->batch;
@@ -1010,7 +1011,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B cg2) failed"); return B200DM_ERR_CUDA; }
-      pl->cg2 = true; pl->wide = false; pl->halo_nb = 3; pl->halo_tps = 3;
+      pl->cg2 = true; pl->wide = false; pl->halo_nb = cg2_n32 ? 4 : 3; pl->halo_tps = 3;
     }
   }
   if (pl->halo) {
@@ -1040,6 +1041,7 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (pl->cg2) {
     if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);
+    if (pl->g.block_n == 32) return launch_halo_cg2<32, 2, kHaloNS, 4, false, false>(pl, s);
     if (pl->g.block_n == 64) return launch_halo_cg2<64, 2, kHaloNSStaged, 3, false>(pl, s);
     return pl->halo_td == 2 ? launch_halo_cg2<128, 2, kHaloNSStaged, 3, false>(pl, s) : launch_halo_cg2<128, 1, kHaloNSStaged, 3, false>(pl, s);
   }

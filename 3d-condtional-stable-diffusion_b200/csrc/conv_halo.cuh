@@ -73,7 +73,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   constexpr int kSlabBytes = PAIR ? 25 * 1024 : halo::kSlabBytes;   // 200 (pair) / 180 rows of 128 B, 1 KB-rounded
   constexpr int kSlabTx = PAIR ? 200 * 128 : halo::kSlabTx;
   constexpr int kKhUnits = PAIR ? 160 : 80;                          // one kh step in 16-byte units (20 / 10 rows)
-  static_assert(!CG2 || (STAGED && BLOCK_N >= 64), "CTA-pair variant: staged epilogue");
+  static_assert(!CG2 || BLOCK_N >= 32, "CTA-pair variant: each CTA stages BLOCK_N / 2 >= 16 weight rows");
   constexpr int kBRows = CG2 ? BLOCK_N / 2 : BLOCK_N;   // weight rows of one tap staged by THIS CTA
   constexpr int kTapBytes = kBRows * 128;
   constexpr int kBBytes = TPS * kTapBytes;
