@@ -998,7 +998,9 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   }
   // CTA pairs (cta_group::2) for every staged halo configuration with 64- or 128-channel tiles: needs an even tile count per
   // n-tile so that the two CTAs of a pair always work on the same n-tile and run the same number of tiles
-  const bool cg2_n32 = g.block_n == 32 && !p.tma_epi && !pl->pair && pl->halo_td == 2 && !p.y2;   // the U-Net's input conv (direct stores)
+  // the U-Net's input conv (256 -> 32, direct stores).  Short-K N=32 convs (the decoder's 32 -> 32 at 128^3) are bound by their
+  // direct-store epilogue; pairing them only couples two epilogues (measured 4.18 -> 4.79 ms), so they stay single-CTA.
+  const bool cg2_n32 = g.block_n == 32 && !p.tma_epi && !pl->pair && pl->halo_td == 2 && !p.y2 && g.nch0 + g.nch1 >= 2;
   if (pl->halo && (((g.block_n == 64 || g.block_n == 128) && p.tma_epi && (pl->pair || pl->halo_td == 2 || g.block_n == 128)) || cg2_n32) &&
       !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
     const int td = pl->halo_td;   // (pair: d step 2)
