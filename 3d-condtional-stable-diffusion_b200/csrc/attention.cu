@@ -367,11 +367,13 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int encode3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+// ld = row stride in elements (0 = d0: contiguous rows); lets Q / K be column blocks of one wider projection output
+int encode3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, uint64_t ld = 0) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) { b200dm_set_error("attention: cuTensorMapEncodeTiled unavailable"); return B200DM_ERR_CUDA; }
+  if (ld == 0) ld = d0;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint64_t strides[2] = {ld * 2, ld * d1 * 2};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
@@ -420,8 +422,12 @@ extern "C" int b200dm_attention_plan_create(const b200dm_attn_desc* d, const voi
   B2_CHECK_ARG(pl, "attention_plan_create: out of memory");
   pl->desc = *d;
   pl->bkv = d->d == 256 ? 64 : 128;
-  int rc = encode3(&pl->mapQ, q, d->d, d->lq, d->batch, 64, 128);
-  if (!rc) rc = encode3(&pl->mapK, k, d->d, d->lk, d->batch, 64, pl->bkv);
+  // reserved[0] / reserved[1]: row strides (elements) of q / k when they are column blocks of a wider tensor (0 = D)
+  B2_CHECK_ARG(d->reserved[0] >= 0 && d->reserved[1] >= 0 && d->reserved[0] % 8 == 0 && d->reserved[1] % 8 == 0 &&
+                   (d->reserved[0] == 0 || d->reserved[0] >= d->d) && (d->reserved[1] == 0 || d->reserved[1] >= d->d),
+               "attention_plan_create: q / k row strides must be 0 or multiples of 8 >= D");
+  int rc = encode3(&pl->mapQ, q, d->d, d->lq, d->batch, 64, 128, (uint64_t)d->reserved[0]);
+  if (!rc) rc = encode3(&pl->mapK, k, d->d, d->lk, d->batch, 64, pl->bkv, (uint64_t)d->reserved[1]);
   if (!rc) rc = encode3(&pl->mapVt, vt, d->lk, d->d, d->batch, 64, d->d);
   if (!rc) rc = encode3(&pl->mapO, o, d->d, d->lq, d->batch, 64, 128);
   if (!rc) rc = encode3(&pl->mapR, residual ? residual : o, d->d, d->lq, d->batch, 64, 128);

@@ -304,14 +304,19 @@ class AttnPlan:
     """softmax(scale * q k^T) v (+ residual) with fixed buffers: q (B,Lq,D), k (B,Lk,D), vt (B,D,Lk), o (B,Lq,D), bf16."""
 
     def __init__(self, q, k, vt, o, scale, residual=None):
+        """q / k may be column blocks of a wider (B, L, ld) tensor (views ``t[..., a:a+D]``): their row stride goes into the desc."""
         _dev()
         B, Lq, D = q.shape
         Lk = k.shape[1]
         assert tuple(k.shape) == (B, Lk, D) and tuple(vt.shape) == (B, D, Lk) and tuple(o.shape) == (B, Lq, D)
-        assert all(t.dtype == torch.bfloat16 and t.is_contiguous() for t in (q, k, vt, o))
+        assert all(t.dtype == torch.bfloat16 for t in (q, k, vt, o)) and vt.is_contiguous() and o.is_contiguous()
+        for t, L_ in ((q, Lq), (k, Lk)):   # rows of D contiguous elements, uniform row stride, samples L rows apart
+            assert t.stride(2) == 1 and t.stride(0) == L_ * t.stride(1), "q / k: unsupported layout"
         self.keep = (q, k, vt, o, residual)
         d = L.AttnDesc()
         d.batch, d.lq, d.lk, d.d, d.scale = B, Lq, Lk, D, float(scale)
+        d.reserved[0] = 0 if q.stride(1) == D else q.stride(1)
+        d.reserved[1] = 0 if k.stride(1) == D else k.stride(1)
         h = C.c_void_p()
         check(lib().b200dm_attention_plan_create(C.byref(d), ptr(q), ptr(k), ptr(vt), ptr(residual), ptr(o), C.byref(h)))
         self.h, self.o, self.owned = h, o, True
@@ -338,6 +343,6 @@ class AttnPlan:
 
 def attention(q, k, vt, scale, residual=None):
     """One-shot flash attention (tests): returns o (B,Lq,D) bf16."""
-    o = torch.empty_like(q)
+    o = torch.empty(q.shape, dtype=q.dtype, device=q.device)
     AttnPlan(q, k, vt, o, scale, residual).run()
     return o

@@ -332,8 +332,12 @@ class UNet:
             pr.sync(lb, lb + 1)
             pr.sync(lb, lb + 2)
             pr.sync(lb, lb + 3)
-            q1 = conv(ln[0], f"{n}.query", c, k=1, dense=True).view(B, Lq, c)
-            k1 = conv(ln[0], f"{n}.key", c, k=1, dense=True).view(B, Lq, c)
+            # query(LN1(h)) and key(LN1(h)) read the same tensor: one Dense with the kernels side by side, [q | k] = x [Wq | Wk];
+            # the attention kernel reads q and k as column blocks (row stride 2C) of its output
+            wqk = torch.cat([P[f"{n}.query.kernel"], P[f"{n}.key.kernel"]], dim=1)
+            bqk = torch.cat([P[f"{n}.query.bias"], P[f"{n}.key.bias"]])
+            qk = conv(ln[0], f"{n}.query+key", 2 * c, k=1, dense=True, kern=wqk, bias_t=bqk).view(B, Lq, 2 * c)
+            q1, k1 = qk[..., :c], qk[..., c:]
             pr.set_lane(lb + 3)
             v1T = conv(ln[0], f"{n}.value", c, k=1, dense=True, transposed_store=True)
             pr.set_lane(lb)

@@ -257,7 +257,8 @@ int b200dm_debug_flag_read_reset(int32_t* flag_out);
 typedef struct {
   int32_t batch, lq, lk, d;
   float scale;
-  int32_t reserved[3];
+  int32_t reserved[3];   /* [0], [1]: row strides (elements) of q / k when they are column blocks of one wider projection output
+                          * (e.g. a fused [q | k] Dense); 0 = D (contiguous rows).  [2]: 0 */
 } b200dm_attn_desc;
 typedef struct b200dm_attn_plan b200dm_attn_plan;
 int b200dm_attention_plan_create(const b200dm_attn_desc* d, const void* q, const void* k, const void* vt,

@@ -83,3 +83,18 @@ def test_flash_attention_full_size_properties(cuda):
     o = _run(cuda, q, torch.zeros(B, L, D), v, D ** -0.5)
     mean = v.mean(1, keepdim=True)
     assert (o - mean).abs().max().item() <= 2e-3 + 2e-2 * mean.abs().max().item()
+
+
+def test_flash_attention_strided_q_k(cuda):
+    """q and k as column blocks of one wider projection output (fused [q | k] Dense): row stride 2D, k 2D*2 bytes... offset D."""
+    from b200dm import ops, _lib
+    B, L, D = 2, 512, 256
+    qk = _rand((B, L, 2 * D), 1)
+    v = _rand((B, L, D), 2)
+    dqk = qk.to(cuda, torch.bfloat16)
+    o = ops.attention(dqk[..., :D], dqk[..., D:], v.transpose(1, 2).contiguous().to(cuda, torch.bfloat16), D ** -0.5)
+    torch.cuda.synchronize()
+    assert _lib.debug_flag() == 0
+    ref = O.attention_core(qk[..., :D], qk[..., D:], v, D ** -0.5)
+    o = o.float().cpu()
+    assert ((o - ref).norm() / ref.norm()).item() <= 5e-3
