@@ -188,7 +188,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   } else if (warp == 2 || (warp == 3 && kIssuers == 2)) {
     // ===================== MMA issuer(s) =====================
     const int pl_lo = kIssuers == 2 ? warp - 2 : 0, pl_hi = kIssuers == 2 ? warp - 1 : TD;   // planes this warp drives
-    const bool tr = warp == 2 && lane == 0;
+    const bool tr = warp == 2;   // (only the elected lane runs the loop below)
     // Descriptors are formed by ADDING 16-byte units to precomputed 64-bit bases (the 14-bit address field cannot
     // carry: smem < 256 KB); inside a stage every offset is a compile-time immediate.
     constexpr uint32_t idesc = ptx::make_idesc_bf16(CG2 ? 256 : 128, BLOCK_N);
@@ -210,6 +210,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       ph = qph ^ (wrap ? 1u : 0u);
       return wrap ? idx - NS : idx;
     };
+    if (ptx::elect_one()) {   // ONE lane runs the whole issue loop: no per-stage elect / warp reconvergence between MMAs
     for (int id = first_tile; id < p.halo_total_tiles && ok && leader; id += tile_step, ++it) {
       const uint32_t as = it & 1;
       if (tr) trace_ev(p, 0, ti, 1);
@@ -246,7 +247,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               ok = ptx::mbar_wait(b_full(sb), bph, p.dbg, 15);
               if (!ok) break;
               ptx::tc_fence_after();
-              if (ptx::elect_one()) {
+              {
                 const uint64_t db0 = b_desc0 + (uint64_t)(sb * (kBBytes >> 4));
 #pragma unroll
                 for (int u = 0; u < TPS; ++u) {
@@ -269,7 +270,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                   if (kd == 2 && TD == 2) commit(slab_empty(rel1));
                 }
               }
-              __syncwarp();
               if (++sb == NB) { sb = 0; bph ^= 1; }
             }
           }
@@ -279,9 +279,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         qs += TD + 2;
         if (qs >= (uint32_t)NS) { qs -= NS; qph ^= 1; }
       }
-      if (ptx::elect_one()) commit(tmem_full(as));
-      __syncwarp();
+      commit(tmem_full(as));
     }
+    }   // elected lane
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 =====================
     // Measured on B200 (64->64 @ 32^3): with 4 warps the epilogue of a tile took as long as the tile's MMA phase and any
