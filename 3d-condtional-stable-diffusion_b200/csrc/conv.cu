@@ -25,6 +25,7 @@
 #include <vector>
 #include "conv_common.cuh"
 #include "conv_halo.cuh"
+#include "conv_halo_up.cuh"
 
 namespace {
 
@@ -533,10 +534,12 @@ struct b200dm_conv_plan {
   int nstage;
   double flops;
   bool halo = false;
+  bool ups = false;    // x2 up-convolution (PARITY mode) on the halo / CTA-pair machinery (conv_halo_up.cuh)
   bool cg2 = false;    // halo kernel, BLOCK_N = 64, two planes, staged: CTA pairs (cta_group::2), see conv_halo.cuh
   bool wide = false;   // halo kernel, BLOCK_N = 128, staged: 3-tap weight stages x 2, 4 slabs (see conv_plan_create)
   bool pair = false;   // halo kernel on 8 x 8 planes: 8w x 8h x 2d tiles from pair slabs (conv_halo.cuh)
   int halo_td = 1, halo_nb = 4, halo_tps = 1;
+  int halo_ns = 0;     // slab ring depth when a variant fixes it (0 = by epilogue kind)
 };
 
 static int* g_dbg_flag = nullptr;
@@ -694,6 +697,26 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
   return B200DM_OK;
 }
 
+template <int BLOCK_N, int NS, int NB>
+static int launch_halo_up(const b200dm_conv_plan* pl, cudaStream_t s) {
+  auto kern = halo::conv_halo_up_kernel<BLOCK_N, NS, NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = pl->grid; cfg.blockDim = dim3(halo::kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
+  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->om, pl->p));
+  return B200DM_OK;
+}
+
 constexpr int kHaloNSPair = 4;   // pair slabs are 25 KB; three per channel chunk are live
 constexpr int kHaloNSWide = 4;
 
@@ -757,7 +780,7 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 
 static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const bool st = pl->p.tma_epi != 0;
-  const int ns = pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : (st ? kHaloNSStaged : kHaloNS));   // (cg2: 5, or 4 for pair slabs)
+  const int ns = pl->halo_ns ? pl->halo_ns : (pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : (st ? kHaloNSStaged : kHaloNS)));   // (cg2: 5, or 4 for pair slabs)
   return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) +
          (size_t)pl->halo_nb * pl->halo_tps * (pl->cg2 ? pl->g.block_n / 2 : pl->g.block_n) * 128 +
          (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
@@ -795,6 +818,15 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
              d->in_d >= 2 && d->reserved[1] == 0 && d->use_halo >= 0 && d->y_dtype == B200DM_BF16 && d->c_out % 64 == 0 &&
              !prelu_alpha && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) && !getenv("B200DM_NO_PAIR");
   if (pl->pair) { pl->halo = true; g.block_n = 64; pl->g.block_n = 64; }
+  // x2 up-convolutions (nearest-upsample + conv3, ConvT k4 s2) on low-resolution planes that fill the 8 x 16 halo tile
+  {
+    const long long per_up = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
+    pl->ups = d->mode == B200DM_CONV_PARITY && d->in_w >= 8 && d->in_h >= 16 && d->in_d >= 2 && d->c_out % 64 == 0 &&
+              d->y_dtype == B200DM_BF16 && !residual && !prelu_alpha && d->reserved[1] == 0 && d->use_halo >= 0 && per_up % 2 == 0 &&
+              (g.block_n == 64 || g.block_n == 128) && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) &&
+              !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0) && !getenv("B200DM_NO_UPS");
+    if (pl->ups) pl->halo = true;
+  }
   // igemm cluster (see the kernel): cl_n n-tiles share A, cl_m m-tiles share B; B200DM_CLUSTER="m,n" switches it on.
   int cl_m = 1, cl_n = 1, a_split_dim = 0, a_split_ext = 0;
   if (!pl->halo && st == 1) {
@@ -1016,12 +1048,25 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       pl->cg2 = true; pl->wide = false; pl->halo_nb = cg2_n32 ? 4 : 3; pl->halo_tps = 3;
     }
   }
+  if (pl->ups) {
+    if (!p.tma_epi) { delete pl; b200dm_set_error("conv_plan_create: internal: up-conv plan without staged epilogue"); return B200DM_ERR_UNSUPPORTED; }
+    // packed [parity][n_pad rows][chunk*8 + tap][64]: one box = this CTA's half of the rows x the 4 in-plane taps of one td
+    cuuint64_t dims3[3] = {64, (cuuint64_t)g.groups * g.n_pad, (cuuint64_t)(g.ktot / 64)};
+    cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
+    cuuint32_t box3[3] = {64, (cuuint32_t)(g.block_n / 2), 4};
+    cuuint32_t es3[3] = {1, 1, 1};
+    if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B up) failed"); return B200DM_ERR_CUDA; }
+    pl->cg2 = true; pl->wide = false; pl->halo_td = 2;
+    pl->halo_nb = g.block_n == 64 ? 3 : 2; pl->halo_tps = 4; pl->halo_ns = 5;
+  }
   if (pl->halo) {
     const int td = pl->halo_td;
     p.tiles_w = (d->in_w + 7) / 8; p.tiles_h = pl->pair ? (d->in_h + 7) / 8 : (d->in_h + 15) / 16; p.tiles_d = (d->in_d + td - 1) / td;
     p.tiles_n = d->batch;
     const long long per = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
-    p.halo_td = td; p.halo_tiles_per_ntile = (int)per; p.halo_ntn = ntiles; p.halo_total_tiles = (int)(per * ntiles);
+    p.halo_td = td; p.halo_tiles_per_ntile = (int)per; p.halo_ntn = ntiles; p.halo_total_tiles = (int)(per * ntiles * (pl->ups ? 8 : 1));
     int ctas = b2_num_sms();
     if (ctas > p.halo_total_tiles) ctas = p.halo_total_tiles;
     if (pl->cg2) ctas &= ~1;   // whole pairs
@@ -1041,6 +1086,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
 extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
+  if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
   if (pl->cg2) {
     if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);
     if (pl->g.block_n == 32) return launch_halo_cg2<32, 2, kHaloNS, 4, false, false>(pl, s);
