@@ -697,9 +697,9 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
   return B200DM_OK;
 }
 
-template <int BLOCK_N, int NS, int NB>
+template <int BLOCK_N, int NS, int NB, bool PAIR = false>
 static int launch_halo_up(const b200dm_conv_plan* pl, cudaStream_t s) {
-  auto kern = halo::conv_halo_up_kernel<BLOCK_N, NS, NB>;
+  auto kern = halo::conv_halo_up_kernel<BLOCK_N, NS, NB, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -826,6 +826,14 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
               (g.block_n == 64 || g.block_n == 128) && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) &&
               !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0) && !getenv("B200DM_NO_UPS");
     if (pl->ups) pl->halo = true;
+    // the same on 8 x 8 low-resolution planes (8^3 -> 16^3): pair-slab tiles
+    const long long per_pair = (long long)((d->in_d + 1) / 2) * d->batch;
+    if (!pl->ups && d->mode == B200DM_CONV_PARITY && d->in_w == 8 && d->in_h == 8 && d->in_d >= 2 && d->in_d % 2 == 0 && d->c_out % 64 == 0 &&
+        d->y_dtype == B200DM_BF16 && !residual && !prelu_alpha && d->reserved[1] == 0 && d->use_halo >= 0 && per_pair % 2 == 0 &&
+        (g.block_n == 64 || g.block_n == 128) && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) &&
+        !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0) && !getenv("B200DM_NO_UPS")) {
+      pl->ups = true; pl->pair = true; pl->halo = true;
+    }
   }
   // igemm cluster (see the kernel): cl_n n-tiles share A, cl_m m-tiles share B; B200DM_CLUSTER="m,n" switches it on.
   int cl_m = 1, cl_n = 1, a_split_dim = 0, a_split_ext = 0;
@@ -1059,7 +1067,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B up) failed"); return B200DM_ERR_CUDA; }
     pl->cg2 = true; pl->wide = false; pl->halo_td = 2;
-    pl->halo_nb = g.block_n == 64 ? 3 : 2; pl->halo_tps = 4; pl->halo_ns = 5;
+    pl->halo_nb = g.block_n == 64 ? 3 : 2; pl->halo_tps = 4; pl->halo_ns = pl->pair ? 4 : 5;
   }
   if (pl->halo) {
     const int td = pl->halo_td;
@@ -1086,6 +1094,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
 extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
+  if (pl->ups && pl->pair) return pl->g.block_n == 64 ? launch_halo_up<64, 4, 3, true>(pl, s) : launch_halo_up<128, 4, 2, true>(pl, s);
   if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
   if (pl->cg2) {
     if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);

@@ -17,13 +17,19 @@
 
 namespace halo {
 
-template <int BLOCK_N, int NS, int NB>
+// PAIR: 8 x 8 low-resolution planes (8^3 -> 16^3): the tile is 8 w x 8 h x 2 d from pair slabs (box {64, 10, 2, 10, 1} of a tensor map
+// whose dims are listed (C, W, D, H, N), rows [h][d][w] as in conv_halo_kernel's PAIR variant): one accumulator, one issuer warp,
+// two pair slabs per channel chunk (td = 0, 1), tap offset (th + ph) * 20 + (tw + pw) rows.
+template <int BLOCK_N, int NS, int NB, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvOutMaps om, const ConvParams p) {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128, "64- or 128-channel tiles");
-  constexpr int TD = 2;
-  constexpr int kSlabBytes = halo::kSlabBytes, kSlabTx = halo::kSlabTx;
+  constexpr int TD = PAIR ? 1 : 2;                 // accumulators (PAIR: one M = 128 tile spanning two planes)
+  constexpr int kSlabsPerChunk = PAIR ? 2 : 3;
+  constexpr int kIss = PAIR ? 1 : 2;               // issuer warps
+  constexpr int kKhUnits = PAIR ? 160 : 80;
+  constexpr int kSlabBytes = PAIR ? 25 * 1024 : halo::kSlabBytes, kSlabTx = PAIR ? 200 * 128 : halo::kSlabTx;
   constexpr int kBRows = BLOCK_N / 2;
   constexpr int kTapBytes = kBRows * 128;
   constexpr int kBBytes = 4 * kTapBytes;
@@ -62,16 +68,16 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     int r = id - nidx * p.halo_tiles_per_ntile;
     t.par = nidx / p.halo_ntn; t.nt = nidx - t.par * p.halo_ntn;
     t.w0 = (r % p.tiles_w) * 8; r /= p.tiles_w;
-    t.h0 = (r % p.tiles_h) * 16; r /= p.tiles_h;
+    t.h0 = (r % p.tiles_h) * (PAIR ? 8 : 16); r /= p.tiles_h;
     t.d0 = (r % p.tiles_d) * 2; r /= p.tiles_d;
     t.n = r;
     return t;
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), 2); }
-    for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 2); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), 2); ptx::mbar_init(tmem_empty(s), 16); }
+    for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), kIss); }
+    for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), kIss); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIss); ptx::mbar_init(tmem_empty(s), 16); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
@@ -94,13 +100,15 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       for (int j = 0; j < nch && ok; ++j) {
         const CUtensorMap* map = j < p.nch0 ? &mapA0 : &mapA1;
         const int c0 = (j < p.nch0 ? j : j - p.nch0) * 64;
-        for (int pl = 0; pl < TD + 1; ++pl) {
+        for (int pl = 0; pl < kSlabsPerChunk; ++pl) {
           ok = ptx::mbar_wait(slab_empty(s), ph, p.dbg, 41);
           if (!ok) break;
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(slab_full(s), 2 * kSlabTx);
-            ptx::tma_load_5d_cg2(slab_base + s * kSlabBytes, map, ptx::mapa_shared(slab_full(s), 0), c0, t.w0 - 1, t.h0 - 1,
-                                 t.d0 - 1 + pd + pl, t.n);
+            if (PAIR) ptx::tma_load_5d_cg2(slab_base + s * kSlabBytes, map, ptx::mapa_shared(slab_full(s), 0), c0, t.w0 - 1,
+                                           t.d0 - 1 + pd + pl, t.h0 - 1, t.n);
+            else ptx::tma_load_5d_cg2(slab_base + s * kSlabBytes, map, ptx::mapa_shared(slab_full(s), 0), c0, t.w0 - 1, t.h0 - 1,
+                                      t.d0 - 1 + pd + pl, t.n);
           }
           __syncwarp();
           if (++s == NS) { s = 0; ph ^= 1; }
@@ -125,7 +133,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (++s == NB) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == 2 || (warp == 3 && kIss == 2)) {
     // ===================== MMA issuers (leader CTA): warp 2 -> output plane 0, warp 3 -> plane 1 =====================
     const int pl = warp - 2;
     constexpr uint32_t idesc = ptx::make_idesc_bf16(256, BLOCK_N);
@@ -153,7 +161,10 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 #pragma unroll 1
           for (int td = 0; td < 2 && ok; ++td) {
             uint32_t phs;
-            if (td == 0) {
+            if (PAIR) {   // pair slab td
+              const uint32_t sl = slot(td, phs);
+              ok = ptx::mbar_wait(slab_full(sl), phs, p.dbg, 44);
+            } else if (td == 0) {
               for (int i = 0; i < TD && ok; ++i) { const uint32_t sl = slot(i, phs); ok = ptx::mbar_wait(slab_full(sl), phs, p.dbg, 44); }
             } else {
               const uint32_t sl = slot(TD, phs);
@@ -167,7 +178,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const uint64_t db0 = b_desc0 + (uint64_t)(sb * (kBBytes >> 4));
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const uint64_t da = a_pl + (uint64_t)((((u >> 1) + ph_) * 80) + ((u & 1) + pw_) * 8);
+              const uint64_t da = a_pl + (uint64_t)((((u >> 1) + ph_) * kKhUnits) + ((u & 1) + pw_) * 8);
               const uint64_t db = db0 + (uint64_t)(u * (kTapBytes >> 4));
               ptx::tc_mma_f16_cg2(acc, da, db, idesc, (j | td | u) != 0 ? 1u : 0u);
               if (ks > 1) ptx::tc_mma_f16_cg2(acc, da + 2, db + 2, idesc, 1u);
@@ -175,7 +186,9 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               if (ks > 3) ptx::tc_mma_f16_cg2(acc, da + 6, db + 6, idesc, 1u);
             }
             ptx::tc_commit_cg2(b_empty(sb), (uint16_t)3);
-            if (td == 0) {
+            if (PAIR) {
+              ptx::tc_commit_cg2(slab_empty(slot(td, phs)), (uint16_t)3);
+            } else if (td == 0) {
               ptx::tc_commit_cg2(slab_empty(slot(0, phs)), (uint16_t)3);
             } else {
               ptx::tc_commit_cg2(slab_empty(slot(1, phs)), (uint16_t)3);
@@ -183,7 +196,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             }
             if (++sb == NB) { sb = 0; bph ^= 1; }
           }
-          qs += TD + 1;
+          qs += kSlabsPerChunk;
           if (qs >= (uint32_t)NS) { qs -= NS; qph ^= 1; }
         }
         ptx::tc_commit_cg2(tmem_full(as), (uint16_t)3);
@@ -248,8 +261,10 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (warp == 4 && lane == 0) {
           for (int g = 0; g < kNG; ++g)
             if (t.nt * BLOCK_N + g * 64 < p.c_out)
-              ptx::tma_store_5d(&om.y[t.par], ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.nt * BLOCK_N + g * 64,
-                                t.w0, t.h0, od, t.n);
+              if (PAIR) ptx::tma_store_5d(&om.y[t.par], ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.nt * BLOCK_N + g * 64,
+                                          t.w0, od, t.h0, t.n);
+              else ptx::tma_store_5d(&om.y[t.par], ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.nt * BLOCK_N + g * 64,
+                                     t.w0, t.h0, od, t.n);
           ptx::bulk_commit_group();
         }
         ++nstore;
