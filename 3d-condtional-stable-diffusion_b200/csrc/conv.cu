@@ -772,7 +772,7 @@ static void halo_ring_config(int block_n, int* nb, int* tps) {
 
 template <int BLOCK_N, int NB, int TPS>
 static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
-  if constexpr (BLOCK_N >= 64) {
+  if constexpr (BLOCK_N >= 32) {
     if (pl->p.tma_epi) return pl->halo_td == 2 ? launch_halo<BLOCK_N, 2, NB, TPS, true>(pl, s) : launch_halo<BLOCK_N, 1, NB, TPS, true>(pl, s);
   }
   return pl->halo_td == 2 ? launch_halo<BLOCK_N, 2, NB, TPS, false>(pl, s) : launch_halo<BLOCK_N, 1, NB, TPS, false>(pl, s);
@@ -970,8 +970,10 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   memset(&pl->om, 0, sizeof(pl->om));
   {
     const bool f32 = d->y_dtype == B200DM_F32;   // fp32 output (the U-Net's eps): halo kernel only, 32-column groups
+    // (halo kernel, C_out = 32: one 32-channel group of 64-byte rows, SWIZZLE_64B -- the decoders' 128^3 convs)
+    const bool n32 = pl->halo && !pl->pair && !pl->ups && d->c_out == 32 && g.block_n == 32 && !f32 && d->mode == B200DM_CONV_DIRECT;
     bool want = cl_m * cl_n == 1 && (!f32 || pl->halo) && d->reserved[1] == 0 && !prelu_alpha &&
-                d->c_out % 64 == 0 && g.block_n >= 64 && !(d->mode == B200DM_CONV_PARITY && residual);
+                ((d->c_out % 64 == 0 && g.block_n >= 64) || n32) && !(d->mode == B200DM_CONV_PARITY && residual);
     if (const char* e = getenv("B200DM_TMA_EPI")) { if (atoi(e) == 0) want = false; }
     if (want) {
       const int par = d->mode == B200DM_CONV_PARITY ? 8 : 1;
@@ -982,7 +984,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
         const cuuint64_t eb = f32 ? 4 : 2;
         cuuint64_t strides[4] = {C * eb * ps, (cuuint64_t)g.out_w * C * eb * ps, (cuuint64_t)g.out_h * g.out_w * C * eb * ps,
                                  (cuuint64_t)g.out_d * g.out_h * g.out_w * C * eb};
-        cuuint32_t box[5] = {f32 ? 32u : 64u, (cuuint32_t)g.box_w, (cuuint32_t)g.box_h, (cuuint32_t)g.box_d, (cuuint32_t)g.box_n};
+        cuuint32_t box[5] = {f32 || n32 ? 32u : 64u, (cuuint32_t)g.box_w, (cuuint32_t)g.box_h, (cuuint32_t)g.box_d, (cuuint32_t)g.box_n};
         if (pl->pair) {   // (C, W, D, H, N) order, one 8w x 2d x 8h tile
           dims[2] = (cuuint64_t)g.m_d; dims[3] = (cuuint64_t)g.m_h;
           const cuuint64_t sh = strides[1], sd = strides[2];
@@ -991,7 +993,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
         } else if (pl->halo) { box[1] = 8; box[2] = 16; box[3] = 1; box[4] = 1; }   // one output plane of the halo kernel's tile
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
         return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                   n32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
       };
       bool okm = true;
       for (int q = 0; q < par && okm; ++q) {
@@ -1040,7 +1042,8 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // n-tile so that the two CTAs of a pair always work on the same n-tile and run the same number of tiles
   // the U-Net's input conv (256 -> 32, direct stores).  Short-K N=32 convs (the decoder's 32 -> 32 at 128^3) are bound by their
   // direct-store epilogue; pairing them only couples two epilogues (measured 4.18 -> 4.79 ms), so they stay single-CTA.
-  const bool cg2_n32 = g.block_n == 32 && !p.tma_epi && !pl->pair && pl->halo_td == 2 && !p.y2 && g.nch0 + g.nch1 >= 2;
+  // With the SWIZZLE_64B staged epilogue (n32 above) those convs run 3.78 ms, paired or not gated on tma_epi any more.
+  const bool cg2_n32 = g.block_n == 32 && !pl->pair && !pl->ups && pl->halo_td == 2 && !p.y2 && g.nch0 + g.nch1 >= 2;
   if (pl->halo && (((g.block_n == 64 || g.block_n == 128) && p.tma_epi && (pl->pair || pl->halo_td == 2 || g.block_n == 128)) || cg2_n32) &&
       !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
     const int td = pl->halo_td;   // (pair: d step 2)
@@ -1098,7 +1101,8 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
   if (pl->cg2) {
     if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);
-    if (pl->g.block_n == 32) return launch_halo_cg2<32, 2, kHaloNS, 4, false, false>(pl, s);
+    if (pl->g.block_n == 32) return pl->p.tma_epi ? launch_halo_cg2<32, 2, kHaloNSStaged, 4, false, true>(pl, s)
+                                                  : launch_halo_cg2<32, 2, kHaloNS, 4, false, false>(pl, s);
     if (pl->g.block_n == 64) return launch_halo_cg2<64, 2, kHaloNSStaged, 3, false>(pl, s);
     return pl->halo_td == 2 ? launch_halo_cg2<128, 2, kHaloNSStaged, 3, false>(pl, s) : launch_halo_cg2<128, 1, kHaloNSStaged, 3, false>(pl, s);
   }

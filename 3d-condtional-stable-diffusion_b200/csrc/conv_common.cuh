@@ -183,7 +183,8 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
 // swizzled staging tile `stg` ([128 rows][128 B], 16-byte chunk index XOR (row & 7) = CU_TENSOR_MAP_SWIZZLE_128B).
 __device__ __forceinline__ void conv_epilogue16_staged(const ConvParams& p, const uint32_t (&rr)[16], int r, int c_local, int col0,
                                                        const float* bs, const float* cb, const float* sc, const uint8_t* rs,
-                                                       uint8_t* stg, bool has_rpre = false, const bf16x8* rpre = nullptr) {
+                                                       uint8_t* stg, bool has_rpre = false, const bf16x8* rpre = nullptr,
+                                                       bool row64 = false) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
@@ -212,8 +213,10 @@ __device__ __forceinline__ void conv_epilogue16_staged(const ConvParams& p, cons
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
   }
-  const int ch = c_local >> 3, sw = r & 7;
-  const uint32_t o0 = (uint32_t)r * 128u + (uint32_t)(((ch) ^ sw) << 4), o1 = (uint32_t)r * 128u + (uint32_t)(((ch + 1) ^ sw) << 4);
+  // 128-byte rows (64 channels, SWIZZLE_128B: chunk ^ (row & 7)) or 64-byte rows (32 channels, SWIZZLE_64B: chunk ^ ((row >> 1) & 3))
+  const int ch = c_local >> 3, sw = row64 ? (r >> 1) & 3 : r & 7;
+  const uint32_t rb_ = (uint32_t)r * (row64 ? 64u : 128u);
+  const uint32_t o0 = rb_ + (uint32_t)(((ch) ^ sw) << 4), o1 = rb_ + (uint32_t)(((ch + 1) ^ sw) << 4);
   if (rs) {
     float a[16];
     unpack8(*reinterpret_cast<const bf16x8*>(rs + o0), *reinterpret_cast<float(*)[8]>(&a[0]));

@@ -52,8 +52,10 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int id) {
 }
 
 // staged epilogue: output staging buffers (each holds one plane's BLOCK_N/64 column groups of 128 rows x 128 B)
-constexpr int stage_bufs(int block_n) { return block_n == 64 ? 2 : 1; }
-constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs(block_n) * (block_n / 64) * 16384 : 0; }
+constexpr int stage_bufs(int block_n) { return block_n <= 64 ? 2 : 1; }
+constexpr int stage_groups(int block_n) { return block_n >= 64 ? block_n / 64 : 1; }          // 64-channel groups (one 32-channel group)
+constexpr int stage_group_bytes(int block_n) { return block_n >= 64 ? 16384 : 8192; }         // 128 rows x 128 B | x 64 B
+constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs(block_n) * stage_groups(block_n) * stage_group_bytes(block_n) : 0; }
 
 // PAIR (small planes, 8 x 8: the 8^3 level of the U-Net): the tile is 8 w x 8 h x 2 d.  The activation tensor map lists
 // its dims as (C, W, D, H, N), so one box {64, 10, 2, 10, 1} lands in smem as rows [h][d][w]: the 16 eight-row groups of
@@ -67,7 +69,7 @@ template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED, bool PAIR =
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const ConvParams p) {
-  static_assert(!STAGED || BLOCK_N >= 64, "staged epilogue works on whole 64-channel groups");
+  static_assert(!STAGED || BLOCK_N >= 32, "staged epilogue works on whole 64-channel groups (or one 32-channel group)");
   static_assert(TPS == 1 || TPS == 3, "taps per weight stage: 1 or 3");
   static_assert(!PAIR || (STAGED && TD == 1), "pair-slab tiles: one accumulator, staged epilogue");
   constexpr int kSlabBytes = PAIR ? 25 * 1024 : halo::kSlabBytes;   // 200 (pair) / 180 rows of 128 B, 1 KB-rounded
@@ -376,13 +378,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       } else if constexpr (STAGED) {
         // bf16 plane tile -> swizzled smem -> one TMA store per 64-channel group (whole 128-byte rows, edges clipped by
         // the TMA unit) instead of row-per-thread 16-byte stores that touch 32 lines per instruction
-        constexpr int kNG = BLOCK_N / 64, kBufs = stage_bufs(BLOCK_N);
-        const int grp = cbase >> 6, cl0 = cbase & 63;
+        constexpr int kNG = stage_groups(BLOCK_N), kBufs = stage_bufs(BLOCK_N), kGB = stage_group_bytes(BLOCK_N);
+        constexpr bool kRow64 = BLOCK_N < 64;   // one 32-channel group: 64-byte rows, SWIZZLE_64B
+        const int grp = kRow64 ? 0 : cbase >> 6, cl0 = kRow64 ? cbase : cbase & 63;
 #pragma unroll
         for (int pl = 0; pl < TD; ++pl) {
           const int od = t.d0 + pl;
           if (od >= p.out_d) break;   // CTA-uniform
-          uint8_t* stg = stg_base + ((nstore % kBufs) * kNG + grp) * 16384;
+          uint8_t* stg = stg_base + ((nstore % kBufs) * kNG + grp) * kGB;
           if (warp == 4 && lane == 0) {   // the store that last used this buffer has finished reading it
             if (kBufs == 2) ptx::bulk_wait_read_1(); else ptx::bulk_wait_read_all();
           }
@@ -393,22 +396,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             const int col0 = colt + c * 16;
             uint32_t ra[16], rb[16];
             ptx::tc_ld_32x32b_x16(taddr + c * 16, ra);
-            ptx::tc_ld_32x32b_x16(taddr + c * 16 + 16, rb);
+            if (c + 1 < kChunks) ptx::tc_ld_32x32b_x16(taddr + c * 16 + 16, rb);
             ptx::tc_wait_ld();
             conv_epilogue16_staged(p, ra, r, cl0 + c * 16, col0, has_bs ? bs + cbase + c * 16 : nullptr, nullptr,
-                                   has_sc ? scs + cbase + c * 16 : nullptr, nullptr, stg, pre, rpre[pl][c]);
-            conv_epilogue16_staged(p, rb, r, cl0 + c * 16 + 16, col0 + 16, has_bs ? bs + cbase + c * 16 + 16 : nullptr, nullptr,
-                                   has_sc ? scs + cbase + c * 16 + 16 : nullptr, nullptr, stg, pre, rpre[pl][c + 1]);
+                                   has_sc ? scs + cbase + c * 16 : nullptr, nullptr, stg, pre, rpre[pl][c], kRow64);
+            if (c + 1 < kChunks)
+              conv_epilogue16_staged(p, rb, r, cl0 + c * 16 + 16, col0 + 16, has_bs ? bs + cbase + c * 16 + 16 : nullptr, nullptr,
+                                     has_sc ? scs + cbase + c * 16 + 16 : nullptr, nullptr, stg, pre, rpre[pl][c + 1 < kChunks ? c + 1 : c], kRow64);
           }
           ptx::fence_proxy_async();
           epilogue_bar_sync256();
           if (warp == 4 && lane == 0) {
             for (int g = 0; g < kNG; ++g)
-              if (t.n_tile * BLOCK_N + g * 64 < p.c_out)
-                if (PAIR) ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.n_tile * BLOCK_N + g * 64,
-                                            t.w0, od, t.h0, t.n);
-                else ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.n_tile * BLOCK_N + g * 64,
-                                       t.w0, t.h0, od, t.n);
+              if (t.n_tile * BLOCK_N + g * 64 < p.c_out) {
+                const uint32_t src = ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * kGB);
+                if (PAIR) ptx::tma_store_5d(&mapY, src, t.n_tile * BLOCK_N + g * 64, t.w0, od, t.h0, t.n);
+                else ptx::tma_store_5d(&mapY, src, t.n_tile * BLOCK_N + g * 64, t.w0, t.h0, od, t.n);
+              }
             ptx::bulk_commit_group();
           }
           ++nstore;
