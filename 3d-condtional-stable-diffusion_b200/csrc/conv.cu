@@ -821,9 +821,11 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // x2 up-convolutions (nearest-upsample + conv3, ConvT k4 s2) on low-resolution planes that fill the 8 x 16 halo tile
   {
     const long long per_up = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
-    pl->ups = d->mode == B200DM_CONV_PARITY && d->in_w >= 8 && d->in_h >= 16 && d->in_d >= 2 && d->c_out % 64 == 0 &&
+    // (C_out = 32 -- the decoders' last ConvT, 64 -> 32 at 64^3 -> 128^3 -- runs N = 32 tiles with 64-byte staged rows)
+    const bool up32 = d->c_out == 32 && g.block_n == 32 && !getenv("B200DM_NO_UP32");
+    pl->ups = d->mode == B200DM_CONV_PARITY && d->in_w >= 8 && d->in_h >= 16 && d->in_d >= 2 && (d->c_out % 64 == 0 || up32) &&
               d->y_dtype == B200DM_BF16 && !residual && !prelu_alpha && d->reserved[1] == 0 && d->use_halo >= 0 && per_up % 2 == 0 &&
-              (g.block_n == 64 || g.block_n == 128) && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) &&
+              (g.block_n == 64 || g.block_n == 128 || up32) && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) &&
               !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0) && !getenv("B200DM_NO_UPS");
     if (pl->ups) pl->halo = true;
     // the same on 8 x 8 low-resolution planes (8^3 -> 16^3): pair-slab tiles
@@ -971,7 +973,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   {
     const bool f32 = d->y_dtype == B200DM_F32;   // fp32 output (the U-Net's eps): halo kernel only, 32-column groups
     // (halo kernel, C_out = 32: one 32-channel group of 64-byte rows, SWIZZLE_64B -- the decoders' 128^3 convs)
-    const bool n32 = pl->halo && !pl->pair && !pl->ups && d->c_out == 32 && g.block_n == 32 && !f32 && d->mode == B200DM_CONV_DIRECT;
+    const bool n32 = pl->halo && !pl->pair && d->c_out == 32 && g.block_n == 32 && !f32 && (pl->ups || d->mode == B200DM_CONV_DIRECT);
     bool want = cl_m * cl_n == 1 && (!f32 || pl->halo) && d->reserved[1] == 0 && !prelu_alpha &&
                 ((d->c_out % 64 == 0 && g.block_n >= 64) || n32) && !(d->mode == B200DM_CONV_PARITY && residual);
     if (const char* e = getenv("B200DM_TMA_EPI")) { if (atoi(e) == 0) want = false; }
@@ -1070,7 +1072,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B up) failed"); return B200DM_ERR_CUDA; }
     pl->cg2 = true; pl->wide = false; pl->halo_td = 2;
-    pl->halo_nb = g.block_n == 64 ? 3 : 2; pl->halo_tps = 4; pl->halo_ns = pl->pair ? 4 : 5;
+    pl->halo_nb = g.block_n == 32 ? 4 : (g.block_n == 64 ? 3 : 2); pl->halo_tps = 4; pl->halo_ns = pl->pair ? 4 : 5;
   }
   if (pl->halo) {
     const int td = pl->halo_td;
@@ -1098,6 +1100,7 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
   if (pl->ups && pl->pair) return pl->g.block_n == 64 ? launch_halo_up<64, 4, 3, true>(pl, s) : launch_halo_up<128, 4, 2, true>(pl, s);
+  if (pl->ups && pl->g.block_n == 32) return launch_halo_up<32, 5, 4>(pl, s);
   if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
   if (pl->cg2) {
     if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);

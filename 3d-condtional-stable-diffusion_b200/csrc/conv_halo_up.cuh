@@ -24,7 +24,7 @@ template <int BLOCK_N, int NS, int NB, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvOutMaps om, const ConvParams p) {
-  static_assert(BLOCK_N == 64 || BLOCK_N == 128, "64- or 128-channel tiles");
+  static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128, "32-, 64- or 128-channel tiles");
   constexpr int TD = PAIR ? 1 : 2;                 // accumulators (PAIR: one M = 128 tile spanning two planes)
   constexpr int kSlabsPerChunk = PAIR ? 2 : 3;
   constexpr int kIss = PAIR ? 1 : 2;               // issuer warps
@@ -207,12 +207,13 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     // ===================== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 4) / 4 =====================
     constexpr int kHalfCols = BLOCK_N / 2;
     constexpr int kChunks = kHalfCols / 16;
-    constexpr int kNG = BLOCK_N / 64, kBufs = stage_bufs(BLOCK_N);
+    constexpr int kNG = stage_groups(BLOCK_N), kBufs = stage_bufs(BLOCK_N), kGB = stage_group_bytes(BLOCK_N);
+    constexpr bool kRow64 = BLOCK_N < 64;   // C_out = 32 (the decoders' last ConvT): 64-byte rows, SWIZZLE_64B (conv_halo.cuh)
     const int qd = warp & 3;
     const int half = (warp - 4) >> 2;
     const int cbase = half * kHalfCols;
     const int r = qd * 32 + lane;
-    const int grp = cbase >> 6, cl0 = cbase & 63;
+    const int grp = kRow64 ? 0 : cbase >> 6, cl0 = kRow64 ? cbase : cbase & 63;
     uint32_t it = 0, nstore = 0;
     for (int id = first_tile; id < p.halo_total_tiles; id += tile_step, ++it) {
       const UTile t = decode(id);
@@ -238,7 +239,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       for (int pl = 0; pl < TD; ++pl) {
         const int od = t.d0 + pl;            // low-resolution (M-space) plane; the parity map places it at 2 * od + pd
         if (od >= p.m_d) break;              // CTA-uniform
-        uint8_t* stg = stg_base + ((nstore % kBufs) * kNG + grp) * 16384;
+        uint8_t* stg = stg_base + ((nstore % kBufs) * kNG + grp) * kGB;
         if (warp == 4 && lane == 0) {
           if (kBufs == 2) ptx::bulk_wait_read_1(); else ptx::bulk_wait_read_all();
         }
@@ -249,21 +250,22 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int col0 = colt + c * 16;
           uint32_t ra[16], rb[16];
           ptx::tc_ld_32x32b_x16(taddr + c * 16, ra);
-          ptx::tc_ld_32x32b_x16(taddr + c * 16 + 16, rb);
+          if (c + 1 < kChunks) ptx::tc_ld_32x32b_x16(taddr + c * 16 + 16, rb);
           ptx::tc_wait_ld();
           conv_epilogue16_staged(p, ra, r, cl0 + c * 16, col0, has_bs ? bs + cbase + c * 16 : nullptr, nullptr,
-                                 has_sc ? scs + cbase + c * 16 : nullptr, nullptr, stg);
-          conv_epilogue16_staged(p, rb, r, cl0 + c * 16 + 16, col0 + 16, has_bs ? bs + cbase + c * 16 + 16 : nullptr, nullptr,
-                                 has_sc ? scs + cbase + c * 16 + 16 : nullptr, nullptr, stg);
+                                 has_sc ? scs + cbase + c * 16 : nullptr, nullptr, stg, false, nullptr, kRow64);
+          if (c + 1 < kChunks)
+            conv_epilogue16_staged(p, rb, r, cl0 + c * 16 + 16, col0 + 16, has_bs ? bs + cbase + c * 16 + 16 : nullptr, nullptr,
+                                   has_sc ? scs + cbase + c * 16 + 16 : nullptr, nullptr, stg, false, nullptr, kRow64);
         }
         ptx::fence_proxy_async();
         epilogue_bar_sync256();
         if (warp == 4 && lane == 0) {
           for (int g = 0; g < kNG; ++g)
             if (t.nt * BLOCK_N + g * 64 < p.c_out)
-              if (PAIR) ptx::tma_store_5d(&om.y[t.par], ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.nt * BLOCK_N + g * 64,
+              if (PAIR) ptx::tma_store_5d(&om.y[t.par], ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * kGB), t.nt * BLOCK_N + g * 64,
                                           t.w0, od, t.h0, t.n);
-              else ptx::tma_store_5d(&om.y[t.par], ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * 16384), t.nt * BLOCK_N + g * 64,
+              else ptx::tma_store_5d(&om.y[t.par], ptx::smem_u32(stg_base + ((nstore % kBufs) * kNG + g) * kGB), t.nt * BLOCK_N + g * 64,
                                      t.w0, t.h0, od, t.n);
           ptx::bulk_commit_group();
         }

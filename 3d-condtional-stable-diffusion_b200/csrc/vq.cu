@@ -31,16 +31,19 @@ __device__ __forceinline__ float4 load_x4(const void* x, int64_t row, int D, int
 }
 
 template <bool kBf16>
-__global__ void __launch_bounds__(256) vq_kernel(b200dm_vq_desc dsc, const void* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) vq_kernel(b200dm_vq_desc dsc, const void* __restrict__ x,
                                                  const float* __restrict__ cb, const float* __restrict__ esq,
                                                  int64_t* __restrict__ idx_out, void* __restrict__ q_out,
                                                  int32_t* __restrict__ hist) {
-  __shared__ float Xs[BK][BM + PAD];
-  __shared__ float Es[BK][BN + PAD];
+  // operand tiles, double-buffered: the global loads of tile it+1 are in flight while tile it is multiplied, one
+  // __syncthreads per tile.  The cross-thread argmin scratch (rbest / ribest) reuses the tile storage after the main loop.
+  constexpr int kTileFloats = BK * (BM + PAD);
+  __shared__ __align__(16) float tiles[4 * kTileFloats];   // [buf][X | E][BK][BM + PAD]
   __shared__ float xsq_s[BM];
-  __shared__ float rbest[BM][17];
-  __shared__ int ribest[BM][17];
   __shared__ int final_idx[BM];
+  static_assert(4 * kTileFloats >= 2 * BM * 17, "argmin scratch fits in the tile storage");
+  float (*rbest)[17] = reinterpret_cast<float (*)[17]>(tiles);
+  int (*ribest)[17] = reinterpret_cast<int (*)[17]>(tiles + BM * 17);
 
   const int D = dsc.d, K = dsc.k;
   const int64_t N = dsc.n;
@@ -67,26 +70,42 @@ __global__ void __launch_bounds__(256) vq_kernel(b200dm_vq_desc dsc, const void*
   for (int i = 0; i < 8; ++i) { best[i] = INFINITY; besti[i] = 0x7fffffff; }
 
   const int lrow = tid >> 2, ld = (tid & 3) << 2;  // loader: rows lrow, lrow+64; 4 consecutive d
-  for (int n0 = 0; n0 < K; n0 += BN) {
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int nd = (D + BK - 1) / BK, total = ((K + BN - 1) / BN) * nd;
+  float4 xa, xb, ea, eb;
+  auto gload = [&](int n0, int d0) {
+    xa = load_x4<kBf16>(x, row0 + lrow, D, d0 + ld, N);
+    xb = load_x4<kBf16>(x, row0 + lrow + 64, D, d0 + ld, N);
+    ea = (n0 + lrow < K && d0 + ld < D) ? __ldg(reinterpret_cast<const float4*>(cb + (int64_t)(n0 + lrow) * D + d0 + ld)) : make_float4(0, 0, 0, 0);
+    eb = (n0 + lrow + 64 < K && d0 + ld < D) ? __ldg(reinterpret_cast<const float4*>(cb + (int64_t)(n0 + lrow + 64) * D + d0 + ld)) : make_float4(0, 0, 0, 0);
+  };
+  auto sstore = [&](int buf) {
+    float (*Xs)[BM + PAD] = reinterpret_cast<float (*)[BM + PAD]>(tiles + (2 * buf) * kTileFloats);
+    float (*Es)[BN + PAD] = reinterpret_cast<float (*)[BN + PAD]>(tiles + (2 * buf + 1) * kTileFloats);
+    Xs[ld + 0][lrow] = xa.x; Xs[ld + 1][lrow] = xa.y; Xs[ld + 2][lrow] = xa.z; Xs[ld + 3][lrow] = xa.w;
+    Xs[ld + 0][lrow + 64] = xb.x; Xs[ld + 1][lrow + 64] = xb.y; Xs[ld + 2][lrow + 64] = xb.z; Xs[ld + 3][lrow + 64] = xb.w;
+    Es[ld + 0][lrow] = ea.x; Es[ld + 1][lrow] = ea.y; Es[ld + 2][lrow] = ea.z; Es[ld + 3][lrow] = ea.w;
+    Es[ld + 0][lrow + 64] = eb.x; Es[ld + 1][lrow + 64] = eb.y; Es[ld + 2][lrow + 64] = eb.z; Es[ld + 3][lrow + 64] = eb.w;
+  };
+  gload(0, 0);
+  sstore(0);
+  __syncthreads();   // (also publishes xsq_s)
 
-    for (int d0 = 0; d0 < D; d0 += BK) {
-      float4 xa = load_x4<kBf16>(x, row0 + lrow, D, d0 + ld, N);
-      float4 xb = load_x4<kBf16>(x, row0 + lrow + 64, D, d0 + ld, N);
-      float4 ea = (n0 + lrow < K && d0 + ld < D) ? __ldg(reinterpret_cast<const float4*>(cb + (int64_t)(n0 + lrow) * D + d0 + ld)) : make_float4(0, 0, 0, 0);
-      float4 eb = (n0 + lrow + 64 < K && d0 + ld < D) ? __ldg(reinterpret_cast<const float4*>(cb + (int64_t)(n0 + lrow + 64) * D + d0 + ld)) : make_float4(0, 0, 0, 0);
-      __syncthreads();
-      Xs[ld + 0][lrow] = xa.x; Xs[ld + 1][lrow] = xa.y; Xs[ld + 2][lrow] = xa.z; Xs[ld + 3][lrow] = xa.w;
-      Xs[ld + 0][lrow + 64] = xb.x; Xs[ld + 1][lrow + 64] = xb.y; Xs[ld + 2][lrow + 64] = xb.z; Xs[ld + 3][lrow + 64] = xb.w;
-      Es[ld + 0][lrow] = ea.x; Es[ld + 1][lrow] = ea.y; Es[ld + 2][lrow] = ea.z; Es[ld + 3][lrow] = ea.w;
-      Es[ld + 0][lrow + 64] = eb.x; Es[ld + 1][lrow + 64] = eb.y; Es[ld + 2][lrow + 64] = eb.z; Es[ld + 3][lrow + 64] = eb.w;
-      __syncthreads();
+  float acc[8][8];
 #pragma unroll
-      for (int k = 0; k < BK; ++k) {
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  int n0 = 0, dt = 0;   // code tile / d tile of iteration `it`
+  for (int it = 0; it < total; ++it) {
+    const int buf = it & 1;
+    const bool more = it + 1 < total;
+    const bool last_d = dt + 1 == nd;
+    if (more) gload(last_d ? n0 + BN : n0, last_d ? 0 : (dt + 1) * BK);
+    {
+      const float (*Xs)[BM + PAD] = reinterpret_cast<const float (*)[BM + PAD]>(tiles + (2 * buf) * kTileFloats);
+      const float (*Es)[BN + PAD] = reinterpret_cast<const float (*)[BN + PAD]>(tiles + (2 * buf + 1) * kTileFloats);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {   // ascending d: the fp32 FMA chain of every (row, code) pair is one fixed sequence
         float a[8], b[8];
         *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
         *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&Xs[k][64 + ty * 4]);
@@ -98,19 +117,30 @@ __global__ void __launch_bounds__(256) vq_kernel(b200dm_vq_desc dsc, const void*
           for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
     }
-    // distances for this code tile; running first-min per row
+    if (more) sstore(buf ^ 1);   // last read at iteration it-1, before that iteration's barrier
+    __syncthreads();
+    if (last_d) {
+      // distances for this code tile; running first-min per row
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int code = n0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-      if (code < K) {
-        const float e2 = __ldg(esq + code);
+      for (int j = 0; j < 8; ++j) {
+        const int code = n0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        if (code < K) {
+          const float e2 = __ldg(esq + code);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
-          const float dist = __fsub_rn(__fadd_rn(xsq_s[r], e2), __fmul_rn(2.0f, acc[i][j]));
-          if (dist < best[i] || (dist == best[i] && code < besti[i])) { best[i] = dist; besti[i] = code; }
+          for (int i = 0; i < 8; ++i) {
+            const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+            const float dist = __fsub_rn(__fadd_rn(xsq_s[r], e2), __fmul_rn(2.0f, acc[i][j]));
+            if (dist < best[i] || (dist == best[i] && code < besti[i])) { best[i] = dist; besti[i] = code; }
+          }
         }
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      n0 += BN; dt = 0;
+    } else {
+      ++dt;
     }
   }
   // cross-thread (16 threads share a row) reduction

@@ -186,6 +186,29 @@ def test_conv_transpose_k4s2(cuda, S, cin, cout):
     _close(y, ref, what="Conv3DTranspose k4 s2")
 
 
+@pytest.mark.parametrize("S,cin,cout,transposed", [(16, 128, 128, False), (16, 64, 64, True), (16, 64, 32, True), (16, 64, 32, False),
+                                                   (16, 96, 32, True)])
+def test_up_conv_halo_kernel_bf16(cuda, S, cin, cout, transposed):
+    """bf16-output x2 up-convolutions on planes that fill the 8 x 16 halo tile run conv_halo_up_kernel (CTA pairs, staged
+    TMA stores through the parity maps); C_out = 32 takes the N = 32 tiles with 64-byte staged rows (the decoders' last
+    ConvT, vqgan_attn_cp.py:404-412).  Tolerance: one bf16 ulp of the output (2^-8) on top of the fp32 bound."""
+    from b200dm import ops, _lib
+    x = _rand((2, S, S, S, cin), 1)
+    b = torch.randn(cout, generator=torch.Generator().manual_seed(3))
+    if transposed:
+        w = _rand((4, 4, 4, cout, cin), 2, 1.0 / np.sqrt(8 * cin))
+        ref = O.conv3d_transpose(x, w, b)
+        tol = 2e-3 + 2.0 ** -8
+    else:
+        w = _rand((3, 3, 3, cin, cout), 2, 1.0 / np.sqrt(27 * cin))
+        ref = O.conv3d(O.upsample_nearest2(x), w, b)
+        tol = 8e-3 + 2.0 ** -8
+    y = ops.conv3d(x.to(cuda, torch.bfloat16), w, bias=b.to(cuda), mode=_lib.CONV_PARITY, transposed=transposed, y_dtype=torch.bfloat16)
+    _check_flag()
+    assert tuple(y.shape) == tuple(ref.shape)
+    _close(y, ref, tol=tol, what="x2 up-conv (halo up kernel), bf16 out")
+
+
 def test_prelu_postact_epilogue(cuda):
     """monai ResUnit tail: relu(x + PReLU(conv(h)))  (vqvae3d_monai.py:233-234), BN folded by the host."""
     from b200dm import ops

@@ -42,7 +42,7 @@ def test_cfg2_chain_is_batch_permutation_equivariant(cuda):
     assert (lat[0] - lat[1]).abs().max() > 1e-3 and (lat - x_T).abs().max() > 1e-3
 
 
-@pytest.mark.parametrize("case", ["halo64", "halo128", "halo32", "halo32s", "pair", "gemm1", "down", "up", "up8"])
+@pytest.mark.parametrize("case", ["halo64", "halo128", "halo32", "halo32s", "pair", "gemm1", "down", "up", "up8", "up32"])
 def test_fullsize_convs_are_exactly_homogeneous(cuda, case):
     """y(4 x) == 4 y(x) bit for bit (no bias): every product and partial sum scales by an exact power of two, so any
     dropped / duplicated tap, tile or K chunk at the full cfg-2 shapes shows up, without an oracle run."""
@@ -52,7 +52,7 @@ def test_fullsize_convs_are_exactly_homogeneous(cuda, case):
                halo32=(32, 256, 32, 3, 1, _lib.CONV_DIRECT), halo32s=(32, 32, 32, 3, 1, _lib.CONV_DIRECT),
                pair=(8, 256, 256, 3, 1, _lib.CONV_DIRECT), gemm1=(8, 256, 1024, 1, 1, _lib.CONV_DIRECT),
                down=(32, 64, 64, 3, 2, _lib.CONV_DIRECT), up=(16, 128, 128, 3, 1, _lib.CONV_PARITY),
-               up8=(8, 256, 256, 3, 1, _lib.CONV_PARITY))[case]
+               up8=(8, 256, 256, 3, 1, _lib.CONV_PARITY), up32=(32, 64, 32, 3, 1, _lib.CONV_PARITY))[case]
     S, cin, cout, k, stride, mode = cfg
     g = torch.Generator().manual_seed(1)
     x = torch.randn(B, S, S, S, cin, generator=g).to(torch.bfloat16)
