@@ -1,0 +1,37 @@
+"""Cut ONE hot-path pass out of an ncu launch list (ncu --metrics gpu__time_duration.sum --csv --log-file X.csv ...) and
+write profiles/<tag>_launches_<what>.csv (every launch) + profiles/<tag>_launches_<what>_summary.csv (per-kernel totals).
+
+    python tools/launch_summary.py gpurun_out/r1h_launches.csv r1h step "<command that produced it>"
+
+`step`: the launches from one step_advance_kernel up to (not including) the next one = one cfg-2 denoise step (graph replay)."""
+import collections, csv, re, sys
+
+src, tag, what, cmd = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
+rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"'))]
+h = rows[0]
+ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+L = []
+for r in rows[1:]:
+    n = re.sub(r"\(.*$", "", re.sub(r"^void ", "", r[ki]))
+    n = re.sub(r"<unnamed>::|\(anonymous namespace\)::|halo::", "", n)
+    L.append((n, float(r[vi].replace(",", "")) / 1000.0))
+marks = [i for i, (n, _) in enumerate(L) if n.startswith("step_advance_kernel")]
+assert len(marks) >= 2, "need two step_advance_kernel launches in the list"
+seq = L[marks[-2]:marks[-1]]
+with open(f"profiles/{tag}_launches_{what}.csv", "w") as f:
+    f.write(f"# {tag}: {cmd}\n# one cfg-2 denoise step (graph replay): every launch from step_advance to the fused update; cold-cache, serialised times\n")
+    f.write("index,kernel,us\n")
+    for i, (n, u) in enumerate(seq):
+        f.write(f'{i},"{n}",{u:.3f}\n')
+tot = sum(u for _, u in seq)
+agg = collections.OrderedDict()
+for n, u in seq:
+    a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += u
+with open(f"profiles/{tag}_launches_{what}_summary.csv", "w") as f:
+    f.write(f"# {tag}: per-kernel totals of one cfg-2 step under ncu (cold-cache, serialised; compare SHARES)\n")
+    f.write("# conv_halo_kernel<BLOCK_N, TD, NS, NB, TPS, STAGED, PAIR, CG2>; conv_halo_up_kernel<BLOCK_N, NS, NB, PAIR>; conv_igemm_kernel<BLOCK_N, NSTAGE, CMODE>\n")
+    f.write("kernel,launches,total_us,share\n")
+    for n, (c, u) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f'"{n}",{c},{u:.1f},{u / tot:.4f}\n')
+    f.write(f"TOTAL,{len(seq)},{tot:.1f},1.0\n")
+print(open(f"profiles/{tag}_launches_{what}_summary.csv").read())
