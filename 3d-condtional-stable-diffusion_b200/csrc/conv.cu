@@ -1045,7 +1045,8 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // the U-Net's input conv (256 -> 32, direct stores).  Short-K N=32 convs (the decoder's 32 -> 32 at 128^3) are bound by their
   // direct-store epilogue; pairing them only couples two epilogues (measured 4.18 -> 4.79 ms), so they stay single-CTA.
   // With the SWIZZLE_64B staged epilogue (n32 above) those convs run 3.78 ms, paired or not gated on tma_epi any more.
-  const bool cg2_n32 = g.block_n == 32 && !pl->pair && !pl->ups && pl->halo_td == 2 && !p.y2 && g.nch0 + g.nch1 >= 2;
+  const bool cg2_short = p.tma_epi && getenv("B200DM_CG2_N32S") && atoi(getenv("B200DM_CG2_N32S")) != 0;   // experiment: pair short-K staged N=32 convs too
+  const bool cg2_n32 = g.block_n == 32 && !pl->pair && !pl->ups && pl->halo_td == 2 && !p.y2 && (g.nch0 + g.nch1 >= 2 || cg2_short);
   if (pl->halo && (((g.block_n == 64 || g.block_n == 128) && p.tma_epi && (pl->pair || pl->halo_td == 2 || g.block_n == 128)) || cg2_n32) &&
       !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
     const int td = pl->halo_td;   // (pair: d step 2)
