@@ -19,6 +19,20 @@ __global__ void sqnorm_kernel(const float* __restrict__ e, int K, int D, float* 
   out[k] = s;
 }
 
+// Two independent IEEE fp32 FMAs in one issue slot (FFMA2, sm_100): each half rounds exactly like fmaf, so distances and
+// indices are bit-identical to the scalar loop; the kernel was issue-bound (76 % issue-active, 81 % of it FFMA).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(uint64_t& acc, uint64_t a, uint64_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 template <bool kBf16>
 __device__ __forceinline__ float4 load_x4(const void* x, int64_t row, int D, int d, int64_t N) {
   if (row >= N || d >= D) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -90,11 +104,11 @@ __global__ void __launch_bounds__(256, 2) vq_kernel(b200dm_vq_desc dsc, const vo
   sstore(0);
   __syncthreads();   // (also publishes xsq_s)
 
-  float acc[8][8];
+  uint64_t acc2[8][4];   // acc2[i][jj] = (acc[i][2 jj], acc[i][2 jj + 1])
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int jj = 0; jj < 4; ++jj) acc2[i][jj] = 0ull;
   int n0 = 0, dt = 0;   // code tile / d tile of iteration `it`
   for (int it = 0; it < total; ++it) {
     const int buf = it & 1;
@@ -111,16 +125,26 @@ __global__ void __launch_bounds__(256, 2) vq_kernel(b200dm_vq_desc dsc, const vo
         *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&Xs[k][64 + ty * 4]);
         *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Es[k][tx * 4]);
         *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Es[k][64 + tx * 4]);
+        uint64_t b2[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int jj = 0; jj < 4; ++jj) b2[jj] = pack2(b[2 * jj], b[2 * jj + 1]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int i = 0; i < 8; ++i) {
+          const uint64_t a2 = pack2(a[i], a[i]);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) ffma2(acc2[i][jj], a2, b2[jj]);
+        }
       }
     }
     if (more) sstore(buf ^ 1);   // last read at iteration it-1, before that iteration's barrier
     __syncthreads();
     if (last_d) {
       // distances for this code tile; running first-min per row
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) unpack2(acc2[i][jj], acc[i][2 * jj], acc[i][2 * jj + 1]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int code = n0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
@@ -137,7 +161,7 @@ __global__ void __launch_bounds__(256, 2) vq_kernel(b200dm_vq_desc dsc, const vo
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int jj = 0; jj < 4; ++jj) acc2[i][jj] = 0ull;
       n0 += BN; dt = 0;
     } else {
       ++dt;
