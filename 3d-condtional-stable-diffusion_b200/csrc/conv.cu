@@ -684,10 +684,13 @@ static int launch_conv(const b200dm_conv_plan* pl, cudaStream_t s) {
 
 constexpr int kHaloNS = 6;         // slab ring depth, direct-store epilogue
 constexpr int kHaloNSStaged = 5;   // staged epilogue: one slab less, the room holds the output staging tiles
+// N <= 32 tiles have small weight stages and 16 KB of staging: room for the 6th slab.  With 5 (4 live per 2-plane tile) the
+// issuers waited ~1000 cycles per 8000-cycle tile for the first two slabs of the next tile (tools/conv_trace.py, 128^3 32 -> 32).
+constexpr int halo_ns_for(int block_n, bool staged) { return staged && block_n > 32 ? kHaloNSStaged : kHaloNS; }
 
 template <int BLOCK_N, int TD, int NB, int TPS, bool STAGED>
 static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
-  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, STAGED ? kHaloNSStaged : kHaloNS, NB, TPS, STAGED>;
+  auto kern = halo::conv_halo_kernel<BLOCK_N, TD, halo_ns_for(BLOCK_N, STAGED), NB, TPS, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -780,7 +783,7 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 
 static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const bool st = pl->p.tma_epi != 0;
-  const int ns = pl->halo_ns ? pl->halo_ns : (pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : (st ? kHaloNSStaged : kHaloNS)));   // (cg2: 5, or 4 for pair slabs)
+  const int ns = pl->halo_ns ? pl->halo_ns : (pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : halo_ns_for(pl->g.block_n, st)));   // (cg2: 5, or 4 for pair slabs)
   return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) +
          (size_t)pl->halo_nb * pl->halo_tps * (pl->cg2 ? pl->g.block_n / 2 : pl->g.block_n) * 128 +
          (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
@@ -1105,7 +1108,7 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
   if (pl->cg2) {
     if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);
-    if (pl->g.block_n == 32) return pl->p.tma_epi ? launch_halo_cg2<32, 2, kHaloNSStaged, 4, false, true>(pl, s)
+    if (pl->g.block_n == 32) return pl->p.tma_epi ? launch_halo_cg2<32, 2, kHaloNS, 4, false, true>(pl, s)
                                                   : launch_halo_cg2<32, 2, kHaloNS, 4, false, false>(pl, s);
     if (pl->g.block_n == 64) return launch_halo_cg2<64, 2, kHaloNSStaged, 3, false>(pl, s);
     return pl->halo_td == 2 ? launch_halo_cg2<128, 2, kHaloNSStaged, 3, false>(pl, s) : launch_halo_cg2<128, 1, kHaloNSStaged, 3, false>(pl, s);
