@@ -11,8 +11,40 @@ import os
 
 import torch
 
+_lib = None
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libb200dm.so")
+# Two builds of the same sources (build.py): bf16 storage (default; fp32 range) and fp16 storage (8x smaller storage
+# rounding: the precision mode that meets the reference-fp32 chain tolerances).  Selected once
+# per process, before the first kernel call: set_precision("fp16") or B200DM_PRECISION=fp16.
+_LIBS = {"bf16": os.path.join(_HERE, "libb200dm.so"), "fp16": os.path.join(_HERE, "libb200dm_f16.so")}
+_precision = os.environ.get("B200DM_PRECISION", "bf16").lower()
+if _precision not in _LIBS:
+    raise ImportError(f"B200DM_PRECISION={_precision!r}: expected 'bf16' or 'fp16'")
+_LIB_PATH = _LIBS[_precision]
+ACT_DTYPE = torch.bfloat16 if _precision == "bf16" else torch.float16   # torch dtype of every 16-bit buffer
+
+
+def storage(dtype=None):
+    """Normalise a dtype argument: None or any 16-bit float type means 'the library's 16-bit storage type'."""
+    return ACT_DTYPE if dtype in (None, torch.bfloat16, torch.float16) else dtype
+
+
+def precision() -> str:
+    return _precision
+
+
+def set_precision(name: str):
+    """Choose the storage build ('bf16' | 'fp16') for this process.  Must be called before the library is first used."""
+    global _precision, _LIB_PATH, ACT_DTYPE
+    name = name.lower()
+    if name not in _LIBS:
+        raise ValueError(f"precision {name!r}: expected 'bf16' or 'fp16'")
+    if name == _precision:
+        return
+    if _lib is not None:
+        raise B200dmError(f"libb200dm ({_precision}) is already loaded; the storage type is chosen once per process")
+    _precision, _LIB_PATH = name, _LIBS[name]
+    ACT_DTYPE = torch.bfloat16 if name == "bf16" else torch.float16
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
@@ -62,10 +94,14 @@ class ConvDesc(C.Structure):
 _SIGS = {
     "b200dm_version": (C.c_int, []),
     "b200dm_last_error": (C.c_char_p, []),
+    "b200dm_storage_dtype": (C.c_char_p, []),
     "b200dm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200dm_ddpm_update": (C.c_int, [C.POINTER(UpdateDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200dm_philox_normal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "b200dm_step_advance": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "b200dm_step_advance_seq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200dm_gather_rows_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200dm_vq_distances": (C.c_int, [C.POINTER(VqDesc)] + [C.c_void_p] * 5),
     "b200dm_bn_fold": (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200dm_gn_stats": (C.c_int, [C.POINTER(NormDesc), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200dm_gn_stats_workspace": (C.c_size_t, [C.POINTER(NormDesc)]),
@@ -116,7 +152,6 @@ _SIGS = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
-_lib = None
 
 
 def lib():
@@ -130,6 +165,9 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
+        got = l.b200dm_storage_dtype().decode()
+        if got != _precision:
+            raise B200dmError(f"{_LIB_PATH} stores {got}, expected {_precision}: rebuild (python __graft_entry__.py build)")
         _lib = l
     return _lib
 
@@ -155,7 +193,7 @@ def stream():
 def dt(t):
     if t.dtype == torch.float32:
         return F32
-    if t.dtype == torch.bfloat16:
+    if t.dtype == ACT_DTYPE:
         return BF16
     raise B200dmError(f"unsupported dtype {t.dtype}")
 

@@ -14,8 +14,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libb200dm.so")
-OBJ = os.path.join(HERE, "build")
+# (library, object directory, extra nvcc flags): the same sources with bf16 and with IEEE fp16 as the 16-bit storage type
+VARIANTS = {"bf16": (os.path.join(HERE, "libb200dm.so"), os.path.join(HERE, "build"), []),
+            "fp16": (os.path.join(HERE, "libb200dm_f16.so"), os.path.join(HERE, "build_f16"), ["-DB200DM_ACT_FP16"])}
+OUT = VARIANTS["bf16"][0]
 SOURCES = ["api.cu", "update.cu", "norm.cu", "norm_ex.cu", "vq.cu", "conv.cu", "attention.cu", "program.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,9 +36,17 @@ def _stamp():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Build both storage variants; returns the path of the default (bf16) library."""
+    with ThreadPoolExecutor(max_workers=len(VARIANTS)) as ex:   # the two variants compile side by side
+        list(ex.map(lambda name: _build_variant(name, force, verbose), VARIANTS))
+    return OUT
+
+
+def _build_variant(name: str, force: bool, verbose: bool) -> str:
+    OUT, OBJ, extra = VARIANTS[name]
     os.makedirs(OBJ, exist_ok=True)
     stamp_file = os.path.join(OBJ, "stamp")
-    stamp = _stamp()
+    stamp = _stamp() + name
     if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return OUT
     if not os.path.exists(NVCC):
@@ -46,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -56,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=6) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)

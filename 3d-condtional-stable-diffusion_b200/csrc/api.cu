@@ -23,6 +23,8 @@ extern "C" int b200dm_version(void) { return B200DM_VERSION; }
 
 extern "C" const char* b200dm_last_error(void) { return g_err; }
 
+extern "C" const char* b200dm_storage_dtype(void) { return B200DM_ACT_NAME; }
+
 extern "C" int b200dm_device_info(int* sm_count, int* cc) {
   int dev = 0;
   B2_CHECK_CUDA(cudaGetDevice(&dev));

@@ -28,8 +28,8 @@ constexpr int kThreads = 192;
 struct AttnParams {
   int batch, lq, lk, d;
   float scale_log2e;                 // scale * log2(e)
-  const __nv_bfloat16* residual;     // [B][Lq][D] or null
-  __nv_bfloat16* o;                  // [B][Lq][D]
+  const act_t* residual;     // [B][Lq][D] or null
+  act_t* o;                  // [B][Lq][D]
   int* dbg;
 };
 
@@ -164,8 +164,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, BKV);
-    constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, D);
+    constexpr uint32_t idesc_s = ptx::make_idesc_act(128, BKV);
+    constexpr uint32_t idesc_o = ptx::make_idesc_act(128, D);
     const uint64_t dq = ptx::make_smem_desc(q_base, 16, 1024, ptx::kLayoutSw128);
     const uint64_t dk = ptx::make_smem_desc(k_base, 16, 1024, ptx::kLayoutSw128);
     const uint64_t dv = ptx::make_smem_desc(v_base, 16, 1024, ptx::kLayoutSw128);
@@ -376,7 +376,7 @@ int encode3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t 
   cuuint64_t strides[2] = {ld * 2, ld * d1 * 2};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = enc(m, kTmapAct16, 3, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { b200dm_set_error("attention: cuTensorMapEncodeTiled failed: %d (dims %llu,%llu,%llu box %u,%u)", (int)r,
@@ -434,8 +434,8 @@ extern "C" int b200dm_attention_plan_create(const b200dm_attn_desc* d, const voi
   if (rc) { delete pl; return rc; }
   pl->p.batch = d->batch; pl->p.lq = d->lq; pl->p.lk = d->lk; pl->p.d = d->d;
   pl->p.scale_log2e = d->scale * 1.4426950408889634f;
-  pl->p.residual = (const __nv_bfloat16*)residual;
-  pl->p.o = (__nv_bfloat16*)o;
+  pl->p.residual = (const act_t*)residual;
+  pl->p.o = (act_t*)o;
   pl->p.dbg = b200dm_dbg_flag_ptr();
   pl->flops = 4.0 * d->batch * (double)d->lq * d->lk * d->d;
   *out = pl;

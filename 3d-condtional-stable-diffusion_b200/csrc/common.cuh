@@ -2,11 +2,34 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/b200dm.h"
 
 void b200dm_set_error(const char* fmt, ...);
+
+// ---- 16-bit activation / weight storage type ------------------------------------------------------------
+// The library is built twice from the same sources: libb200dm.so stores activations and packed weights as bf16
+// (8 significand bits, fp32 range), libb200dm_f16.so (-DB200DM_ACT_FP16) as IEEE fp16 (11 significand bits: 8x smaller
+// storage rounding, range 65504).  tcgen05.mma kind::f16 runs both at the same rate and always accumulates in fp32.
+#ifdef B200DM_ACT_FP16
+typedef __half act_t;
+typedef __half2 act2_t;
+__device__ __forceinline__ float2 act2_to_float2(const act2_t v) { return __half22float2(v); }
+__device__ __forceinline__ act2_t floats_to_act2(float a, float b) { return __floats2half2_rn(a, b); }
+__device__ __forceinline__ float act_to_float(const act_t v) { return __half2float(v); }
+__device__ __forceinline__ act_t float_to_act(float v) { return __float2half_rn(v); }
+#define B200DM_ACT_NAME "fp16"
+#else
+typedef __nv_bfloat16 act_t;
+typedef __nv_bfloat162 act2_t;
+__device__ __forceinline__ float2 act2_to_float2(const act2_t v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ act2_t floats_to_act2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ float act_to_float(const act_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ act_t float_to_act(float v) { return __float2bfloat16_rn(v); }
+#define B200DM_ACT_NAME "bf16"
+#endif
 
 #define B2_CHECK_ARG(cond, ...)                 \
   do {                                          \
@@ -60,7 +83,7 @@ static inline cudaError_t b2_launch(void (*kern)(KArgs...), dim3 grid, dim3 bloc
 
 // ---- small device helpers ------------------------------------------------------------------
 struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  act2_t v[4];
 };
 
 __device__ __forceinline__ bf16x8 ldg_bf16x8(const bf16x8* p) {   // 16-byte read-only load
@@ -72,7 +95,7 @@ __device__ __forceinline__ bf16x8 ldg_bf16x8(const bf16x8* p) {   // 16-byte rea
 __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
+    float2 t = act2_to_float2(p.v[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -80,7 +103,7 @@ __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
 __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   bf16x8 p;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) p.v[i] = floats_to_act2(f[2 * i], f[2 * i + 1]);
   return p;
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }

@@ -173,7 +173,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     {  // whole warp walks the loop; one elected lane issues (no per-lane serialisation loops around UTCHMMA)
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
+      constexpr uint32_t idesc = ptx::make_idesc_act(128, BLOCK_N);
       const uint64_t a_desc0 = ptx::make_smem_desc(smem_base, 16, 1024, ptx::kLayoutSw128);
       const uint64_t b_desc0 = ptx::make_smem_desc(smem_base + kABytes, 16, 1024, ptx::kLayoutSw128);
       bool ok = true;
@@ -513,7 +513,13 @@ int compute_geometry(const b200dm_conv_desc* d, Geometry* g) {
   return B200DM_OK;
 }
 
-uint16_t f32_to_bf16_rne(float f) {
+uint16_t f32_to_bf16_rne(float f) {   // fp32 -> the library's 16-bit storage type (host side), round to nearest even
+#ifdef B200DM_ACT_FP16
+  const __half h = __float2half_rn(f);
+  uint16_t r;
+  memcpy(&r, &h, 2);
+  return r;
+#endif
   uint32_t u;
   memcpy(&u, &f, 4);
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
@@ -878,7 +884,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     else if (cl_n > 1) box[a_split_dim] = (cuuint32_t)a_split_ext;          // this CTA's share of the multicast A tile
 
     cuuint32_t es[5] = {1, (cuuint32_t)st, (cuuint32_t)st, (cuuint32_t)st, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+    CUresult r = enc(m, kTmapAct16, 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200dm_set_error("cuTensorMapEncodeTiled(A) failed: %d (C=%d dims %d,%d,%d,%d box %d,%d,%d,%d stride %d)", (int)r, C, d->in_w, d->in_h, d->in_d, d->batch, g.box_w, g.box_h, g.box_d, g.box_n, st); return B200DM_ERR_CUDA; }
@@ -913,11 +919,11 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       cuuint64_t dims3[3] = {64, (cuuint64_t)g.n_pad, (cuuint64_t)(g.ktot / 64)};
       cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
       cuuint32_t box3[3] = {64, (cuuint32_t)g.block_n, (cuuint32_t)pl->halo_tps};
-      r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es,
+      r = enc(&pl->mapB, kTmapAct16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
-      r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, es,
+      r = enc(&pl->mapB, kTmapAct16, 2, const_cast<void*>(w_packed), dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
@@ -939,7 +945,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   p.act = d->act; p.post_act = d->reserved[0]; p.y_f32 = d->y_dtype == B200DM_F32; p.transposed_store = d->reserved[1];
   p.chan_bias_rows = d->chan_bias_rows;
   p.bias = bias; p.chan_bias = chan_bias; p.t_dev = t_dev;
-  p.residual = (const __nv_bfloat16*)residual; p.prelu_alpha = (const __nv_bfloat16*)prelu_alpha;
+  p.residual = (const act_t*)residual; p.prelu_alpha = (const act_t*)prelu_alpha;
   p.y = y; p.dbg = g_dbg_flag;
   if (const char* e = getenv("B200DM_EPI_DBG")) p.epi_dbg = atoi(e);
   p.cl_m = cl_m; p.cl_n = cl_n; p.a_split_dim = a_split_dim; p.a_split_ext = a_split_ext;
@@ -997,7 +1003,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
           box[1] = 8; box[2] = 2; box[3] = 8; box[4] = 1;
         } else if (pl->halo) { box[1] = 8; box[2] = 16; box[3] = 1; box[4] = 1; }   // one output plane of the halo kernel's tile
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
-        return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : kTmapAct16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    n32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
       };
       bool okm = true;
@@ -1022,7 +1028,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     cuuint64_t strides[4] = {Lv * 2, Lv * d->c_out * 2, Lv * d->c_out * 2, Lv * d->c_out * 2};
     cuuint32_t box[5] = {64, 128, 1, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    if (Lv % 8 == 0 && enc(&pl->om.y[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (Lv % 8 == 0 && enc(&pl->om.y[0], kTmapAct16, 5, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
       p.swap_ab = 1;
       p.tma_epi = 1;
@@ -1038,7 +1044,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
     cuuint32_t box3[3] = {64, 128, 3};
     cuuint32_t es3[3] = {1, 1, 1};
-    if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
+    if (enc(&pl->mapB, kTmapAct16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B wide) failed"); return B200DM_ERR_CUDA; }
     pl->wide = true; pl->halo_nb = 2; pl->halo_tps = 3;
@@ -1059,7 +1065,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
       cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
       cuuint32_t box3[3] = {64, (cuuint32_t)(g.block_n / 2), 3};   // this CTA's half of the rows of a 3-tap weight stage
       cuuint32_t es3[3] = {1, 1, 1};
-      if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
+      if (enc(&pl->mapB, kTmapAct16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B cg2) failed"); return B200DM_ERR_CUDA; }
       pl->cg2 = true; pl->wide = false; pl->halo_nb = cg2_n32 ? 4 : 3; pl->halo_tps = 3;
@@ -1072,7 +1078,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
     cuuint32_t box3[3] = {64, (cuuint32_t)(g.block_n / 2), 4};
     cuuint32_t es3[3] = {1, 1, 1};
-    if (enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
+    if (enc(&pl->mapB, kTmapAct16, 3, const_cast<void*>(w_packed), dims3, strides3, box3, es3,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(B up) failed"); return B200DM_ERR_CUDA; }
     pl->cg2 = true; pl->wide = false; pl->halo_td = 2;
@@ -1157,8 +1163,8 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
   if (p->pair || p->wide || p->cg2) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo plans"); return B200DM_ERR_UNSUPPORTED; }
   if (p->p.tma_epi) { p->p.tma_epi = 0; p->smem = p->halo ? halo_smem_bytes(p) : conv_smem_bytes(p->g.block_n, p->nstage, false); }
-  if (!p->p.y2) { p->p.y2 = (__nv_bfloat16*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
-  else if (!p->p.y3) { p->p.y3 = (__nv_bfloat16*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
+  if (!p->p.y2) { p->p.y2 = (act_t*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
+  else if (!p->p.y3) { p->p.y3 = (act_t*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
   else { b200dm_set_error("conv_plan_add_output: at most two extra outputs"); return B200DM_ERR_UNSUPPORTED; }
   return B200DM_OK;
 }
@@ -1179,7 +1185,7 @@ extern "C" int b200dm_conv_plan_set_side_norm(b200dm_conv_plan* pl, void* y_side
                            (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
   cuuint32_t box[5] = {64, (cuuint32_t)pl->g.box_w, (cuuint32_t)pl->g.box_h, (cuuint32_t)pl->g.box_d, (cuuint32_t)pl->g.box_n};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  if (!enc || enc(&pl->om.s, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, y_side, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (!enc || enc(&pl->om.s, kTmapAct16, 5, y_side, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
     b200dm_set_error("conv_plan_set_side_norm: cuTensorMapEncodeTiled failed");
     return B200DM_ERR_CUDA;

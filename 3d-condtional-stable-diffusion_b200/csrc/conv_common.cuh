@@ -32,14 +32,14 @@ struct ConvParams {
   const float* out_shift;            // CONSUMER: y = act(scale * (acc + bias + temb) + shift)), fp32[c_out]
   const float* chan_bias;
   const int* t_dev;
-  const __nv_bfloat16* residual;
-  const __nv_bfloat16* prelu_alpha;  // (d,h,w,c) bf16, no batch dim
+  const act_t* residual;
+  const act_t* prelu_alpha;  // (d,h,w,c) bf16, no batch dim
   void* y;
   // up to two EXTRA bf16 outputs of the same shape: y_k = act_k(scale_k[co] * v + shift_k[co]) of the final value v --
   // the folded BatchNorm (+ swish) of the tensor's consumers, written by the producer so that no separate
   // normalisation pass ever re-reads the tensor
-  __nv_bfloat16* y2; const float* scale2; const float* shift2; int act2;
-  __nv_bfloat16* y3; const float* scale3; const float* shift3; int act3;
+  act_t* y2; const float* scale2; const float* shift2; int act2;
+  act_t* y3; const float* scale3; const float* shift3; int act3;
   int* dbg;
   long long* trace;                  // optional per-role clock64 timeline of CTA 0 (tuning aid), else nullptr
 };
@@ -60,10 +60,10 @@ __device__ __forceinline__ void trace_ev(const ConvParams& p, int region, int& i
   }
 }
 
-__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float bf(const act_t v) { return act_to_float(v); }
 
 // one extra normalised copy of 16 channels: act(scale * v + shift) -> bf16
-__device__ __forceinline__ void extra_output16(const float (&v)[16], __nv_bfloat16* yo, const float* sc, const float* sh, int act) {
+__device__ __forceinline__ void extra_output16(const float (&v)[16], act_t* yo, const float* sc, const float* sh, int act) {
   float w[16];
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
@@ -117,7 +117,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
     }
     if (p.prelu_alpha) {
       float a[16];
-      const __nv_bfloat16* ap = p.prelu_alpha + vox * p.c_out + col0;
+      const act_t* ap = p.prelu_alpha + vox * p.c_out + col0;
       unpack8(*reinterpret_cast<const bf16x8*>(ap), *reinterpret_cast<float(*)[8]>(&a[0]));
       unpack8(*reinterpret_cast<const bf16x8*>(ap + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
 #pragma unroll
@@ -133,7 +133,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
         unpack8(rpre[0], *reinterpret_cast<float(*)[8]>(&a[0]));
         unpack8(rpre[1], *reinterpret_cast<float(*)[8]>(&a[8]));
       } else {
-        const __nv_bfloat16* rp = p.residual + row_off + col0;
+        const act_t* rp = p.residual + row_off + col0;
         unpack8(*reinterpret_cast<const bf16x8*>(rp), *reinterpret_cast<float(*)[8]>(&a[0]));
         unpack8(*reinterpret_cast<const bf16x8*>(rp + 8), *reinterpret_cast<float(*)[8]>(&a[8]));
       }
@@ -149,7 +149,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
-      __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + row_off + col0;
+      act_t* yo = reinterpret_cast<act_t*>(p.y) + row_off + col0;
       *reinterpret_cast<bf16x8*>(yo) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
       *reinterpret_cast<bf16x8*>(yo + 8) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
     }
@@ -171,7 +171,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
         x = apply_act(x, p.post_act);
         const int64_t o = p.transposed_store ? ((int64_t)n * p.c_out + col) * vox_per + vox : row_off + col;
         if (p.y_f32) reinterpret_cast<float*>(p.y)[o] = x;
-        else reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(x);
+        else reinterpret_cast<act_t*>(p.y)[o] = float_to_act(x);
       }
     }
   }

@@ -193,7 +193,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const bool tr = warp == 2;   // (only the elected lane runs the loop below)
     // Descriptors are formed by ADDING 16-byte units to precomputed 64-bit bases (the 14-bit address field cannot
     // carry: smem < 256 KB); inside a stage every offset is a compile-time immediate.
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(CG2 ? 256 : 128, BLOCK_N);
+    constexpr uint32_t idesc = ptx::make_idesc_act(CG2 ? 256 : 128, BLOCK_N);
     auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accum) {
       if (CG2) ptx::tc_mma_f16_cg2(d, da, db, idesc, accum); else ptx::tc_mma_f16(d, da, db, idesc, accum);
     };

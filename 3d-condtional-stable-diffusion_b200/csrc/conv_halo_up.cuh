@@ -141,7 +141,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   } else if (warp == 2 || (warp == 3 && kIss == 2)) {
     // ===================== MMA issuers (leader CTA): warp 2 -> output plane 0, warp 3 -> plane 1 =====================
     const int pl = warp - 2;
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(256, BLOCK_N);
+    constexpr uint32_t idesc = ptx::make_idesc_act(256, BLOCK_N);
     const uint64_t a_desc0 = ptx::make_smem_desc(slab_base, 16, 1280, ptx::kLayoutSw128);
     const uint64_t b_desc0 = ptx::make_smem_desc(bring_base, 16, 1024, ptx::kLayoutSw128);
     if (leader && ptx::elect_one()) {

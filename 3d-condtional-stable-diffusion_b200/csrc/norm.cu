@@ -23,11 +23,11 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 // pass: its 16 affine coefficients live in registers and the loop is loads / FMAs / stores with no index division
 // (ncu on the generic form: 169 warp instructions per 16-byte vector, issue-bound at 2.3 TB/s).
 template <int ACT>
-__global__ void __launch_bounds__(256, 4) norm_act_kernel(b200dm_norm_desc d, const __nv_bfloat16* __restrict__ x0,
-                                                          const __nv_bfloat16* __restrict__ x1,
+__global__ void __launch_bounds__(256, 4) norm_act_kernel(b200dm_norm_desc d, const act_t* __restrict__ x0,
+                                                          const act_t* __restrict__ x1,
                                                           const float* __restrict__ pa, const float* __restrict__ pb,
                                                           const float* __restrict__ mean_rstd,
-                                                          __nv_bfloat16* __restrict__ y) {
+                                                          act_t* __restrict__ y) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sm[];
@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(256, 4) norm_act_kernel(b200dm_norm_desc d, co
   __syncthreads();
   const int c8n = C >> 3, c08 = d.c0 >> 3;
   const int64_t total = d.voxels * c8n;
-  const __nv_bfloat16* s0 = x0 + (int64_t)n * d.voxels * d.c0;
-  const __nv_bfloat16* s1 = x1 ? x1 + (int64_t)n * d.voxels * d.c1 : nullptr;
-  __nv_bfloat16* yo = y + (int64_t)n * d.voxels * C;
+  const act_t* s0 = x0 + (int64_t)n * d.voxels * d.c0;
+  const act_t* s1 = x1 ? x1 + (int64_t)n * d.voxels * d.c1 : nullptr;
+  act_t* yo = y + (int64_t)n * d.voxels * C;
   constexpr int U = 4;   // independent 16-byte vectors in flight per thread (loads issued before any use)
   const uint32_t tot32 = (uint32_t)total, stride = gridDim.x * blockDim.x;
   const uint32_t i00 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(256, 4) norm_act_kernel(b200dm_norm_desc d, co
     const float4 a0 = *reinterpret_cast<const float4*>(sa + (c8 << 3)), a1 = *reinterpret_cast<const float4*>(sa + (c8 << 3) + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(sb + (c8 << 3)), b1 = *reinterpret_cast<const float4*>(sb + (c8 << 3) + 4);
     const bool first = (int)c8 < c08;
-    const __nv_bfloat16* src = first ? s0 + (c8 << 3) : s1 + ((c8 - c08) << 3);
+    const act_t* src = first ? s0 + (c8 << 3) : s1 + ((c8 - c08) << 3);
     const uint32_t sstride = first ? d.c0 : d.c1;
-    __nv_bfloat16* dst = yo + (c8 << 3);
+    act_t* dst = yo + (c8 << 3);
     for (uint32_t v = i00 / (uint32_t)c8n; v < nvox; v += dv * U) {
       bf16x8 pk[U];
 #pragma unroll
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_kernel(b200dm_norm_desc d, co
 // grid = (chunks, batch).  Thread (row r, octet o) keeps per-channel sum / sumsq for its octet over
 // voxels r, r+R, ... of the block's chunk; the block reduces in a fixed order and writes one
 // (sum, sumsq) pair per group to partial[n][chunk][g].  gn_final combines chunks in fp64.
-__global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t voxels, int C,
+__global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict__ x, int64_t voxels, int C,
                                                          int groups, int chunks, float* __restrict__ partial) {
   pdl_launch_dependents();
   pdl_wait();
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  const __nv_bfloat16* xs = x + (int64_t)n * voxels * C + (o << 3);
+  const act_t* xs = x + (int64_t)n * voxels * C + (o << 3);
   if (r < rows) {
     for (int64_t v = v0 + r; v < v1; v += rows) {
       float f[8];
@@ -186,11 +186,11 @@ __global__ void gn_final_kernel(const float* __restrict__ partial, int batch, in
 
 // ------------------------------------------------------------------ LayerNorm over C (one warp per row)
 template <int kVecPerLane>
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C,
+__global__ void __launch_bounds__(256) layernorm_kernel(const act_t* __restrict__ x, int64_t rows, int C,
                                                         float eps, int n_out, const float* g0, const float* b0,
                                                         const float* g1, const float* b1, const float* g2,
-                                                        const float* b2, __nv_bfloat16* y0, __nv_bfloat16* y1,
-                                                        __nv_bfloat16* y2) {
+                                                        const float* b2, act_t* y0, act_t* y1,
+                                                        act_t* y2) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     for (int o = 0; o < n_out; ++o) {
       const float* g = o == 0 ? g0 : (o == 1 ? g1 : g2);
       const float* b = o == 0 ? b0 : (o == 1 ? b1 : b2);
-      __nv_bfloat16* y = o == 0 ? y0 : (o == 1 ? y1 : y2);
+      act_t* y = o == 0 ? y0 : (o == 1 ? y1 : y2);
 #pragma unroll
       for (int k = 0; k < kVecPerLane; ++k) {
         const int c = (k * 32 + lane) << 3;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------ row softmax fp32 -> bf16
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p,
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, act_t* __restrict__ p,
                                                            int64_t rows, int cols, float scale) {
   pdl_launch_dependents();
   pdl_wait();
@@ -265,13 +265,13 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     __syncthreads();
     const float inv = 1.0f / bc;
     for (int c = threadIdx.x; c < cols; c += blockDim.x)
-      p[row * cols + c] = __float2bfloat16_rn(__expf(sr[c] * scale - m) * inv);
+      p[row * cols + c] = float_to_act(__expf(sr[c] * scale - m) * inv);
     __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------ casts
-__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, act_t* __restrict__ y,
                                                             int64_t n) {
   const int64_t n8 = n >> 3;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -280,9 +280,9 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
     *reinterpret_cast<float4*>(&f[4]) = __ldg(reinterpret_cast<const float4*>(x + (i << 3) + 4));
     *reinterpret_cast<bf16x8*>(y + (i << 3)) = pack8(f);
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) y[(n8 << 3) + threadIdx.x] = __float2bfloat16_rn(x[(n8 << 3) + threadIdx.x]);
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) y[(n8 << 3) + threadIdx.x] = float_to_act(x[(n8 << 3) + threadIdx.x]);
 }
-__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const act_t* __restrict__ x, float* __restrict__ y,
                                                             int64_t n) {
   const int64_t n8 = n >> 3;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16*
     *reinterpret_cast<float4*>(y + (i << 3)) = *reinterpret_cast<float4*>(&f[0]);
     *reinterpret_cast<float4*>(y + (i << 3) + 4) = *reinterpret_cast<float4*>(&f[4]);
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) y[(n8 << 3) + threadIdx.x] = __bfloat162float(x[(n8 << 3) + threadIdx.x]);
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) y[(n8 << 3) + threadIdx.x] = act_to_float(x[(n8 << 3) + threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ small fp32 dense
@@ -376,7 +376,7 @@ extern "C" int b200dm_gn_stats(const b200dm_norm_desc* d, const void* x, float e
   B2_CHECK_ARG(C <= 512 && 256 % (C / 8) == 0, "gn_stats: C=%d unsupported (need C/8 to divide 256, C<=512)", C);
   const int chunks = 64;
   cudaStream_t s = (cudaStream_t)stream;
-  B2_CHECK_CUDA(b2_launch(gn_partial_kernel, dim3(chunks, d->batch), dim3(256), 0, s, (const __nv_bfloat16*)x, d->voxels, C, d->groups, chunks, workspace));
+  B2_CHECK_CUDA(b2_launch(gn_partial_kernel, dim3(chunks, d->batch), dim3(256), 0, s, (const act_t*)x, d->voxels, C, d->groups, chunks, workspace));
   B2_CHECK_LAUNCH();
   const int tot = d->batch * d->groups;
   B2_CHECK_CUDA(b2_launch(gn_final_kernel, dim3((tot + 127) / 128), dim3(128), 0, s, workspace, d->batch, d->groups, chunks,
@@ -415,7 +415,7 @@ extern "C" int b200dm_norm_act_fwd(const b200dm_norm_desc* d, const void* x0, co
     if (m > 1 && (int64_t)gx * 256 < items) gx = (gx + m - 1) / m * m;
   }
   B2_CHECK_CUDA(b2_launch(kern, dim3(gx, d->batch), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream,
-      *d, (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, a, b, mean_rstd, (__nv_bfloat16*)y));
+      *d, (const act_t*)x0, (const act_t*)x1, a, b, mean_rstd, (act_t*)y));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
@@ -428,14 +428,14 @@ extern "C" int b200dm_layernorm_fwd(const void* x, int64_t rows, int32_t c, floa
   B2_CHECK_ARG(n_out >= 1 && n_out <= 3, "layernorm_fwd: n_out must be 1..3");
   const float* g[3] = {nullptr, nullptr, nullptr};
   const float* b[3] = {nullptr, nullptr, nullptr};
-  __nv_bfloat16* y[3] = {nullptr, nullptr, nullptr};
+  act_t* y[3] = {nullptr, nullptr, nullptr};
   for (int i = 0; i < n_out; ++i) {
-    g[i] = gammas[i]; b[i] = betas[i]; y[i] = (__nv_bfloat16*)ys[i];
+    g[i] = gammas[i]; b[i] = betas[i]; y[i] = (act_t*)ys[i];
     B2_CHECK_ARG(g[i] && b[i] && y[i], "layernorm_fwd: null affine/output %d", i);
   }
   const int grid = grid_for(rows * 32, 256, 8);
   cudaStream_t s = (cudaStream_t)stream;
-  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  const act_t* xb = (const act_t*)x;
   if (c <= 256) B2_CHECK_CUDA(b2_launch(layernorm_kernel<1>, dim3(grid), dim3(256), 0, s, xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]));
   else if (c <= 512) B2_CHECK_CUDA(b2_launch(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]));
   else B2_CHECK_CUDA(b2_launch(layernorm_kernel<4>, dim3(grid), dim3(256), 0, s, xb, rows, c, eps, n_out, g[0], b[0], g[1], b[1], g[2], b[2], y[0], y[1], y[2]));
@@ -447,7 +447,7 @@ extern "C" int b200dm_softmax_rows(const float* s, void* p_bf16, int64_t rows, i
   B2_CHECK_ARG(s && p_bf16 && rows > 0 && cols > 0, "softmax_rows: bad arguments");
   const int64_t cap = (int64_t)b2_num_sms() * 8;
   const int grid = (int)(rows < cap ? rows : cap);
-  B2_CHECK_CUDA(b2_launch(softmax_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, s, (__nv_bfloat16*)p_bf16, rows, cols, scale));
+  B2_CHECK_CUDA(b2_launch(softmax_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, s, (act_t*)p_bf16, rows, cols, scale));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
@@ -456,8 +456,8 @@ extern "C" int b200dm_cast(const void* x, int32_t x_dtype, void* y, int32_t y_dt
   B2_CHECK_ARG(x && y && n > 0, "cast: bad arguments");
   const int grid = grid_for((n + 7) / 8, 256, 8);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == B200DM_F32 && y_dtype == B200DM_BF16) cast_f32_bf16_kernel<<<grid, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)y, n);
-  else if (x_dtype == B200DM_BF16 && y_dtype == B200DM_F32) cast_bf16_f32_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (float*)y, n);
+  if (x_dtype == B200DM_F32 && y_dtype == B200DM_BF16) cast_f32_bf16_kernel<<<grid, 256, 0, s>>>((const float*)x, (act_t*)y, n);
+  else if (x_dtype == B200DM_BF16 && y_dtype == B200DM_F32) cast_bf16_f32_kernel<<<grid, 256, 0, s>>>((const act_t*)x, (float*)y, n);
   else { b200dm_set_error("cast: unsupported dtype pair %d -> %d", x_dtype, y_dtype); return B200DM_ERR_UNSUPPORTED; }
   B2_CHECK_LAUNCH();
   return B200DM_OK;
@@ -470,6 +470,27 @@ extern "C" int b200dm_dense_f32(const float* x, const float* w, const float* b, 
   B2_CHECK_ARG((m + 7) / 8 <= 65535, "dense_f32: M too large");
   dim3 grid((unsigned)((n + 127) / 128), (unsigned)((m + 7) / 8));
   dense_f32_kernel<<<grid, 128, (size_t)k * 8 * sizeof(float), (cudaStream_t)stream>>>(x, w, b, y, m, k, n, act_in, act_out);
+  B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}
+
+// out[r][:] = table[idx[r]][:] (fp32): per-sample timestep rows of the hoisted Dense(swish(temb)) tables when the network is
+// called with a (B,) vector of DISTINCT timesteps (train_step draws t ~ U{0..T-1} per sample, conditional_dm3d.py:474,493)
+namespace {
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int32_t* __restrict__ idx, float* __restrict__ out,
+                                   int rows, int cols, int table_rows) {
+  const int r = blockIdx.y;
+  int t = idx[r];
+  t = t < 0 ? 0 : (t >= table_rows ? table_rows - 1 : t);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+    out[(int64_t)r * cols + c] = table[(int64_t)t * cols + c];
+}
+}  // namespace
+
+extern "C" int b200dm_gather_rows_f32(const float* table, int32_t table_rows, const int32_t* idx, float* out, int32_t rows,
+                                      int32_t cols, void* stream) {
+  B2_CHECK_ARG(table && idx && out && rows > 0 && cols > 0 && table_rows > 0 && rows <= 65535, "gather_rows_f32: bad arguments");
+  gather_rows_kernel<<<dim3((cols + 255) / 256, rows), 256, 0, (cudaStream_t)stream>>>(table, idx, out, rows, cols, table_rows);
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }

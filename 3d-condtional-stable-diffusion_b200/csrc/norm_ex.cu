@@ -16,7 +16,7 @@ struct ExParams {
   int batch, od, oh, ow, c, kind, groups, act, post_act, upsample, x_f32, y_f32;
   const void* x;
   const float* pa; const float* pb; const float* mean_rstd;
-  const __nv_bfloat16* alpha; const __nv_bfloat16* residual;
+  const act_t* alpha; const act_t* residual;
   void* y;
 };
 
@@ -49,9 +49,9 @@ __global__ void __launch_bounds__(256) norm_ex_vec_kernel(const ExParams p) {
   const int64_t vox_out = (int64_t)p.od * p.oh * p.ow;
   const int64_t vox_in = p.upsample ? vox_out >> 3 : vox_out;
   const int64_t total = vox_out * c8n;
-  const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(p.x) + (int64_t)n * vox_in * p.c;
-  const __nv_bfloat16* rs = p.residual ? p.residual + (int64_t)n * vox_out * p.c : nullptr;
-  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + (int64_t)n * vox_out * p.c;
+  const act_t* xs = reinterpret_cast<const act_t*>(p.x) + (int64_t)n * vox_in * p.c;
+  const act_t* rs = p.residual ? p.residual + (int64_t)n * vox_out * p.c : nullptr;
+  act_t* yo = reinterpret_cast<act_t*>(p.y) + (int64_t)n * vox_out * p.c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t vo = i / c8n;
     const int c0 = (int)(i - vo * c8n) << 3;
@@ -95,17 +95,17 @@ __global__ void __launch_bounds__(256) norm_ex_scalar_kernel(const ExParams p) {
     const int64_t vo = i / p.c;
     const int c = (int)(i - vo * p.c);
     const int64_t si = ((int64_t)n * vox_in + src_voxel(p, vo)) * p.c + c;
-    float v = p.x_f32 ? reinterpret_cast<const float*>(p.x)[si] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.x)[si]);
+    float v = p.x_f32 ? reinterpret_cast<const float*>(p.x)[si] : act_to_float(reinterpret_cast<const act_t*>(p.x)[si]);
     float a, b;
     affine_of(p, n, c, a, b);
     v = fmaf(v, a, b);
-    if (p.alpha) { const float al = __bfloat162float(p.alpha[vo * p.c + c]); v = fmaxf(v, 0.f) + al * fminf(v, 0.f); }
+    if (p.alpha) { const float al = act_to_float(p.alpha[vo * p.c + c]); v = fmaxf(v, 0.f) + al * fminf(v, 0.f); }
     v = apply_act(v, p.act);
     const int64_t oi = ((int64_t)n * vox_out + vo) * p.c + c;
-    if (p.residual) v += __bfloat162float(p.residual[oi]);
+    if (p.residual) v += act_to_float(p.residual[oi]);
     v = apply_act(v, p.post_act);
     if (p.y_f32) reinterpret_cast<float*>(p.y)[oi] = v;
-    else reinterpret_cast<__nv_bfloat16*>(p.y)[oi] = __float2bfloat16_rn(v);
+    else reinterpret_cast<act_t*>(p.y)[oi] = float_to_act(v);
   }
 }
 
@@ -165,8 +165,8 @@ extern "C" int b200dm_norm_act_ex(const b200dm_norm_ex_desc* d, const void* x, c
   ExParams p;
   p.batch = d->batch; p.od = d->out_d; p.oh = d->out_h; p.ow = d->out_w; p.c = d->c; p.kind = d->kind; p.groups = d->groups;
   p.act = d->act; p.post_act = d->post_act; p.upsample = d->upsample; p.x_f32 = d->x_dtype == B200DM_F32; p.y_f32 = d->y_dtype == B200DM_F32;
-  p.x = x; p.pa = a; p.pb = b; p.mean_rstd = mean_rstd; p.alpha = (const __nv_bfloat16*)prelu_alpha;
-  p.residual = (const __nv_bfloat16*)residual; p.y = y;
+  p.x = x; p.pa = a; p.pb = b; p.mean_rstd = mean_rstd; p.alpha = (const act_t*)prelu_alpha;
+  p.residual = (const act_t*)residual; p.y = y;
   const int64_t vox = (int64_t)d->out_d * d->out_h * d->out_w;
   const bool vec = d->c % 8 == 0 && !p.x_f32 && !p.y_f32;
   const int64_t items = vec ? vox * (d->c >> 3) : vox * d->c;

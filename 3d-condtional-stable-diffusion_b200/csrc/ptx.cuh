@@ -217,9 +217,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)(base_offset & 7u) << 49) |
          (layout << 61);
 }
-// Instruction descriptor, kind::f16: c=F32 (bit4), a=b=BF16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor, kind::f16: c=F32 (bit4), a/b format at bits 7 / 10 (0 = F16, 1 = BF16: the library's 16-bit
+// storage type, common.cuh), K-major both, N>>3 @17, M>>4 @24.
+#ifdef B200DM_ACT_FP16
+constexpr uint32_t kIdescAB = 0u;
+#define kTmapAct16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#else
+constexpr uint32_t kIdescAB = (1u << 7) | (1u << 10);
+#define kTmapAct16 CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#endif
+__host__ __device__ constexpr uint32_t make_idesc_act(int m, int n) {
+  return (1u << 4) | kIdescAB | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -88,7 +88,7 @@ __device__ __forceinline__ float step_one(const Coef& k, int sampler, float x, f
 template <bool kEpsBf16>
 __global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const float* __restrict__ x_t,
                                                      const void* __restrict__ eps, const float* __restrict__ noise,
-                                                     float* __restrict__ x_prev, __nv_bfloat16* __restrict__ x_bf16) {
+                                                     float* __restrict__ x_prev, act_t* __restrict__ x_bf16) {
   pdl_launch_dependents();
   pdl_wait();
   const Coef k = load_coef(d);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const
       *reinterpret_cast<float4*>(&x[u][0]) = __ldg(reinterpret_cast<const float4*>(x_t + off));
       *reinterpret_cast<float4*>(&x[u][4]) = __ldg(reinterpret_cast<const float4*>(x_t + off + 4));
       if (kEpsBf16) {
-        unpack8(ldg_bf16x8(reinterpret_cast<const bf16x8*>(reinterpret_cast<const __nv_bfloat16*>(eps) + off)), e[u]);
+        unpack8(ldg_bf16x8(reinterpret_cast<const bf16x8*>(reinterpret_cast<const act_t*>(eps) + off)), e[u]);
       } else {
         *reinterpret_cast<float4*>(&e[u][0]) = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eps) + off));
         *reinterpret_cast<float4*>(&e[u][4]) = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eps) + off + 4));
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const
   }
 }
 
-__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ x, act_t* __restrict__ xb,
                                                             int64_t n_per_sample, int batch, uint64_t seed,
                                                             int64_t sample_id0, int step, int stream_id) {
   const int64_t n4 = n_per_sample >> 2, total = n4 * batch;
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ 
     const int64_t off = b * n_per_sample + (j << 2);
     *reinterpret_cast<float4*>(x + off) = *reinterpret_cast<float4*>(&z[0]);
     if (xb) {
-      *reinterpret_cast<__nv_bfloat162*>(xb + off) = __floats2bfloat162_rn(z[0], z[1]);
-      *reinterpret_cast<__nv_bfloat162*>(xb + off + 2) = __floats2bfloat162_rn(z[2], z[3]);
+      *reinterpret_cast<act2_t*>(xb + off) = floats_to_act2(z[0], z[1]);
+      *reinterpret_cast<act2_t*>(xb + off + 2) = floats_to_act2(z[2], z[3]);
     }
   }
 }
@@ -165,6 +165,18 @@ __global__ void step_advance_kernel(int32_t* t_dev, int32_t delta) {
   pdl_wait();
   t_dev[0] += delta;
   t_dev[1] += delta;
+}
+
+// t_dev = [t, t_prev, idx, -]: move to the next entry of a device-resident timestep sequence (terminated by -1), so one
+// captured step graph replays ANY sequence -- every DDPM range, strided DDIM, non-uniform spacings -- with no host work.
+__global__ void step_advance_seq_kernel(int32_t* t_dev, const int32_t* __restrict__ seq) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = t_dev[2] + 1;
+  t_dev[2] = i;
+  const int t = seq[i];
+  t_dev[0] = t < 0 ? 0 : t;                 // past the end: stay on a valid table row (the step's result is unused)
+  t_dev[1] = t < 0 ? -1 : seq[i + 1];
 }
 
 }  // namespace
@@ -185,9 +197,9 @@ extern "C" int b200dm_ddpm_update(const b200dm_update_desc* d, const float* x_t,
   const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)d->batch);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->eps_dtype == B200DM_BF16)
-    B2_CHECK_CUDA(b2_launch(update_kernel<true>, grid, dim3(256), 0, s, *d, x_t, eps, noise, x_prev, (__nv_bfloat16*)x_prev_bf16));
+    B2_CHECK_CUDA(b2_launch(update_kernel<true>, grid, dim3(256), 0, s, *d, x_t, eps, noise, x_prev, (act_t*)x_prev_bf16));
   else
-    B2_CHECK_CUDA(b2_launch(update_kernel<false>, grid, dim3(256), 0, s, *d, x_t, eps, noise, x_prev, (__nv_bfloat16*)x_prev_bf16));
+    B2_CHECK_CUDA(b2_launch(update_kernel<false>, grid, dim3(256), 0, s, *d, x_t, eps, noise, x_prev, (act_t*)x_prev_bf16));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }
@@ -198,8 +210,15 @@ extern "C" int b200dm_philox_normal(float* x, void* x_bf16, int64_t n_per_sample
   const int64_t total = (n_per_sample >> 2) * batch;
   const int64_t want = (total + 255) / 256;
   const int grid = (int)(want < (int64_t)b2_num_sms() * 8 ? want : (int64_t)b2_num_sms() * 8);
-  philox_normal_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)x_bf16, n_per_sample, batch, seed,
+  philox_normal_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (act_t*)x_bf16, n_per_sample, batch, seed,
                                                               sample_id0, step, stream_id);
+  B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_step_advance_seq(int32_t* t_dev, const int32_t* seq, void* stream) {
+  B2_CHECK_ARG(t_dev && seq, "step_advance_seq: null argument");
+  B2_CHECK_CUDA(b2_launch(step_advance_seq_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, t_dev, seq));
   B2_CHECK_LAUNCH();
   return B200DM_OK;
 }

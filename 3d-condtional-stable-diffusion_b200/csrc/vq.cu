@@ -37,8 +37,8 @@ template <bool kBf16>
 __device__ __forceinline__ float4 load_x4(const void* x, int64_t row, int D, int d, int64_t N) {
   if (row >= N || d >= D) return make_float4(0.f, 0.f, 0.f, 0.f);
   if (kBf16) {
-    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * D + d);
-    const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+    const act2_t* p = reinterpret_cast<const act2_t*>(reinterpret_cast<const act_t*>(x) + row * D + d);
+    const float2 a = act2_to_float2(p[0]), b = act2_to_float2(p[1]);
     return make_float4(a.x, a.y, b.x, b.y);
   }
   return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row * D + d));
@@ -183,6 +183,9 @@ __global__ void __launch_bounds__(256, 2) vq_kernel(b200dm_vq_desc dsc, const vo
       const int vi = ribest[tid][t];
       if (v < b || (v == b && vi < bi)) { b = v; bi = vi; }
     }
+    // a row holding a NaN compares false against everything and keeps the sentinel: report code 0 for it (tf.argmin
+    // also returns an in-range index for such rows) instead of indexing the histogram / codebook out of bounds
+    if ((unsigned)bi >= (unsigned)K) bi = 0;
     final_idx[tid] = bi;
     const int64_t r = row0 + tid;
     if (r < N) {
@@ -203,16 +206,71 @@ __global__ void __launch_bounds__(256, 2) vq_kernel(b200dm_vq_desc dsc, const vo
         if (dsc.q_dtype == B200DM_F32) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(q_out) + gr * D + d) = v;
         } else {
-          __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(q_out) + gr * D + d);
-          o[0] = __floats2bfloat162_rn(v.x, v.y);
-          o[1] = __floats2bfloat162_rn(v.z, v.w);
+          act2_t* o = reinterpret_cast<act2_t*>(reinterpret_cast<act_t*>(q_out) + gr * D + d);
+          o[0] = floats_to_act2(v.x, v.y);
+          o[1] = floats_to_act2(v.z, v.w);
         }
       }
     }
   }
 }
 
+// get_code_indices(..., distribution=True) (vqvae3d_monai.py:165-177): the (N, K) matrix of squared distances itself, with
+// the same fp32 chain as vq_kernel (ascending-d FMA, then (||x||^2 + ||e||^2) - 2 x.e), so argmin(row) == the kernel's index.
+// A training-time diagnostic of the reference: one thread per (row, code), 16 rows x 16 codes per block through smem.
+template <bool kBf16>
+__global__ void __launch_bounds__(256) vq_dist_kernel(b200dm_vq_desc dsc, const void* __restrict__ x, const float* __restrict__ cb,
+                                                      const float* __restrict__ esq, float* __restrict__ out) {
+  __shared__ float xs[16][65], es[16][65];
+  const int D = dsc.d, K = dsc.k;
+  const int64_t N = dsc.n, row0 = (int64_t)blockIdx.y * 16;
+  const int code0 = blockIdx.x * 16, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc = 0.f, xsq = 0.f;
+  for (int d0 = 0; d0 < D; d0 += 64) {
+    for (int i = threadIdx.x; i < 16 * 16; i += 256) {   // 16 rows x 16 float4
+      const int r = i >> 4, d = d0 + ((i & 15) << 2);
+      const float4 v = load_x4<kBf16>(x, row0 + r, D, d, N);
+      xs[r][(i & 15) * 4] = v.x; xs[r][(i & 15) * 4 + 1] = v.y; xs[r][(i & 15) * 4 + 2] = v.z; xs[r][(i & 15) * 4 + 3] = v.w;
+      const float4 e = (code0 + r < K && d < D) ? __ldg(reinterpret_cast<const float4*>(cb + (int64_t)(code0 + r) * D + d)) : make_float4(0, 0, 0, 0);
+      es[r][(i & 15) * 4] = e.x; es[r][(i & 15) * 4 + 1] = e.y; es[r][(i & 15) * 4 + 2] = e.z; es[r][(i & 15) * 4 + 3] = e.w;
+    }
+    __syncthreads();
+    const int nd = (D - d0) < 64 ? (D - d0) : 64;
+    for (int d = 0; d < nd; ++d) {
+      acc = fmaf(xs[ty][d], es[tx][d], acc);
+      xsq = __fadd_rn(xsq, __fmul_rn(xs[ty][d], xs[ty][d]));
+    }
+    __syncthreads();
+  }
+  const int64_t r = row0 + ty;
+  const int code = code0 + tx;
+  if (r < N && code < K) out[r * K + code] = __fsub_rn(__fadd_rn(xsq, __ldg(esq + code)), __fmul_rn(2.0f, acc));
+}
+
 }  // namespace
+
+extern "C" int b200dm_vq_distances(const b200dm_vq_desc* d, const void* x, const float* codebook_kd, const float* code_sqnorm,
+                                   float* dist, void* stream) {
+  B2_CHECK_ARG(d, "vq_distances: null desc");
+  if (d->n == 0) return B200DM_OK;
+  B2_CHECK_ARG(x && codebook_kd && code_sqnorm && dist, "vq_distances: null argument");
+  B2_CHECK_ARG(d->n > 0 && d->k > 0 && d->d > 0 && d->d % 4 == 0, "vq_distances: need d %% 4 == 0, k > 0");
+  B2_CHECK_ARG(d->x_dtype == B200DM_F32 || d->x_dtype == B200DM_BF16, "vq_distances: bad x dtype");
+  const int64_t by = (d->n + 15) / 16;
+  B2_CHECK_ARG(by <= 65535 * 16, "vq_distances: too many rows for one call (diagnostic path; split the input)");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int64_t y0 = 0; y0 < by; y0 += 65535) {   // grid.y limit
+    const unsigned ny = (unsigned)((by - y0) < 65535 ? (by - y0) : 65535);
+    b200dm_vq_desc dd = *d;
+    dd.n = d->n - y0 * 16;
+    const char* xp = (const char*)x + (size_t)y0 * 16 * d->d * (d->x_dtype == B200DM_F32 ? 4 : 2);
+    const dim3 grid((d->k + 15) / 16, ny);
+    if (d->x_dtype == B200DM_BF16) vq_dist_kernel<true><<<grid, 256, 0, s>>>(dd, xp, codebook_kd, code_sqnorm, dist + y0 * 16 * d->k);
+    else vq_dist_kernel<false><<<grid, 256, 0, s>>>(dd, xp, codebook_kd, code_sqnorm, dist + y0 * 16 * d->k);
+  }
+  B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}
 
 extern "C" int b200dm_vq_prepare(const float* codebook_kd, int32_t k, int32_t d, float* code_sqnorm, void* stream) {
   B2_CHECK_ARG(codebook_kd && code_sqnorm && k > 0 && d > 0, "vq_prepare: bad arguments");

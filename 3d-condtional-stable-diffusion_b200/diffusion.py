@@ -104,7 +104,9 @@ class DiffusionModel:
         return c
 
     def _compile(self, batch, sampler, inject_noise, seed, sample_id0):
-        key = (batch, sampler, inject_noise, self._num_chains(batch))
+        # the compiled copies hold PACKED weights: key on the network's weights version so that network.set_weights /
+        # network.load_weights is never followed by sampling with the old weights
+        key = (batch, sampler, inject_noise, self._num_chains(batch), self.network.weights_version)
         if self._step is not None and self._step["key"] == key:
             st = self._step
             if (st["seed"], st["sample_id0"]) != (seed, sample_id0):
@@ -116,7 +118,8 @@ class DiffusionModel:
         L.require_gpu()
         dev = torch.device("cuda", torch.cuda.current_device())
         self.b.to(dev)
-        t_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+        t_dev = torch.zeros(4, dtype=torch.int32, device=dev)        # [t, t_prev, sequence index, -]
+        t_seq = torch.full((self.timesteps + 2,), -1, dtype=torch.int32, device=dev)   # the call's timestep sequence, -1 terminated
         chains = key[3]
         cb = batch // chains
         # one compiled program per chain: shallow copies of self.network (weights shared on the host, buffers per chain)
@@ -126,8 +129,8 @@ class DiffusionModel:
         noise = torch.zeros_like(x) if inject_noise else None
         descs = [ops.make_update_desc(self.b, x[0].numel(), cb, 0, -1, 1 if sampler == "ddim" else 0, seed,
                                       sample_id0 + c * cb, L.F32, t_dev=t_dev) for c in range(chains)]
-        self._step = dict(key=key, nets=nets, net=nets[0], x=x, noise=noise, descs=descs, t_dev=t_dev, graph=None, dev=dev,
-                          delta=-1, chains=chains, chain_batch=cb, seed=seed, sample_id0=sample_id0, streams=None)
+        self._step = dict(key=key, nets=nets, net=nets[0], x=x, noise=noise, descs=descs, t_dev=t_dev, t_seq=t_seq, graph=None, dev=dev,
+                          chains=chains, chain_batch=cb, seed=seed, sample_id0=sample_id0, streams=None)
         return self._step
 
     def _run_chain(self, st, c):
@@ -140,8 +143,8 @@ class DiffusionModel:
                                            L.ptr(net.x_in), L.stream()))
 
     def _run_step_eager(self, st, parallel=False):
-        """Every chain's forward + update, then t -= delta.  ``parallel``: fork the chains onto side streams (inside a
-        graph capture this records parallel branches)."""
+        """Every chain's forward + update, then t_dev moves to the next entry of the device-resident timestep sequence.
+        ``parallel``: fork the chains onto side streams (inside a graph capture this records parallel branches)."""
         if parallel and st["chains"] > 1:
             if st["streams"] is None:
                 st["streams"] = [torch.cuda.Stream() for _ in range(st["chains"] - 1)]
@@ -156,7 +159,7 @@ class DiffusionModel:
         else:
             for c in range(st["chains"]):
                 self._run_chain(st, c)
-        L.check(L.lib().b200dm_step_advance(L.ptr(st["t_dev"]), st["delta"], L.stream()))
+        L.check(L.lib().b200dm_step_advance_seq(L.ptr(st["t_dev"]), L.ptr(st["t_seq"]), L.stream()))
 
     def _capture(self, st):
         g = torch.cuda.CUDAGraph()
@@ -171,13 +174,20 @@ class DiffusionModel:
         st["graph"] = g
         return g
 
-    def generate(self, shape=(1, 16, 16, 16, 16), last_step=0, context_value=None, *, x_T=None, noise=None, seed=1234,
-                 sample_id0=0, sampler="ddpm", steps=None, context=None, use_graph=True, on_step=None):
+    def generate(self, shape=(1, 16, 16, 16, 16), last_step=0, context_value=None, *, x_T=None, noise=None, seed=None,
+                 sample_id0=0, sampler="ddpm", steps=None, context=None, use_graph=True, on_step=None, timestep_seq=None):
         """Reverse diffusion from t=T-1 down to ``last_step`` (dm3d.py:510-532).  ``noise``: callable i -> tensor or
-        dict/sequence indexed by timestep, injected instead of the Philox stream (parity tests).  Returns fp32 latents."""
+        dict/sequence indexed by timestep, injected instead of the Philox stream (parity tests).  ``seed=None`` draws a fresh
+        seed per call (the reference draws fresh tf.random.normal noise on every call); it is kept in ``self.last_seed``.
+        ``sampler="ddim"`` with ``steps=n`` (or an explicit descending ``timestep_seq``) walks a sub-sequence of the schedule.
+        The timestep sequence lives in device memory and the captured step graph indexes it, so every sequence -- DDPM ranges,
+        strided or non-uniform DDIM -- replays the same graph with no host work between steps.  Returns fp32 latents."""
         shape = tuple(shape)
         B = shape[0]
         assert shape[1] == self.latent_size and shape[-1] == self.lc, "shape must match the compiled latent geometry"
+        if seed is None:
+            seed = int.from_bytes(os.urandom(7), "little")
+        self.last_seed = seed
         st = self._compile(B, sampler, noise is not None, seed, sample_id0)
         dev, nets, cb = st["dev"], st["nets"], st["chain_batch"]
         if self.conditional:
@@ -187,49 +197,47 @@ class DiffusionModel:
                 ctx = ctx.expand(B)  # the reference feeds a batch-1 context (conditional_dm3d.py:552)
             for c, net in enumerate(nets):
                 net.set_context(ctx[c * cb:(c + 1) * cb])
+        T = self.timesteps
+        if timestep_seq is not None:
+            seq = [int(v) for v in timestep_seq]
+            assert all(0 <= v < T for v in seq) and all(a > b for a, b in zip(seq, seq[1:])), "timestep_seq: descending values in [0, T)"
+        elif sampler == "ddim":
+            n = steps or T
+            seq = sorted({int(round(v)) for v in np.linspace(last_step, T - 1, n)}, reverse=True)
+        else:
+            seq = list(range(T - 1, last_step - 1, -1))
+        if not seq:
+            raise ValueError("generate: empty timestep sequence")
+        # one small H2D per call: the whole sequence (+ the -1 terminators) and the walker's start state
+        st["t_seq"].copy_(torch.tensor(seq + [-1] * (T + 2 - len(seq)), dtype=torch.int32), non_blocking=True)
+        start = torch.tensor([seq[0], seq[1] if len(seq) > 1 else -1, 0, 0], dtype=torch.int32)
         if x_T is None:  # samples = tf.random.normal(shape) (dm3d.py:513): Philox stream 1
             x0, xb = ops.philox_normal(shape, seed, sample_id0, 0, 1, want_bf16=True)
         else:
-            x0 = x_T.to(dev, torch.float32).contiguous()
-            xb = ops.cast(x0, torch.bfloat16)
+            x0 = x_T.to(dev, torch.float32, non_blocking=True).contiguous()
+            xb = ops.cast(x0, L.ACT_DTYPE)
 
         def load_state():
             st["x"].copy_(x0)
             for c, net in enumerate(nets):
                 net.x_in.copy_(xb[c * cb:(c + 1) * cb])
+            st["t_dev"].copy_(start, non_blocking=True)
 
         load_state()
-        T = self.timesteps
-        if sampler == "ddim":
-            n = steps or T
-            seq = sorted({int(round(v)) for v in np.linspace(last_step, T - 1, n)}, reverse=True)
-        else:
-            seq = list(range(T - 1, last_step - 1, -1))
-        uniform = all(seq[i] - seq[i + 1] == seq[0] - seq[1] for i in range(len(seq) - 1)) if len(seq) > 1 else True
-        delta = (seq[1] - seq[0]) if len(seq) > 1 else -1
-        graph_ok = use_graph and noise is None and on_step is None and uniform and sampler == "ddpm"
-        if graph_ok:
-            if st["graph"] is None or st["delta"] != delta:
-                st["delta"] = delta
-                st["t_dev"].copy_(torch.tensor([seq[0], seq[0] + delta], dtype=torch.int32))
-                # capture runs one warm-up step + records one: restore state afterwards
-                self._capture(st)
+        if use_graph and noise is None and on_step is None:
+            if st["graph"] is None:
+                self._capture(st)   # runs one warm-up step + records one: restore the state afterwards
                 load_state()
-            st["t_dev"].copy_(torch.tensor([seq[0], seq[0] + delta], dtype=torch.int32))
             for _ in seq:
                 st["graph"].replay()
         else:
-            for j, i in enumerate(seq):
-                nxt = seq[j + 1] if j + 1 < len(seq) else -1
-                st["t_dev"].copy_(torch.tensor([i, nxt], dtype=torch.int32))
+            for i in seq:
                 if noise is not None and i > 0:
                     z = noise(i) if callable(noise) else noise[i]
                     st["noise"].copy_(z.to(dev, torch.float32))
-                st["delta"] = 0
                 self._run_step_eager(st)
                 if on_step is not None:
                     on_step(i, st["x"], torch.cat([net.eps for net in nets], 0))
-            st["delta"] = -1 if st["graph"] is None else st["delta"]
         return st["x"].clone()
 
     def encode(self, images):
@@ -251,19 +259,20 @@ class DiffusionModel:
         """latents -> volumes through the first-stage decoder; ``quantize=True`` snaps latents to the codebook first
         (extension: the reference's test() decodes un-quantized latents, dm3d.py:541)."""
         if quantize:
-            latents, _, _ = self.quantizer.quantize(latents)
+            latents, _, _ = self.quantizer.quantize(latents, q_dtype=L.ACT_DTYPE)   # the decoder's input dtype: no cast pass
         return self.decoder(latents)
 
-    def test(self, test_prefix, context=None, shape=None, out_dir="./generated_images_dm3d"):
+    def test(self, test_prefix, context=None, shape=None, out_dir="./generated_images_dm3d", **gen_kw):
         """reference test(): generate (10,16,16,16,64) latents, decode, save .npy (dm3d.py:534-545).  The literal shape
-        is a default; pass ``shape`` to override (the reference's literals are mutually inconsistent)."""
+        is a default; pass ``shape`` to override (the reference's literals are mutually inconsistent).  Extra keyword
+        arguments (seed=, sampler=, steps=, x_T=, noise=) go to generate()."""
         i = self.timesteps
         print(f"Generating for {i} rsteps")
         if self.vqvae_load_ckpt is not None:
             self.vqvae_trainer.load_weights(self.vqvae_load_ckpt)
         shape = shape or (10, self.latent_size, self.latent_size, self.latent_size, self.lc)
         kw = dict(context_value=context) if self.conditional and context is not None else {}
-        lat = self.generate(shape, last_step=self.timesteps - i, **kw)
+        lat = self.generate(shape, last_step=self.timesteps - i, **{**kw, **gen_kw})
         images = self.decoder(lat)
         os.makedirs(out_dir, exist_ok=True)
         np.save(os.path.join(out_dir, f"{test_prefix}-{i}rsteps.npy"), images.cpu().numpy())

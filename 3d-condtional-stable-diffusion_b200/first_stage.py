@@ -54,9 +54,14 @@ class VectorQuantizer:
     def get_code_indices(self, flattened_inputs, distribution=False):
         """(N, D) -> (N,) int64; lowest index on ties.  ``distribution=True`` (the (N,K) distance matrix) is a
         training-time diagnostic of the reference and is not part of this path."""
-        if distribution:
-            raise NotImplementedError("distribution=True is not on the sampling/decode path")
         st = self._device_state()
+        if distribution:   # the (N, K) squared-distance matrix itself (vqvae3d_monai.py:172-175), same fp32 arithmetic as the argmin
+            x = flattened_inputs.contiguous()
+            d = L.VqDesc()
+            d.n, d.d, d.k, d.x_dtype, d.q_dtype = x.shape[0], x.shape[1], self.num_embeddings, L.dt(x), L.F32
+            dist = torch.empty(x.shape[0], self.num_embeddings, dtype=torch.float32, device=x.device)
+            L.check(L.lib().b200dm_vq_distances(d, L.ptr(x), L.ptr(st["kd"]), L.ptr(st["sq"]), L.ptr(dist), L.stream()))
+            return dist
         idx, _ = ops.vq_argmin_gather(flattened_inputs.contiguous(), st["kd"], st["sq"], want_q=False)
         return idx
 
@@ -115,7 +120,7 @@ class _DecoderBase:
         if self.prog is None or tuple(latents.shape) != tuple(self.z_in.shape):
             self.compile(latents.shape[0], latents.shape[1])
         z = latents.to(self.device)
-        self.z_in.copy_(z if z.dtype == torch.bfloat16 else ops.cast(z.contiguous().float(), torch.bfloat16))
+        self.z_in.copy_(z if z.dtype == L.ACT_DTYPE else ops.cast(z.contiguous().float(), L.ACT_DTYPE))
         self.prog.run()
         return self.out.clone()
 
@@ -153,7 +158,7 @@ class MonaiDecoder(_DecoderBase):
         pr = self.prog = Program(dev)
         s = self.in_size
         self.z_in = pr.buf((batch, s, s, s, self.cin))
-        alpha = lambda n: P[n].to(dev, torch.bfloat16).contiguous()  # noqa: E731
+        alpha = lambda n: P[n].to(dev, L.ACT_DTYPE).contiguous()  # noqa: E731
         x = self._conv(pr, self.z_in, P["stem.kernel"], P["stem.bias"], self.ch[0], prelu_alpha=alpha("stem.prelu.alpha"), note="stem")
         for i, c in enumerate(self.ch):
             for j in range(self.R):
@@ -214,7 +219,7 @@ class MonaiEncoder(_DecoderBase):
         cpad = -(-self.cin // 8) * 8
         self.z_in = pr.buf((batch, S, S, S, cpad))
         self.z_in.zero_()
-        alpha = lambda n: P[n].to(dev, torch.bfloat16).contiguous()  # noqa: E731
+        alpha = lambda n: P[n].to(dev, L.ACT_DTYPE).contiguous()  # noqa: E731
         x = self.z_in
         for i, c in enumerate(self.ch):
             w = P[f"level.{i}.down.kernel"]
@@ -235,10 +240,12 @@ class MonaiEncoder(_DecoderBase):
 
     def __call__(self, volumes):
         """encoder(volumes (B,S,S,S,in) fp32|bf16) -> latents (B,s,s,s,D) fp32."""
+        if getattr(self, "weights_missing", None):
+            raise L.B200dmError(f"encoder: {self.weights_missing} holds no encoder tensors -- encode() would run on random weights")
         if self.prog is None or volumes.shape[0] != self.z_in.shape[0]:
             self.compile(volumes.shape[0], volumes.shape[1])
         v = volumes.to(self.device)
-        self.z_in[..., :self.cin].copy_(v if v.dtype == torch.bfloat16 else ops.cast(v.contiguous().float(), torch.bfloat16))
+        self.z_in[..., :self.cin].copy_(v if v.dtype == L.ACT_DTYPE else ops.cast(v.contiguous().float(), L.ACT_DTYPE))
         self.prog.run()
         return self.out.clone()
 
@@ -365,7 +372,7 @@ class VqganFamilyDecoder(_DecoderBase):
         pr = self.prog = Program(dev)
         s = self.in_size
         self.z_in = pr.buf((batch, s, s, s, self.cin))
-        alpha = lambda n: P[n].to(dev, torch.bfloat16).contiguous()  # noqa: E731
+        alpha = lambda n: P[n].to(dev, L.ACT_DTYPE).contiguous()  # noqa: E731
         g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
 
         def bn_fold(name, kernel, bias, eps, transposed=False):
@@ -468,31 +475,38 @@ class VQVAE:
 
 
 def _load_first_stage(model, path):
-    """.npz of canonical names, or the prefix of a TensorFlow checkpoint of the reference's first-stage trainer
-    (``vqvae_trainer.load_weights(ckpt)``, dm3d.py:408-414).  In the object graph the decoder is a subclassed model that
-    holds ``self.blocks`` (a Sequential, or a list in vqgan_attn_cp), so its variables sit under
-    ``decoder/blocks/layer_with_weights-<n>/...`` in layer order, and the codebook under ``quantizer/embeddings``."""
+    """.npz of canonical names (``encoder.*``, ``decoder.*``, ``quantizer.embeddings``), or the prefix of a TensorFlow
+    checkpoint of the reference's first-stage trainer (``vqvae_trainer.load_weights(ckpt)``, dm3d.py:408-414), which restores
+    encoder, quantizer and decoder.  In the object graph encoder / decoder are subclassed models that hold ``self.blocks`` (a
+    Sequential, or a list in vqgan_attn_cp), so their variables sit under ``<part>/blocks/...`` in layer order, and the codebook
+    under ``quantizer/embeddings``.  A file without encoder tensors still loads (sampling + decode need none), but the
+    encoder then refuses to run instead of encoding with random weights."""
     import os as _os
+    has_enc = hasattr(model.encoder, "set_weights")
     if not str(path).endswith(".npz") and _os.path.exists(str(path) + ".index"):
         from . import tf_checkpoint as T
         variables = T.read_checkpoint(str(path))
-        groups = T.keras_layer_variables(variables, "decoder/blocks")
-        if not groups:   # list-tracked blocks: decoder/blocks/<i>/...
-            import re as _re
-            pat = _re.compile(r"decoder/blocks/(\d+)/(?:layer_with_weights-\d+/)?([A-Za-z_0-9]+)/\.ATTRIBUTES/VARIABLE_VALUE$")
-            g = {}
-            for k, v in variables.items():
-                m = pat.match(k)
-                if m:
-                    g.setdefault(int(m.group(1)), {})[m.group(2)] = v
-            groups = sorted(g.items())
-        model.decoder.set_weights(T.assign_by_creation_order(model.decoder.spec, groups))
+        model.decoder.set_weights(T.assign_by_creation_order(model.decoder.spec, T.block_layer_variables(variables, "decoder/blocks")))
+        if has_enc:
+            enc_groups = T.block_layer_variables(variables, "encoder/blocks")
+            if enc_groups:
+                model.encoder.set_weights(T.assign_by_creation_order(model.encoder.spec, enc_groups))
+                model.encoder.weights_missing = None
+            else:
+                model.encoder.weights_missing = str(path)
         emb = [v for k, v in variables.items() if k.startswith("quantizer/embeddings") and k.endswith("VARIABLE_VALUE")]
         if emb:
             model.quantizer.set_embeddings(emb[0])
         return
     p = Wt.load_npz(path)
     model.decoder.set_weights({k[len("decoder."):]: v for k, v in p.items() if k.startswith("decoder.")})
+    if has_enc:
+        enc = {k[len("encoder."):]: v for k, v in p.items() if k.startswith("encoder.")}
+        if enc:
+            model.encoder.set_weights(enc)
+            model.encoder.weights_missing = None
+        else:
+            model.encoder.weights_missing = str(path)
     model.quantizer.set_embeddings(p["quantizer.embeddings"])
 
 

@@ -67,7 +67,7 @@ def ddpm_update(tables, x_t, eps, t, noise=None, seed=0, sample_id0=0, sampler=0
     n = x_t[0].numel()
     d = make_update_desc(tables, n, B, t, t_prev, sampler, seed, sample_id0, dt(eps))
     out = torch.empty_like(x_t)
-    out_b = torch.empty(x_t.shape, dtype=torch.bfloat16, device=x_t.device) if want_bf16 else None
+    out_b = torch.empty(x_t.shape, dtype=L.ACT_DTYPE, device=x_t.device) if want_bf16 else None
     check(lib().b200dm_ddpm_update(C.byref(d), ptr(x_t), ptr(eps), ptr(noise), ptr(out), ptr(out_b), stream()))
     return (out, out_b) if want_bf16 else out
 
@@ -75,7 +75,7 @@ def ddpm_update(tables, x_t, eps, t, noise=None, seed=0, sample_id0=0, sampler=0
 def philox_normal(shape, seed, sample_id0=0, step=0, stream_id=1, want_bf16=False):
     dev = _dev()
     x = torch.empty(shape, dtype=torch.float32, device=dev)
-    xb = torch.empty(shape, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    xb = torch.empty(shape, dtype=L.ACT_DTYPE, device=dev) if want_bf16 else None
     check(lib().b200dm_philox_normal(ptr(x), ptr(xb), x[0].numel(), shape[0], seed, sample_id0, step, stream_id, stream()))
     return (x, xb) if want_bf16 else x
 
@@ -110,7 +110,7 @@ def norm_act(x0, a, b, act=None, x1=None, kind=0, groups=1, mean_rstd=None, out=
     _dev()
     d = make_norm_desc(x0, x1, kind, groups, act)
     if out is None:
-        out = torch.empty(*x0.shape[:-1], d.c0 + d.c1, dtype=torch.bfloat16, device=x0.device)
+        out = torch.empty(*x0.shape[:-1], d.c0 + d.c1, dtype=L.ACT_DTYPE, device=x0.device)
     check(lib().b200dm_norm_act_fwd(C.byref(d), ptr(x0), ptr(x1), ptr(a), ptr(b), ptr(mean_rstd), ptr(out), stream()))
     return out
 
@@ -133,7 +133,7 @@ def layernorm(x, gammas, betas, eps=1e-3):
 
 def cast(x, dtype):
     _dev()
-    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    y = torch.empty(x.shape, dtype=L.storage(dtype), device=x.device)
     check(lib().b200dm_cast(ptr(x), dt(x), ptr(y), dt(y), x.numel(), stream()))
     return y
 
@@ -156,7 +156,7 @@ def vq_argmin_gather(x, codebook_kd, code_sqnorm=None, want_q=True, q_dtype=torc
     d = L.VqDesc()
     d.n, d.d, d.k, d.x_dtype, d.q_dtype = n, D, codebook_kd.shape[0], dt(x), (L.F32 if q_dtype == torch.float32 else L.BF16)
     idx = torch.empty(n, dtype=torch.int64, device=x.device)
-    q = torch.empty(x.shape, dtype=q_dtype, device=x.device) if want_q else None
+    q = torch.empty(x.shape, dtype=L.storage(q_dtype), device=x.device) if want_q else None
     check(lib().b200dm_vq_argmin_gather(C.byref(d), ptr(x), ptr(codebook_kd), ptr(code_sqnorm), ptr(idx), ptr(q), ptr(hist), stream()))
     return idx, q
 
@@ -174,7 +174,7 @@ def dense_f32(x, w, b=None, act_in=None, act_out=None):
 def softmax_rows(s, scale=1.0):
     _dev()
     cols = s.shape[-1]
-    p = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
+    p = torch.empty(s.shape, dtype=L.ACT_DTYPE, device=s.device)
     check(lib().b200dm_softmax_rows(ptr(s), ptr(p), s.numel() // cols, cols, scale, stream()))
     return p
 
@@ -198,7 +198,7 @@ def pack_conv_weights(desc: L.ConvDesc, keras_kernel: torch.Tensor, transposed=F
     if nbytes == 0:
         raise L.B200dmError("pack_conv_weights: " + lib().b200dm_last_error().decode())
     w = keras_kernel.detach().to("cpu", torch.float32).contiguous()
-    out = torch.empty(nbytes // 2, dtype=torch.bfloat16)
+    out = torch.empty(nbytes // 2, dtype=L.ACT_DTYPE)
     check(lib().b200dm_conv_pack_weights(C.byref(desc), C.c_void_p(w.data_ptr()), int(transposed), C.c_void_p(out.data_ptr())))
     return out
 
@@ -232,7 +232,7 @@ class ConvPlan:
 
     def add_output(self, y_extra, scale, shift, act=None):
         """Extra bf16 output act(scale*v + shift) of the final value (the consumer's folded BatchNorm), same shape as y."""
-        assert y_extra.shape == self.y.shape and y_extra.dtype == torch.bfloat16
+        assert y_extra.shape == self.y.shape and y_extra.dtype == L.ACT_DTYPE
         check(lib().b200dm_conv_plan_add_output(self.h, ptr(y_extra), ptr(scale), ptr(shift), L.ACT[act]))
         self.keep = self.keep + (y_extra, scale, shift)
         return y_extra
@@ -280,7 +280,7 @@ def conv3d(x0, keras_kernel, bias=None, x1=None, mode=L.CONV_DIRECT, stride=1, a
                           chan_bias_rows=B if chan_bias is not None else 0, use_halo=use_halo)
     wp = pack_conv_weights(desc, keras_kernel, transposed).to(dev)
     od, oh, ow = conv_out_shape(mode, (D, H, W), stride)
-    y = torch.empty(B, od, oh, ow, c_out, dtype=y_dtype, device=dev)
+    y = torch.empty(B, od, oh, ow, c_out, dtype=L.storage(y_dtype), device=dev)
     plan = ConvPlan(desc, x0, wp, y, x1=x1, bias=bias, chan_bias=chan_bias, residual=residual, prelu_alpha=prelu_alpha,
                     out_affine=out_affine)
     plan.run()
@@ -293,7 +293,7 @@ def batched_gemm(a, b, y_dtype=torch.float32, residual=None):
     B, M, K = a.shape
     N = b.shape[1]
     desc = make_conv_desc(L.CONV_BATCHED_GEMM, B, (1, 1, M), K, 0, N, 1, 1, None, None, y_dtype)
-    y = torch.empty(B, M, N, dtype=y_dtype, device=dev)
+    y = torch.empty(B, M, N, dtype=L.storage(y_dtype), device=dev)
     plan = ConvPlan(desc, a, b, y, residual=residual)
     plan.run()
     return y
@@ -309,7 +309,7 @@ class AttnPlan:
         B, Lq, D = q.shape
         Lk = k.shape[1]
         assert tuple(k.shape) == (B, Lk, D) and tuple(vt.shape) == (B, D, Lk) and tuple(o.shape) == (B, Lq, D)
-        assert all(t.dtype == torch.bfloat16 for t in (q, k, vt, o)) and vt.is_contiguous() and o.is_contiguous()
+        assert all(t.dtype == L.ACT_DTYPE for t in (q, k, vt, o)) and vt.is_contiguous() and o.is_contiguous()
         for t, L_ in ((q, Lq), (k, Lk)):   # rows of D contiguous elements, uniform row stride, samples L rows apart
             assert t.stride(2) == 1 and t.stride(0) == L_ * t.stride(1), "q / k: unsupported layout"
         self.keep = (q, k, vt, o, residual)

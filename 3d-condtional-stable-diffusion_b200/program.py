@@ -27,7 +27,7 @@ class Program:
 
     # -- allocation helper
     def buf(self, shape, dtype=torch.bfloat16):
-        t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+        t = torch.empty(tuple(shape), dtype=L.storage(dtype), device=self.device)
         self.keep.append(t)
         return t
 
@@ -56,7 +56,7 @@ class Program:
         """act(scale*t + shift) as an extra output of the conv that produces ``t``; None if ``t`` is not a conv output or
         the producer has no free output slot (the caller then runs a norm pass)."""
         plan = self.producers.get(t.data_ptr())
-        if plan is None or t.dtype != torch.bfloat16 or t.shape[-1] % 16 != 0:
+        if plan is None or t.dtype != L.ACT_DTYPE or t.shape[-1] % 16 != 0:
             return None
         y = self.buf(t.shape)
         try:

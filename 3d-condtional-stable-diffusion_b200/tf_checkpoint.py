@@ -214,6 +214,36 @@ def keras_layer_variables(variables, root):
     return sorted(groups.items())
 
 
+def block_layer_variables(variables, root):
+    """Layer groups of a first-stage encoder / decoder under ``<root>`` = ``decoder/blocks`` or ``encoder/blocks``, in block
+    order.  Handles the three ways the reference's blocks are tracked:
+      * a Sequential:  ``<root>/layer_with_weights-<n>/<attr>``
+      * a Python list: ``<root>/<i>/<attr>``  (a plain layer at list index i)
+      * nested models (VQVAEResidualUnit: conv1, conv2[, norm], PReLU as attributes / inner Sequentials):
+        ``<root>/<i>/<sub>/<attr>`` or ``<root>/<i>/<sub>/layer_with_weights-<m>/<attr>`` -- flattened to one group per inner
+        layer, ordered (i, position of <sub> in the unit's construction order, m).
+    Returns [(index tuple, {attr: array})] sorted; every assignment downstream is shape-checked."""
+    root = root.rstrip("/") + "/"
+    sub_order = {"conv1": 0, "conv2": 1, "norm": 2, "bn": 2, "act": 3, "prelu": 3}
+    groups = {}
+    for k, v in variables.items():
+        if not (k.startswith(root) and k.endswith(_SUFFIX)) or ".OPTIMIZER_SLOT" in k:
+            continue
+        parts = k[len(root):-len(_SUFFIX)].split("/")
+        attr, path = parts[-1], parts[:-1]
+        key = []
+        for comp in path:
+            m = re.match(r"layer_with_weights-(\d+)$", comp)
+            if m:
+                key.append(int(m.group(1)))
+            elif comp.isdigit():
+                key.append(int(comp))
+            else:
+                key.append(sub_order.get(comp, 9))
+        groups.setdefault(tuple(key), {})[attr] = v
+    return sorted(groups.items())
+
+
 _ATTR_OF_LEAF = {"kernel": "kernel", "bias": "bias", "gamma": "gamma", "beta": "beta", "mean": "moving_mean", "var": "moving_variance",
                  "alpha": "alpha", "embedding": "embeddings"}
 

@@ -123,6 +123,8 @@ class UNet:
         self.spec = param_spec(cfg)
         self._params = None  # {name: fp32 CPU tensor, Keras layout}; random-initialised lazily
         self.prog = None
+        self.weights_version = 0   # bumped by set_weights: compiled copies held elsewhere (DiffusionModel._step) key on it
+        self._per_sample = None    # lazily compiled variant for a (B,) vector of distinct timesteps
 
     @property
     def params(self):
@@ -135,6 +137,8 @@ class UNet:
         Wt.check_against_spec(params, self.spec)
         self._params = {k: torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).float().cpu() for k, v in params.items()}
         self.prog = None
+        self._per_sample = None
+        self.weights_version += 1
 
     def load_weights(self, path, name_map=None):
         """``path``: a flat .npz of canonical names, or the prefix of a TensorFlow checkpoint written by the reference's
@@ -150,8 +154,11 @@ class UNet:
         return sum(int(np.prod(s)) for _, s, _ in self.spec)
 
     # ---- compilation ------------------------------------------------------------------------
-    def compile(self, batch: int, timesteps: int, device=None, t_dev=None):
-        """Pack weights, precompute the t-only tables, allocate every activation buffer and record the launches."""
+    def compile(self, batch: int, timesteps: int, device=None, t_dev=None, per_sample_t=False):
+        """Pack weights, precompute the t-only tables, allocate every activation buffer and record the launches.
+        ``per_sample_t``: the ResidualBlock time-embedding rows come from per-sample (B, w) buffers (filled by
+        ``_set_timesteps`` from the hoisted tables) instead of one device-side timestep for the whole batch -- the form
+        train_step calls the network in (t ~ U{0..T-1} per sample, conditional_dm3d.py:474,493)."""
         L.require_gpu()
         cfg, P = self.cfg, self.params
         dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -170,7 +177,8 @@ class UNet:
         # pipelined HBM stream at 4.9 TB/s.  Off unless B200DM_SIDE_NORM=1 (kept, tested, for a persistent variant).
         self.side_norm = os.environ.get("B200DM_SIDE_NORM", "0") == "1"
         self.lanes = os.environ.get("B200DM_LANES", "1") != "0"   # branch-parallel CrossAttentionBlock (program lanes)
-        self.t_dev = t_dev if t_dev is not None else torch.zeros(2, dtype=torch.int32, device=dev)
+        self.t_dev = t_dev if t_dev is not None else torch.zeros(4, dtype=torch.int32, device=dev)   # [t, t_prev, seq idx, -]
+        self.per_sample_t, self._temb_rows = bool(per_sample_t), []
         g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
 
         # --- K12: time embedding MLP for every t, then per-ResidualBlock Dense(swish(temb)) tables (T, w)
@@ -188,7 +196,8 @@ class UNet:
             Bx, D, H, Wd, c0 = x0.shape
             c1 = x1.shape[-1] if x1 is not None else 0
             desc = ops.make_conv_desc(mode, Bx, (D, H, Wd), c0, c1, cout, k, stride, act, None, y_dtype,
-                                      chan_bias_rows=1 if chan_bias is not None else 0, transposed_store=transposed_store)
+                                      chan_bias_rows=(batch if self.per_sample_t else 1) if chan_bias is not None else 0,
+                                      transposed_store=transposed_store)
             kern_key = None if kern is None else "override"
             if kern is None:
                 kern = P[f"{kname}.kernel"]
@@ -203,7 +212,8 @@ class UNet:
                 y = pr.buf((Bx, cout, od * oh * ow) if transposed_store else (Bx, od, oh, ow, cout), y_dtype)
             bias_dev = None if not bias else (bias_t.to(dev).contiguous() if bias_t is not None else g(f"{kname}.bias"))
             return pr.conv(desc, x0, wp, y, x1=x1, bias=bias_dev, chan_bias=chan_bias,
-                           t_dev=self.t_dev if chan_bias is not None else None, residual=residual, out_affine=out_affine,
+                           t_dev=self.t_dev if (chan_bias is not None and not self.per_sample_t) else None, residual=residual,
+                           out_affine=out_affine,
                            note=note or kname, side=side)
 
         def bgemm(a, b, y_dtype, residual=None, note=""):
@@ -260,6 +270,10 @@ class UNet:
                 one, zero = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
                 res = pr.norm_act(x, one, zero, pr.buf((*x.shape[:-1], cin)), x1=skip, note=f"{n}.concat")
             table = ops.dense_f32(temb, g(f"{n}.temb.kernel"), g(f"{n}.temb.bias"), act_in="silu")  # (T, w)
+            if self.per_sample_t:   # (B, w) rows gathered from the table per call
+                rows = torch.zeros(x.shape[0], w, dtype=torch.float32, device=dev)
+                self._temb_rows.append((pr.hold(table), rows))
+                table = rows
             if h is None:
                 h, h1 = bn_act(x, f"{n}.norm1", "silu", x1=skip)
             # conv1 + temb -> BN(norm2) -> swish (dm3d.py:237-244): conv1's output has no other reader, so norm2 and the
@@ -470,7 +484,7 @@ class UNet:
         for site in self.ctx_sites:
             n, c, s = site["name"], site["c"], site["s"]
             if "dev" not in site:   # device copies of the site's weights + the two projection plans, built once
-                ctxbuf = torch.empty(B, s, s, s, c, dtype=torch.bfloat16, device=dev)
+                ctxbuf = torch.empty(B, s, s, s, c, dtype=L.ACT_DTYPE, device=dev)
                 plans = []
                 for wname, out, tr in (("key", site["kc"], False), ("value", site["vcT"], True)):
                     desc = ops.make_conv_desc(L.CONV_DIRECT, B, (s, s, s), c, 0, c, 1, 1, transposed_store=tr)
@@ -479,7 +493,7 @@ class UNet:
                 site["dev"] = dict(w=P[f"{n}.ctxmlp.kernel"].to(dev), b=P[f"{n}.ctxmlp.bias"].to(dev), ctx=ctxbuf, plans=plans)
             d = site["dev"]
             ctx = ops.dense_f32(cemb, d["w"], d["b"], act_out="silu")     # ContextMLP (conditional_dm3d.py:310-318)
-            d["ctx"].copy_(ops.cast(ctx, torch.bfloat16).view(B, s, s, s, c))
+            d["ctx"].copy_(ops.cast(ctx, L.ACT_DTYPE).view(B, s, s, s, c))
             for plan in d["plans"]:
                 plan.run()
         torch.cuda.synchronize(dev)
@@ -496,12 +510,27 @@ class UNet:
         x, t = inputs[0], inputs[1]
         if self.prog is None or self.batch != x.shape[0]:
             raise L.B200dmError("UNet: call compile(batch, timesteps) first (batch must match)")
-        tv = int(torch.as_tensor(t).reshape(-1)[0])
-        if not bool((torch.as_tensor(t).reshape(-1) == tv).all()):
-            raise L.B200dmError("UNet: the sampling path uses one timestep per batch, as generate() does")
+        tvec = torch.as_tensor(t).reshape(-1).to(torch.int64).cpu()
+        if tvec.numel() == 1:
+            tvec = tvec.expand(x.shape[0])
+        if tvec.numel() != x.shape[0] or int(tvec.min()) < 0 or int(tvec.max()) >= self.timesteps:
+            raise L.B200dmError(f"UNet: t must hold {x.shape[0]} timesteps in [0, {self.timesteps})")
+        tv = int(tvec[0])
+        if not bool((tvec == tv).all()) and not self.per_sample_t:
+            # distinct timesteps per sample (train_step's call, conditional_dm3d.py:493): a second compiled program whose conv
+            # epilogues read per-sample (B, w) time-embedding rows; same packed weights, own activation buffers
+            if self._per_sample is None:
+                import copy
+                self._per_sample = copy.copy(self).compile(self.batch, self.timesteps, self.device, per_sample_t=True)
+            return self._per_sample(inputs)
         if len(inputs) > 2 and self.cfg.conditional:
             self.set_context(torch.as_tensor(inputs[2]).reshape(-1))
-        self.t_dev.copy_(torch.tensor([tv, tv - 1], dtype=torch.int32))
+        if self.per_sample_t:
+            tidx = tvec.to(torch.int32).to(self.device)
+            for table, rows in self._temb_rows:
+                L.check(L.lib().b200dm_gather_rows_f32(L.ptr(table), table.shape[0], L.ptr(tidx), L.ptr(rows), rows.shape[0],
+                                                      rows.shape[1], L.stream()))
+        self.t_dev.copy_(torch.tensor([tv, tv - 1, 0, 0], dtype=torch.int32))
         x = x.to(self.device)
-        self.x_in.copy_(x if x.dtype == torch.bfloat16 else ops.cast(x.contiguous().float(), torch.bfloat16))
+        self.x_in.copy_(x if x.dtype == L.ACT_DTYPE else ops.cast(x.contiguous().float(), L.ACT_DTYPE))
         return self.forward_inplace().clone()

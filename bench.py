@@ -114,10 +114,11 @@ def barrier(world):
 
 
 # ----------------------------------------------------------------------------------------------- CPU (reference) arm
-def oracle_cpu_rate(steps, warmup, budget_s=90.0):
+def oracle_cpu_rate(steps, warmup, budget_s=90.0, batch=None):
     """The reference's algorithm for this path on the host CPU (oracle port: PyTorch-CPU fp32 restatement of
     conditional_dm3d.build_model + DiffusionModel.sample; TensorFlow is not installable here).  Bounded sample:
-    ONE volume (B=1) of the cfg-2 workload per step, all host threads."""
+    a few DDPM steps of the cfg-2 workload at ``batch`` volumes per step (default: the workload's own 8), all host threads."""
+    Bc = batch or CFG["B"]
     from oracle.unet import UNet as OUNet
     from oracle import init as OI, sampler as OS
     from oracle.schedule import Betas
@@ -126,14 +127,14 @@ def oracle_cpu_rate(steps, warmup, budget_s=90.0):
     ou = OUNet(S, C, [64, 128, 256], [False, False, True, True], first_conv_channels=32, conditional=True)
     P = OI.make_params(ou.spec(), 0, "keras")
     b = Betas(CFG["T"])
-    x = OI.normal((1, S, S, S, C), 1)
-    ctx = torch.tensor([1])
-    z = OI.normal((1, S, S, S, C), 2)
+    x = OI.normal((Bc, S, S, S, C), 1)
+    ctx = torch.arange(Bc) % 2
+    z = OI.normal((Bc, S, S, S, C), 2)
 
     def one(t):
         nonlocal x
         with torch.no_grad():
-            eps = ou.forward(P, x, torch.tensor([t]), ctx=ctx)
+            eps = ou.forward(P, x, torch.full((Bc,), t), ctx=ctx)
             x = OS.ddpm_step(b, x, eps, t, z)
 
     t0 = time.perf_counter()
@@ -147,8 +148,8 @@ def oracle_cpu_rate(steps, warmup, budget_s=90.0):
     for i in range(n):
         one(CFG["T"] - 2 - w - i)
     dt = time.perf_counter() - t0
-    return dict(rate=n / dt, steps=n, warmup=w + 1, ms_per_step=1e3 * dt / n, cores=torch.get_num_threads(),
-                sample=f"1 volume (of the 8-volume batch) x {n} DDPM steps of cfg-2 (32^3x256 latent, conditional U-Net), PyTorch-CPU fp32 oracle port")
+    return dict(rate=Bc * n / dt, steps=n, warmup=w + 1, ms_per_step=1e3 * dt / n, cores=torch.get_num_threads(), batch=Bc,
+                sample=f"{Bc} volumes x {n} DDPM steps of cfg-2 (32^3x256 latent, conditional U-Net, per-sample class ids), PyTorch-CPU fp32 oracle port")
 
 
 def run_reference(args):
@@ -159,7 +160,7 @@ def run_reference(args):
     r = oracle_cpu_rate(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
             "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(1, per_step_volumes=1),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(1, per_step_volumes=r["batch"]),
             "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -177,6 +178,29 @@ def workload_config(n_gpus, per_step_volumes=None):
 
 
 # ----------------------------------------------------------------------------------------------- CUDA arm
+def ncu_traffic():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel family from the committed
+    ncu --set full capture of this same command (profiles/r2_traffic.json, written by tools/ncu_traffic.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            return json.load(f)
+    except OSError:
+        return None
+
+
+def event_time(fn, iters, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def run_ours(args):
     world, rank, local = dist_setup(args.gpus)
     if not torch.cuda.is_available():
@@ -189,7 +213,10 @@ def run_ours(args):
     S, C, B, T = CFG["S"], CFG["C_lat"], CFG["B"], CFG["T"]
     K, W = args.steps, max(args.warmup, 3)
     a = types.SimpleNamespace(timesteps=T, num_gpus=world, kernel_resize=False, bs=B * world)
-    dm = b200dm.ConditionalDiffusionModel(S, 1024, C, None, a)
+    # first stage of the sampling + decode job (north_star; BASELINE configs[2]): vqgan_attn_cp quantizer (K=1024, D=256) + Decoder
+    # (32,64,128): 32^3 x 256 latents -> 128^3 x 1 volumes
+    fs = b200dm.VQGAN(num_channels=(32, 64, 128), num_embeddings=1024, embedding_dim=C)
+    dm = b200dm.ConditionalDiffusionModel(S, 1024, C, None, a, first_stage=fs)
     shape = (B, S, S, S, C)
     sid0 = rank * B
     ctx = (torch.arange(B) + sid0) % 2
@@ -201,11 +228,12 @@ def run_ours(args):
     graph, nets = st["graph"], st["nets"]
     launches_per_step = sum(net.prog.num_launches + 1 for net in nets) + 1   # per chain: U-Net program + update; + t advance
 
-    def reset(t0):
-        st["t_dev"].copy_(torch.tensor([t0, t0 - 1], dtype=torch.int32))
+    def reset(t0=T - 1):   # restart the device-side timestep walker on the DDPM sequence T-1, T-2, ...
+        st["t_seq"].copy_(torch.tensor(list(range(T - 1, -1, -1)) + [-1, -1], dtype=torch.int32))
+        st["t_dev"].copy_(torch.tensor([t0, t0 - 1, T - 1 - t0, 0], dtype=torch.int32))
 
     # ---- device-resident timing: K graph replays between CUDA events on the launching stream
-    reset(T - 1)
+    reset()
     for _ in range(W):
         graph.replay()
     clocks = ClockSampler(local)
@@ -240,14 +268,71 @@ def run_ours(args):
     e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes / K, "d2h_bytes_per_step": nbytes / K,
            "call": "ConditionalDiffusionModel.generate(shape, last_step=T-K, x_T=<pinned host>, context=ids) -> host latents"}
 
+    # ---- the sampling + decode job (north_star's scaling target), through the public API with host buffers:
+    #      generate(K steps) -> quantize -> vqgan_attn_cp decoder -> host volumes
+    vol_host = torch.empty(B, 128, 128, 128, 1, dtype=torch.float32).pin_memory()
+
+    def sample_decode(last_step):
+        lat_ = dm.generate(shape, last_step=last_step, x_T=x_host, seed=1234, sample_id0=sid0, context=ctx)
+        vol_host.copy_(dm.decode(lat_, quantize=True), non_blocking=True)
+        torch.cuda.synchronize()
+
+    sample_decode(T - 2)   # compiles the decoder program
+    assert torch.isfinite(vol_host).all() and L.debug_flag() == 0
+    barrier(world)
+    t0 = time.perf_counter()
+    sample_decode(T - K)
+    sd_s = max_over_ranks(time.perf_counter() - t0, world, dev)
+    barrier(world)
+    e2e_sd = {"value": world * B * K / sd_s, "unit": UNIT, "volumes_per_s": world * B / sd_s, "seconds": sd_s, "steps": K,
+              "h2d_bytes": nbytes, "d2h_bytes": vol_host.numel() * 4,
+              "call": "generate(last_step=T-K, x_T=<pinned host>) -> decode(latents, quantize=True) [VQ K=1024 + vqgan_attn_cp decoder 32^3->128^3] -> host volumes"}
+
+    # ---- sustained: the FULL 1000-step chain (device-resident replay, ~3 s) with its own clock record, and the whole
+    #      1000-step sampling + decode job through the public API
+    sustained = None
+    if not args.no_sustained:
+        reset()
+        c2 = ClockSampler(local)
+        c2.start()
+        time.sleep(0.2)
+        barrier(world)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(T):
+            graph.replay()
+        s1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        s_ms = max_over_ranks(s0.elapsed_time(s1), world, dev)
+        c2r = c2.stop()
+        barrier(world)
+        t0 = time.perf_counter()
+        sample_decode(0)
+        job_s = max_over_ranks(time.perf_counter() - t0, world, dev)
+        barrier(world)
+        sustained = {"steps": T, "ms_per_step": s_ms / T, "value": world * B * T / (s_ms * 1e-3), "unit": UNIT, "clocks": c2r,
+                     "job_1000_steps_plus_decode": {"seconds": job_s, "volumes_per_s": world * B / job_s,
+                                                    "volume_steps_per_s": world * B * T / job_s, "volumes": world * B,
+                                                    "call": "generate(shape, x_T=<pinned host>) [T=1000] -> decode(quantize=True) -> host volumes"}}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(world), chains=st["chains"]), "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * K}
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": L.precision(), "data": "synthetic",
+            "config": dict(workload_config(world), chains=st["chains"], storage=L.precision()), "clocks": clk, "e2e": e2e,
+            "e2e_sample_decode": e2e_sd, "gpu_launches": launches_per_step * K}
+    if sustained:
+        line["sustained"] = sustained
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (conv_igemm): per-launch CUDA events over one more step
+        # ---- roofline of the dominant kernel family: per-launch CUDA events over one more step
         pk = peaks()
-        reset(T - 1)
+        # burst conditions (SM clock at its maximum, no power cap) -> the burst cuBLAS figure is the honest denominator; the
+        # sustained one (taken at ~1290 MHz under the power cap) only when the sampler saw the clock drop
+        at_max = clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] >= 0.97 * clk["sm_max_mhz"]
+        tf_peak, tf_src = (pk["tf"], "bf16_tflops (burst: SM clock at max during the timed region)") if at_max else \
+            (pk["tf_sustained"], "bf16_tflops_sustained (SM clock below max during the timed region)")
+        reset()
         rows = []
         for net in nets:          # every chain's program, one launch at a time with an event pair around each
             net.prog.run_timed()
@@ -259,62 +344,57 @@ def run_ours(args):
             ms_, work = sum(r[3] for r in sel), sum(r[2] for r in sel)
             return sel, ms_, work
 
-        # dominant kernel of the step: the persistent halo-reuse 3^3 conv (conv_halo_kernel)
         sel, h_ms, h_fl = agg(("conv_halo",))
         ach = h_fl / (h_ms * 1e-3) / 1e12
-        line["roofline"] = {"kernel": "conv_halo_kernel (persistent tcgen05 implicit-GEMM 3^3 Conv3D, TMA halo slabs): all its launches of one step",
-                            "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                            "peak_source": f"{pk['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
-                            "traffic": None, "launches": len(sel), "avg_launch_ms": h_ms / max(1, len(sel)),
+        tr = ncu_traffic()
+        line["roofline"] = {"kernel": "conv_halo_kernel / conv_halo_up_kernel (persistent tcgen05 implicit-GEMM 3^3 Conv3D, TMA halo slabs): all launches of one step",
+                            "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                            "peak_source": f"{pk['src']} MEASURED_PEAKS.json {tf_src}", "frac_of_sustained_peak": ach / pk["tf_sustained"],
+                            "frac_of_burst_peak": ach / pk["tf"],
+                            "traffic": (tr or {}).get("halo_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                            "algorithmic_bytes_per_launch": (tr or {}).get("halo_algorithmic_bytes_per_launch"),
+                            "launches": len(sel), "avg_launch_ms": h_ms / max(1, len(sel)),
                             "algorithmic_gflop_per_launch_avg": h_fl / 1e9 / max(1, len(sel)), "share_of_step": h_ms / tot_ms,
                             "timing": "CUDA events around every launch on the launching stream (b200dm_program_run_timed)"}
-        try:   # ncu dram__bytes_(read+write) of representative launches (one --set full capture each; profiles/)
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1d_traffic.json")) as f:
-                line["roofline"]["traffic_samples"] = json.load(f)["samples"]
-            line["roofline"]["traffic_note"] = "traffic is null for the 36-launch aggregate; per-launch ncu samples are listed in traffic_samples"
-        except OSError:
-            pass
         sel, t_ms, t_fl = agg(("conv_halo", "conv", "attn"))
-        line["roofline_all_tensor_kernels"] = {"kernels": "conv_halo_kernel + conv_igemm_kernel (1^3 / strided / parity convs, GEMMs) + flash_attn_kernel",
-                                               "bound": "tensor", "achieved": t_fl / (t_ms * 1e-3) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                                               "frac": t_fl / (t_ms * 1e-3) / 1e12 / pk["tf_sustained"], "launches": len(sel),
+        line["roofline_all_tensor_kernels"] = {"kernels": "conv_halo(_up)_kernel + conv_igemm_kernel (1^3 / strided / parity convs, GEMMs) + flash_attn_kernel",
+                                               "bound": "tensor", "achieved": t_fl / (t_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                                               "frac": t_fl / (t_ms * 1e-3) / 1e12 / tf_peak, "launches": len(sel),
                                                "algorithmic_gflop_per_step": t_fl / 1e9, "share_of_step": t_ms / tot_ms}
+        line["roofline_step"] = {"bound": "tensor", "achieved": t_fl / (ms / K * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                                 "frac": t_fl / (ms / K * 1e-3) / 1e12 / tf_peak,
+                                 "note": "all algorithmic conv/attention FLOPs of one step / the graph-replayed step time (everything included)"}
         sel, e_ms, e_by = agg(("norm_act", "layernorm", "gn_stats", "softmax"))
         if sel:
             line["roofline_hbm_kernels"] = {"kernels": "norm_act / layernorm (fused elementwise passes left in the step)", "bound": "hbm",
                                             "achieved": e_by / (e_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                             "frac": e_by / (e_ms * 1e-3) / 1e9 / pk["hbm"], "launches": len(sel), "share_of_step": e_ms / tot_ms}
-        # the two HBM-bound kernels that move the bytes: the fused posterior update (largest pass of the step) and the largest
-        # BN+swish(+concat) pass -- each timed alone with CUDA events on its stream (tiny launches dominate the aggregate above)
+        # the fused posterior update, timed alone with CUDA events on its stream, against SURVEY 8(d)'s algorithmic bytes
         net0 = nets[0]
         xs = st["x"][:st["chain_batch"]]
-        reset(T - 1)
+        reset()
+        upd_eps = st.get("update_eps", net0.eps)
 
         def upd():
-            L.check(L.lib().b200dm_ddpm_update(ctypes.byref(st["descs"][0]), L.ptr(xs), L.ptr(net0.eps), None, L.ptr(xs), L.ptr(net0.x_in), L.stream()))
+            L.check(L.lib().b200dm_ddpm_update(ctypes.byref(st["descs"][0]), L.ptr(xs), L.ptr(upd_eps), None, L.ptr(xs), L.ptr(net0.x_in), L.stream()))
 
-        for _ in range(3):
-            upd()
-        torch.cuda.synchronize()
-        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        u0.record()
-        for _ in range(10):
-            upd()
-        u1.record()
-        torch.cuda.synchronize()
-        u_ms = u0.elapsed_time(u1) / 10
-        u_bytes = xs.numel() * (4.0 + 4.0 + 4.0 + 2.0)
-        line["roofline_update_kernel"] = {"kernel": "update_kernel (fused DDPM posterior + Philox noise): x_t fp32 + eps fp32 -> x_{t-1} fp32 + bf16 copy",
-                                          "bound": "hbm", "achieved": u_bytes / (u_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                          "frac": u_bytes / (u_ms * 1e-3) / 1e9 / pk["hbm"], "algorithmic_bytes_per_launch": u_bytes,
-                                          "avg_launch_ms": u_ms, "working_set": "940 MB per launch (> 126 MB L2)"}
+        u_ms = event_time(upd, 10, 3)
+        u_alg = xs.numel() * (4.0 + 2.0 + 4.0 + 2.0)          # x_t fp32 + eps 16-bit + x_{t-1} fp32 + 16-bit copy
+        u_moved = xs.numel() * (4.0 + upd_eps.element_size() + 4.0 + 2.0)
+        line["roofline_update_kernel"] = {"kernel": "update_kernel (fused DDPM posterior + in-register Philox noise)",
+                                          "bound": "hbm", "achieved": u_alg / (u_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                          "frac": u_alg / (u_ms * 1e-3) / 1e9 / pk["hbm"], "algorithmic_bytes_per_launch": u_alg,
+                                          "bytes_moved_per_launch": u_moved, "moved_gbps": u_moved / (u_ms * 1e-3) / 1e9,
+                                          "avg_launch_ms": u_ms, "working_set": "> 126 MB L2"}
         big = max((r for r in rows if r[0] == "norm_act"), key=lambda r: r[2], default=None)
         if big is not None:
             line["roofline_largest_norm_pass"] = {"kernel": f"norm_act_kernel ({big[1]})", "bound": "hbm", "achieved": big[2] / (big[3] * 1e-3) / 1e9,
                                                   "peak": pk["hbm"], "unit": "GB/s", "frac": big[2] / (big[3] * 1e-3) / 1e9 / pk["hbm"],
                                                   "algorithmic_bytes_per_launch": big[2], "avg_launch_ms": big[3]}
+        if not args.no_cfg3:
+            line["cfg3"] = cfg3_line(b200dm, L, dev, pk, tf_peak)
         if world == 1 and not args.no_cpu:
-            r = oracle_cpu_rate(3, 1, budget_s=25.0)
+            r = oracle_cpu_rate(3, 1, budget_s=25.0)   # 8 volumes per step, like the GPU arm
             line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         if args.dump_ops:
             with open(args.dump_ops, "w") as f:
@@ -324,6 +404,41 @@ def run_ours(args):
     barrier(world)
 
 
+def cfg3_line(b200dm, L, dev, pk, tf_peak):
+    """BASELINE configs[2]: VQ quantize (K=1024, D=256) + vqgan_attn_cp Decoder (32,64,128), 32^3 latents -> 128^3 volumes, batch 16,
+    device-resident (CUDA events), with per-kernel rooflines from per-launch events."""
+    Bd, s, D, Kc = 16, 32, 256, 1024
+    vq = b200dm.VQGAN(num_channels=(32, 64, 128), num_embeddings=Kc, embedding_dim=D)
+    z = torch.randn(Bd, s, s, s, D, device=dev) * 0.05
+    q, idx, perp = vq.quantizer.quantize(z)
+    vol = vq.decoder(q)
+    assert torch.isfinite(vol).all() and L.debug_flag() == 0 and tuple(vol.shape) == (Bd, 128, 128, 128, 1)
+    ms_q = event_time(lambda: vq.quantizer.quantize(z), 3, 1)
+    ms_d = event_time(lambda: vq.decoder.prog.run(), 5, 2)
+    vq.decoder.prog.run_timed()
+    rows = vq.decoder.prog.run_timed()
+    N = Bd * s ** 3
+    out = {"workload": "cfg-3: VQ quantize (K=1024, D=256) + vqgan_attn_cp Decoder (32,64,128): 32^3x256 -> 128^3x1, batch 16",
+           "quantize_ms": ms_q, "decode_ms": ms_d, "volumes_per_s": Bd / ((ms_q + ms_d) * 1e-3), "decode_volumes_per_s": Bd / (ms_d * 1e-3),
+           "vq_rows_per_s": N / (ms_q * 1e-3)}
+    vq_fl, vq_by = 2.0 * N * Kc * D, N * D * 4.0 * 2 + N * 8.0 + Kc * D * 4.0
+    out["roofline_vq"] = {"kernel": "vq argmin + gather", "bound": "tensor", "achieved": vq_fl / (ms_q * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                          "frac": vq_fl / (ms_q * 1e-3) / 1e12 / tf_peak, "hbm_gbps": vq_by / (ms_q * 1e-3) / 1e9, "hbm_frac": vq_by / (ms_q * 1e-3) / 1e9 / pk["hbm"],
+                          "note": "2*N*K*D FLOP vs the dense bf16 tensor peak and N*D*4*2 + N*8 + K*D*4 bytes vs HBM (SURVEY 8d: compute-bound at K=1024)"}
+    tens = [r for r in rows if r[0] in ("conv", "conv_halo")]
+    t_ms, t_fl = sum(r[3] for r in tens), sum(r[2] for r in tens)
+    out["roofline_decoder_convs"] = {"bound": "tensor", "achieved": t_fl / (t_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                                     "frac": t_fl / (t_ms * 1e-3) / 1e12 / tf_peak, "launches": len(tens), "ms": t_ms, "algorithmic_gflop": t_fl / 1e9}
+    hb = [r for r in rows if r[0] in ("norm_act", "gn_stats", "stencil")]
+    if hb:
+        h_ms, h_by = sum(r[3] for r in hb), sum(r[2] for r in hb)
+        out["roofline_decoder_hbm_passes"] = {"bound": "hbm", "achieved": h_by / (h_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                              "frac": h_by / (h_ms * 1e-3) / 1e9 / pk["hbm"], "launches": len(hb), "ms": h_ms}
+    out["decoder_whole"] = {"algorithmic_gflop": t_fl / 1e9, "achieved_tflops": t_fl / (ms_d * 1e-3) / 1e12, "frac": t_fl / (ms_d * 1e-3) / 1e12 / tf_peak}
+    out["top_ops"] = [{"kind": r[0], "op": r[1], "ms": round(r[3], 4)} for r in sorted(rows, key=lambda r: -r[3])[:8]]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +446,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the 1000-step sustained legs (tuning runs)")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg-3 (quantize + decode) leg (tuning runs)")
     ap.add_argument("--batch", type=int, default=None, help="tuning aid: per-GPU batch other than the cfg-2 value (8); not a bench line")
     ap.add_argument("--dump-ops", default=None, help="write per-op (kind,name,work,ms) CSV of one step")
     args = ap.parse_args()

@@ -34,7 +34,7 @@ extern "C" {
 #define B200DM_ERR_KERNEL_TIMEOUT (-4)
 
 #define B200DM_F32 0
-#define B200DM_BF16 1
+#define B200DM_BF16 1   /* "the library's 16-bit storage type": bf16 in libb200dm.so, IEEE fp16 in libb200dm_f16.so */
 
 #define B200DM_ACT_NONE 0
 #define B200DM_ACT_SILU 1
@@ -42,6 +42,10 @@ extern "C" {
 
 int b200dm_version(void);
 const char* b200dm_last_error(void);
+/* "bf16" or "fp16": the 16-bit type this build stores activations and packed weights in (every B200DM_BF16 buffer).
+ * The same sources are compiled twice; the reference computes in fp32 (conditional_dm3d.py has no mixed-precision
+ * policy), so the fp16 build is the closer one (8x smaller storage rounding) and the bf16 build the range-safe one. */
+const char* b200dm_storage_dtype(void);
 /* number of SMs / compute capability of the current device (major*10+minor); <0 on error */
 int b200dm_device_info(int* sm_count, int* cc);
 
@@ -83,6 +87,14 @@ int b200dm_philox_normal(float* x, void* x_bf16_or_null, int64_t n_per_sample, i
                          void* stream);
 /* t_dev[0] += delta (and t_dev[1] += delta): lets a captured CUDA graph walk the schedule. */
 int b200dm_step_advance(int32_t* t_dev, int32_t delta, void* stream);
+/* t_dev = {t, t_prev, idx, -}: idx += 1; t = seq[idx]; t_prev = seq[idx + 1] (seq is a device array terminated by two -1
+ * entries).  One captured step graph then replays any timestep sequence: range(T-1, last_step-1, -1) of generate()
+ * (dm3d.py:516), a strided / non-uniform DDIM schedule, ... with no host work between steps. */
+int b200dm_step_advance_seq(int32_t* t_dev, const int32_t* seq, void* stream);
+/* out[r][:] = table[idx[r]][:], fp32: the per-sample rows of the hoisted time-embedding tables when network([x, t]) is called
+ * with distinct t per sample (train_step, conditional_dm3d.py:474,493) */
+int b200dm_gather_rows_f32(const float* table, int32_t table_rows, const int32_t* idx, float* out, int32_t rows, int32_t cols,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K6/K7  fused normalisation + activation (+ channel concat, + per-voxel PReLU) in one HBM pass.
@@ -161,6 +173,10 @@ int b200dm_vq_argmin_gather(const b200dm_vq_desc* d, const void* x, const float*
                             const float* code_sqnorm /* fp32[K] from b200dm_vq_prepare */,
                             int64_t* idx, void* q_or_null, int32_t* hist_or_null, void* stream);
 int b200dm_vq_prepare(const float* codebook_kd, int32_t k, int32_t d, float* code_sqnorm, void* stream);
+/* get_code_indices(flat, distribution=True) (vqvae3d_monai.py:165-177): the (N,K) fp32 matrix of squared distances, same
+ * arithmetic as the argmin kernel (row-wise argmin of it == idx). */
+int b200dm_vq_distances(const b200dm_vq_desc* d, const void* x, const float* codebook_kd, const float* code_sqnorm,
+                        float* dist, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K12  small fp32 dense: Y = act(X W + b), X (M,K), W (K,N) Keras layout.  Replaces the Dense layers on the

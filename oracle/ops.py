@@ -17,18 +17,19 @@ class Emu:
     ``Emu(True)`` rounds to bf16 at the CUDA path's bf16 storage points (activations
     written to HBM, weights fed to the tensor cores)."""
 
-    def __init__(self, bf16: bool = False, trace: dict | None = None):
+    def __init__(self, bf16: bool = False, trace: dict | None = None, dtype: torch.dtype = torch.bfloat16):
         self.bf16 = bf16
         self.trace = trace  # optional {tag: tensor} of every tagged storage point (layer-by-layer debugging)
+        self.dtype = dtype  # the CUDA build's 16-bit storage type: torch.bfloat16 (libb200dm.so) or torch.float16 (libb200dm_f16.so)
 
     def a(self, x: torch.Tensor, tag: str | None = None) -> torch.Tensor:  # activation storage point
-        y = x.to(torch.bfloat16).to(x.dtype) if self.bf16 else x
+        y = x.to(self.dtype).to(x.dtype) if self.bf16 else x
         if self.trace is not None and tag is not None:
             self.trace[tag] = y
         return y
 
     def w(self, x: torch.Tensor) -> torch.Tensor:  # tensor-core weight operand
-        return x.to(torch.bfloat16).to(x.dtype) if self.bf16 else x
+        return x.to(self.dtype).to(x.dtype) if self.bf16 else x
 
 
 EXACT = Emu(False)

@@ -133,3 +133,20 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_fp16_storage_build_exports_the_same_abi(L):
+    """libb200dm_f16.so (same sources, -DB200DM_ACT_FP16): same symbols, reports its storage type; the selection is per process."""
+    path = L._LIBS["fp16"]
+    assert os.path.exists(path), "build.py builds both storage variants"
+    lib16 = C.CDLL(path)
+    for n in header_functions():
+        assert hasattr(lib16, n), n
+    lib16.b200dm_storage_dtype.restype = C.c_char_p
+    assert lib16.b200dm_storage_dtype() == b"fp16"
+    assert L.lib().b200dm_storage_dtype() == L.precision().encode()
+    code = ("import os,sys; os.environ['B200DM_PRECISION']='fp16'; sys.path.insert(0, %r); import torch, b200dm; from b200dm import _lib as L; "
+            "assert L.precision()=='fp16' and L.ACT_DTYPE is torch.float16 and L.lib().b200dm_storage_dtype()==b'fp16'; "
+            "import pytest\ntry:\n    L.set_precision('bf16'); raise SystemExit(3)\nexcept L.B200dmError:\n    pass") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -120,3 +120,70 @@ def test_first_stage_weights_from_checkpoint(tmp_path):
     for k, a in want.items():
         assert np.array_equal(vq.decoder.params[k].numpy(), a), k
     assert np.array_equal(np.asarray(vq.quantizer.embeddings), cb)
+
+
+def test_first_stage_nested_object_graph_keys_and_encoder(tmp_path):
+    """The monai first stage as the reference's object graph tracks it (vqvae3d_monai.py:218-234, 253-306, 342-391):
+    ``blocks`` is a Sequential; a VQVAEResidualUnit is a nested Model whose ``conv1`` is a layer attribute and whose ``conv2`` is
+    an inner Sequential (Conv3D, BatchNormalization, PReLU) -> keys ``.../layer_with_weights-N/conv2/layer_with_weights-M/...``.
+    vqvae_trainer.load_weights restores encoder, quantizer AND decoder: both are filled here, and a checkpoint
+    without encoder tensors makes encode() refuse instead of running on random weights."""
+    vq = b200dm.VQVAE(1, 1, (32, 64), 1, (32, 64), num_embeddings=16, embedding_dim=8, latent_size=4)
+    rng = np.random.default_rng(2)
+    vars_, want = {}, {"decoder": {}, "encoder": {}}
+    for part, spec in (("decoder", vq.decoder.spec), ("encoder", vq.encoder.spec)):
+        n = -1          # Sequential index of the current weighted block
+        last_unit = None
+        for name, shape, _ in spec:
+            a = rng.standard_normal(shape).astype(np.float32)
+            want[part][name] = a
+            stem, leaf = name.rsplit(".", 1)
+            attr = T._ATTR_OF_LEAF.get(leaf, leaf)
+            if ".res." in stem:
+                unit, sub = stem.rsplit(".", 1)          # level.i.res.j , conv1|conv2|norm|prelu
+                if unit != last_unit:
+                    n += 1
+                    last_unit = unit
+                inner = {"conv1": "conv1", "conv2": "conv2/layer_with_weights-0", "norm": "conv2/layer_with_weights-1",
+                         "prelu": "conv2/layer_with_weights-2"}[sub]
+                key = f"{part}/blocks/layer_with_weights-{n}/{inner}/{attr}"
+            else:
+                if leaf in ("kernel", "alpha") or last_unit is not None:
+                    if leaf != "bias":
+                        n += 1
+                    last_unit = None
+                key = f"{part}/blocks/layer_with_weights-{n}/{attr}"
+            vars_[key + "/.ATTRIBUTES/VARIABLE_VALUE"] = a
+    cb = rng.standard_normal((8, 16)).astype(np.float32)
+    vars_["quantizer/embeddings/.ATTRIBUTES/VARIABLE_VALUE"] = cb
+    prefix = str(tmp_path / "vqvae-nested")
+    T.write_checkpoint(prefix, vars_, checksum_limit=1 << 14)
+    vq.load_weights(prefix)
+    for part, obj in (("decoder", vq.decoder), ("encoder", vq.encoder)):
+        for k, a in want[part].items():
+            assert np.array_equal(obj.params[k].numpy(), a), (part, k)
+    assert vq.encoder.weights_missing is None
+    # decoder-only checkpoint: loads, but the encoder refuses to run
+    dec_only = {k: v for k, v in vars_.items() if not k.startswith("encoder/")}
+    prefix2 = str(tmp_path / "vqvae-deconly")
+    T.write_checkpoint(prefix2, dec_only, checksum_limit=1 << 14)
+    vq2 = b200dm.VQVAE(1, 1, (32, 64), 1, (32, 64), num_embeddings=16, embedding_dim=8, latent_size=4)
+    vq2.load_weights(prefix2)
+    assert vq2.encoder.weights_missing == prefix2
+    import torch
+    with pytest.raises(b200dm._lib.B200dmError):
+        vq2.encoder(torch.zeros(1, 16, 16, 16, 1))
+
+
+def test_first_stage_npz_roundtrip_includes_encoder(tmp_path):
+    vq = b200dm.VQVAE(1, 1, (32, 64), 1, (32, 64), num_embeddings=16, embedding_dim=8, latent_size=4)
+    rng = np.random.default_rng(3)
+    flat = {f"decoder.{n}": rng.standard_normal(s).astype(np.float32) for n, s, _ in vq.decoder.spec}
+    flat.update({f"encoder.{n}": rng.standard_normal(s).astype(np.float32) for n, s, _ in vq.encoder.spec})
+    flat["quantizer.embeddings"] = rng.standard_normal((8, 16)).astype(np.float32)
+    path = str(tmp_path / "fs.npz")
+    np.savez(path, **flat)
+    vq.load_weights(path)
+    for n, _, _ in vq.encoder.spec:
+        assert np.array_equal(vq.encoder.params[n].numpy(), flat[f"encoder.{n}"]), n
+    assert vq.encoder.weights_missing is None
