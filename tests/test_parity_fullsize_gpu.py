@@ -227,27 +227,54 @@ def test_cfg3_monai_decoder_fullsize(cuda):
 def test_cfg4_level0_attention_unet_and_ddim_chain(cuda):
     """dm3d.build_model(16, 16, [64,128,256], has_attention=[True, False, True]): AttentionBlocks at the finest level
     (L = 16^3 = 4096 tokens, d = 64) -- forward vs the oracle (residual on the NORMALISED input, dm3d.py:63), then a 25-step
-    DDIM chain (eta = 0, strided schedule) through generate(sampler='ddim') on the captured-graph path."""
+    DDIM chain (eta = 0, strided schedule) through generate(sampler='ddim') on the captured-graph path.
+
+    Conditioning.  With the plain stress weights the level-0 logits have a standard deviation of ~25 (the activations of the
+    up path are large), the 4096-token softmax is one-hot and the network is discontinuous in its 16-bit roundings: the fp32
+    oracle and the oracle that merely ROUNDS where the CUDA path stores 16-bit values differ by 0.44 rel-L2 (0.15 with fp16)
+    although every block agrees with a CPU evaluation of its own inputs to 1.7e-3 (tools/layer_trace.py 16 16 1 1,0,1 0).
+    That case is reported and bounded by the oracle's own divergence; the asserted comparison uses the same weights with the
+    level-0 query/key kernels scaled by 1/4 (logit std ~1.5, the regime of a trained network), where the two oracles agree
+    to 2.2e-2 (bf16) / 2.3e-3 (fp16)."""
     import b200dm
     torch.set_num_threads(os.cpu_count() or 1)
     S, C, B, T = 16, 16, 1, 250
     has = [True, False, True]
     ou = OUNet(S, C, [64, 128, 256], has, first_conv_channels=64)
-    P = OI.make_params(ou.spec(), 0, "stress")
+    P_sat = OI.make_params(ou.spec(), 0, "stress")
+    P = {k: (v * 0.25 if k.startswith(("down.0.attn", "up.0.attn")) and k.endswith(("query.kernel", "key.kernel")) else v)
+         for k, v in P_sat.items()}
     net = b200dm.build_model(S, C, [64, 128, 256], has)
-    net.set_weights(P)
-    net.compile(B, T)
-    assert any("attn" in b.get("name", "") and b.get("s") == S for b in net.blocks)
     x = OI.normal((B, S, S, S, C), 1)
     tt = torch.full((B,), 123)
+    # saturated-softmax case: bounded by the divergence of the two oracles
+    net.set_weights(P_sat)
+    net.compile(B, T)
+    assert any("attn" in b.get("name", "") and b.get("s") == S for b in net.blocks)
+    y = net([x.to(cuda), tt]).cpu()
+    flag_ok()
+    with torch.no_grad():
+        ref, ref_e = ou.forward(P_sat, x, tt), ou.forward(P_sat, x, tt, emu=emu16())
+    r_sat, r_or = rel(y, ref), rel(ref_e, ref)
+    report("cfg-4 level-0 attention U-Net, SATURATED softmax (plain stress weights)", rel_l2_vs_fp32_oracle=r_sat,
+           emulating_oracle_vs_fp32_oracle=r_or)
+    assert r_sat <= 1.5 * r_or + 2e-2, (r_sat, r_or)
+    # conditioned case
+    net.set_weights(P)
+    net.compile(B, T)
     y = net([x.to(cuda), tt]).cpu()
     flag_ok()
     with torch.no_grad():
         ref = ou.forward(P, x, tt)
     r = rel(y, ref)
     report("cfg-4 level-0 attention U-Net forward S=16 (L=4096)", rel_l2_vs_fp32_oracle=r)
-    assert r <= tol(3e-2, 5e-3), r
+    assert r <= tol(4e-2, 6e-3), r
 
+    # DDIM has no clip on eps_hat: a random-init network whose eps_hat is 11-36x its input (measured with these weights) blows the
+    # chain up to inf within 10 steps on BOTH sides, so the chain runs with the output conv scaled to a contraction (gain < 1)
+    P = dict(P)
+    P["out.conv.kernel"] = P["out.conv.kernel"] / 64
+    net.set_weights(P)
     dm = b200dm.DiffusionModel(S, 256, C, None, types.SimpleNamespace(timesteps=T, num_gpus=1, kernel_resize=False, bs=B))
     dm.network = net
     n = 25
@@ -262,7 +289,8 @@ def test_cfg4_level0_attention_unet_and_ddim_chain(cuda):
             xr = OS.ddim_step(b, xr, eps, i, seq[j + 1] if j + 1 < len(seq) else -1)
     r, ma = rel(lat, xr), maxabs(lat, xr)
     report("cfg-4 25-step DDIM chain (graph path)", rel_l2=r, max_abs=ma)
-    assert r <= tol(3e-2, 5e-3), (r, ma)
+    assert torch.isfinite(lat).all() and torch.isfinite(xr).all()
+    assert r <= tol(1.5e-2, 2.5e-3), (r, ma)
     # a non-uniform sequence replays the SAME graph
     g0 = dm._step["graph"]
     lat2 = dm.generate((B, S, S, S, C), x_T=x, sampler="ddim", timestep_seq=[249, 200, 120, 60, 30, 10, 3, 0]).cpu()
@@ -337,7 +365,7 @@ def test_fp16_build_meets_chain_tolerances(cuda):
     """libb200dm_f16.so (same sources, IEEE fp16 as the 16-bit storage type): the cfg-2 / cfg-1 / cfg-3 parity tests of this file in a
     child process; their fp16 tolerances are north_star's chain targets (rel-L2 <= 1e-3 x 1.5-3 margin, max-abs <= 2e-2)."""
     env = dict(os.environ, B200DM_PRECISION="fp16", B200DM_ORACLE_CACHE=CACHE)
-    sel = "cfg2 or cfg1 or cfg3 or per_sample"
+    sel = "cfg2 or cfg1 or cfg3 or cfg4 or per_sample"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-s", "-k", sel],
                        env=env, cwd=ROOT, capture_output=True, text=True)
     lines = [ln[ln.index("[parity"):] for ln in r.stdout.splitlines() if "[parity" in ln]
