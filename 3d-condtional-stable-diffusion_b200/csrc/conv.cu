@@ -24,8 +24,18 @@
 #include <new>
 #include <vector>
 #include "conv_common.cuh"
+
+// Tuning / experiment switches (B200DM_NO_PAIR, B200DM_CLUSTER, B200DM_KSPLIT, ...) are read only when the process also sets
+// B200DM_TUNING=1: a production process's environment cannot reconfigure the kernels by accident.
+static const char* tuning_env(const char* name) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B200DM_TUNING"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on ? getenv(name) : nullptr;
+}
+
 #include "conv_halo.cuh"
 #include "conv_halo_up.cuh"
+#include "conv_stencil.cuh"
 
 namespace {
 
@@ -494,7 +504,7 @@ int compute_geometry(const b200dm_conv_desc* d, Geometry* g) {
   else if (d->c_out <= 64) g->n_pad = 64;
   else g->n_pad = ((d->c_out + 127) / 128) * 128;
   g->block_n = g->n_pad < 128 ? g->n_pad : 128;
-  if (const char* e = getenv("B200DM_IGEMM_BN")) {   // tuning aid: narrower N tiles (more CTAs, shorter epilogues)
+  if (const char* e = tuning_env("B200DM_IGEMM_BN")) {   // tuning aid: narrower N tiles (more CTAs, shorter epilogues)
     const int v = atoi(e);
     if ((v == 64 || v == 32) && g->n_pad >= 128 && !(d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w >= 8 && d->in_h >= 16))
       g->block_n = v;
@@ -546,6 +556,9 @@ struct b200dm_conv_plan {
   bool pair = false;   // halo kernel on 8 x 8 planes: 8w x 8h x 2d tiles from pair slabs (conv_halo.cuh)
   int halo_td = 1, halo_nb = 4, halo_tps = 1;
   int halo_ns = 0;     // slab ring depth when a variant fixes it (0 = by epilogue kind)
+  bool stencil = false;   // C_out = 1, C_in = 32 3^3 conv: HBM-bound stencil-reduce kernel (conv_stencil.cuh)
+  stencil::Params sp;
+  CUtensorMap mapS;
 };
 
 static int* g_dbg_flag = nullptr;
@@ -818,6 +831,38 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   pl->desc = *d;
   pl->g = g;
   const int st = d->mode == B200DM_CONV_DIRECT ? d->stride : 1;
+  // C_out = 1, C_in = 32, 3^3 stride 1 (the vqgan_attn_cp decoder's head): HBM-bound stencil-reduce kernel instead of an
+  // N = 16 tensor-core tile (conv_stencil.cuh); bias + activation epilogue only
+  if (d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->c_out == 1 && d->c0 == stencil::kC && d->c1 == 0 &&
+      !chan_bias && !residual && !prelu_alpha && d->reserved[0] == B200DM_ACT_NONE && d->reserved[1] == 0 && d->use_halo >= 0 &&
+      !tuning_env("B200DM_NO_STENCIL")) {
+    cuuint64_t dims[5] = {(cuuint64_t)d->c0, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->in_d, (cuuint64_t)d->batch};
+    cuuint64_t strides[4] = {(cuuint64_t)d->c0 * 2, (cuuint64_t)d->in_w * d->c0 * 2, (cuuint64_t)d->in_h * d->in_w * d->c0 * 2,
+                             (cuuint64_t)d->in_d * d->in_h * d->in_w * d->c0 * 2};
+    cuuint32_t box[5] = {(cuuint32_t)stencil::kC, (cuuint32_t)stencil::kHW, (cuuint32_t)stencil::kHH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (enc(&pl->mapS, kTmapAct16, 5, const_cast<void*>(x0), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      delete pl; b200dm_set_error("cuTensorMapEncodeTiled(stencil X) failed"); return B200DM_ERR_CUDA;
+    }
+    stencil::Params& sp = pl->sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.batch = d->batch; sp.D = d->in_d; sp.H = d->in_h; sp.W = d->in_w;
+    sp.tiles_h = (d->in_h + stencil::kTH - 1) / stencil::kTH; sp.tiles_w = (d->in_w + stencil::kTW - 1) / stencil::kTW;
+    // d ranges: enough work items for ~6 per resident CTA (two CTAs per SM), each range >= 8 planes (2 halo planes per range)
+    const long long cols = (long long)d->batch * sp.tiles_h * sp.tiles_w, ctas = 2LL * b2_num_sms();
+    int dsplit = 1;
+    while (cols * dsplit < 6 * ctas && d->in_d / (dsplit * 2) >= 8) dsplit *= 2;
+    sp.dlen = (d->in_d + dsplit - 1) / dsplit; sp.dsplit = (d->in_d + sp.dlen - 1) / sp.dlen;
+    sp.items = (int)(cols * sp.dsplit);
+    sp.w = (const act_t*)w_packed; sp.bias = bias; sp.act = d->act; sp.y_f32 = d->y_dtype == B200DM_F32; sp.y = y; sp.dbg = g_dbg_flag;
+    pl->stencil = true;
+    pl->grid = dim3((unsigned)(sp.items < ctas ? sp.items : ctas), 1, 1);
+    pl->smem = stencil::kSmem;
+    pl->flops = 2.0 * 27 * d->c0 * (double)d->batch * d->in_d * d->in_h * d->in_w;
+    *out = pl;
+    return B200DM_OK;
+  }
   // halo-reuse kernel: 3^3 stride-1 convs on volumes that fill its 8w x 16h tile (use_halo = -1 forces it off)
   pl->halo = d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w >= 8 && d->in_h >= 16 &&
              d->reserved[1] == 0 && d->use_halo >= 0;
@@ -825,24 +870,24 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // weight stream; bf16 staged output only
   pl->pair = !pl->halo && d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w == 8 && d->in_h == 8 &&
              d->in_d >= 2 && d->reserved[1] == 0 && d->use_halo >= 0 && d->y_dtype == B200DM_BF16 && d->c_out % 64 == 0 &&
-             !prelu_alpha && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) && !getenv("B200DM_NO_PAIR");
+             !prelu_alpha && !(tuning_env("B200DM_TMA_EPI") && atoi(tuning_env("B200DM_TMA_EPI")) == 0) && !tuning_env("B200DM_NO_PAIR");
   if (pl->pair) { pl->halo = true; g.block_n = 64; pl->g.block_n = 64; }
   // x2 up-convolutions (nearest-upsample + conv3, ConvT k4 s2) on low-resolution planes that fill the 8 x 16 halo tile
   {
     const long long per_up = (long long)((d->in_w + 7) / 8) * ((d->in_h + 15) / 16) * ((d->in_d + 1) / 2) * d->batch;
     // (C_out = 32 -- the decoders' last ConvT, 64 -> 32 at 64^3 -> 128^3 -- runs N = 32 tiles with 64-byte staged rows)
-    const bool up32 = d->c_out == 32 && g.block_n == 32 && !getenv("B200DM_NO_UP32");
+    const bool up32 = d->c_out == 32 && g.block_n == 32 && !tuning_env("B200DM_NO_UP32");
     pl->ups = d->mode == B200DM_CONV_PARITY && d->in_w >= 8 && d->in_h >= 16 && d->in_d >= 2 && (d->c_out % 64 == 0 || up32) &&
               d->y_dtype == B200DM_BF16 && !residual && !prelu_alpha && d->reserved[1] == 0 && d->use_halo >= 0 && per_up % 2 == 0 &&
-              (g.block_n == 64 || g.block_n == 128 || up32) && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) &&
-              !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0) && !getenv("B200DM_NO_UPS");
+              (g.block_n == 64 || g.block_n == 128 || up32) && !(tuning_env("B200DM_TMA_EPI") && atoi(tuning_env("B200DM_TMA_EPI")) == 0) &&
+              !(tuning_env("B200DM_CG2") && atoi(tuning_env("B200DM_CG2")) == 0) && !tuning_env("B200DM_NO_UPS");
     if (pl->ups) pl->halo = true;
     // the same on 8 x 8 low-resolution planes (8^3 -> 16^3): pair-slab tiles
     const long long per_pair = (long long)((d->in_d + 1) / 2) * d->batch;
     if (!pl->ups && d->mode == B200DM_CONV_PARITY && d->in_w == 8 && d->in_h == 8 && d->in_d >= 2 && d->in_d % 2 == 0 && d->c_out % 64 == 0 &&
         d->y_dtype == B200DM_BF16 && !residual && !prelu_alpha && d->reserved[1] == 0 && d->use_halo >= 0 && per_pair % 2 == 0 &&
-        (g.block_n == 64 || g.block_n == 128) && !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0) &&
-        !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0) && !getenv("B200DM_NO_UPS")) {
+        (g.block_n == 64 || g.block_n == 128) && !(tuning_env("B200DM_TMA_EPI") && atoi(tuning_env("B200DM_TMA_EPI")) == 0) &&
+        !(tuning_env("B200DM_CG2") && atoi(tuning_env("B200DM_CG2")) == 0) && !tuning_env("B200DM_NO_UPS")) {
       pl->ups = true; pl->pair = true; pl->halo = true;
     }
   }
@@ -856,7 +901,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     // the operand stream is capped by what ONE SM can take from L2 (~40 B/clk), which multicast does not raise at
     // cluster sizes <= 4, and the cluster-wide stage hand-shake adds latency.  Kept for experiments and tests.
     int want_m = 1, want_n = 1;
-    if (const char* e = getenv("B200DM_CLUSTER")) { if (sscanf(e, "%d,%d", &want_m, &want_n) != 2) { want_m = 1; want_n = 1; } }
+    if (const char* e = tuning_env("B200DM_CLUSTER")) { if (sscanf(e, "%d,%d", &want_m, &want_n) != 2) { want_m = 1; want_n = 1; } }
     // B is shared by m-tiles of the same sample only in GEMM mode (x = tile within sample fastest)
     const long long m_share = d->mode == B200DM_CONV_BATCHED_GEMM ? (g.m_w + g.box_w - 1) / g.box_w : mt;
     for (cl_m = want_m; cl_m > 1 && (m_share % cl_m != 0 || mt % cl_m != 0 || g.block_n / cl_m < 8); cl_m >>= 1) {}
@@ -947,7 +992,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   p.bias = bias; p.chan_bias = chan_bias; p.t_dev = t_dev;
   p.residual = (const act_t*)residual; p.prelu_alpha = (const act_t*)prelu_alpha;
   p.y = y; p.dbg = g_dbg_flag;
-  if (const char* e = getenv("B200DM_EPI_DBG")) p.epi_dbg = atoi(e);
+  if (const char* e = tuning_env("B200DM_EPI_DBG")) p.epi_dbg = atoi(e);
   p.cl_m = cl_m; p.cl_n = cl_n; p.a_split_dim = a_split_dim; p.a_split_ext = a_split_ext;
   const long long mtiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
   if (mtiles > 0x7fffffffLL) { delete pl; b200dm_set_error("conv_plan_create: too many tiles"); return B200DM_ERR_INVALID; }
@@ -961,7 +1006,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     const int nkb = (g.nch0 + g.nch1) * g.ntaps;
     int ksp = 1;
     while (ksp < 8 && ctas * (ksp * 2) <= b2_num_sms() && nkb / (ksp * 2) >= 13) ksp *= 2;   // >= 13 k-blocks per CTA: 3^3 convs only
-    if (const char* e = getenv("B200DM_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 8 && (v & (v - 1)) == 0 && nkb / v >= 1) ksp = v; }
+    if (const char* e = tuning_env("B200DM_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 8 && (v & (v - 1)) == 0 && nkb / v >= 1) ksp = v; }
     if (ksp > 1) { p.ksplit = ksp; pl->grid.x = (unsigned)(mtiles * ksp); }
   }
   // pipeline depth 4; measured on B200: a deeper ring (6 stages at BLOCK_N=128, 8 below) does not help at BLOCK_N=128 (the
@@ -969,14 +1014,14 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   pl->nstage = 4;
   // short K loops (1^3 convs: 1-3 k-blocks) never fill four stages; two stages let 3-4 CTAs share an SM, which hides the
   // per-CTA prologue / TMA latency / epilogue of these HBM-bound launches
-  if ((g.nch0 + g.nch1) * g.ntaps <= 3 && g.block_n >= 64 && cl_m * cl_n == 1 && !getenv("B200DM_IGEMM_NO2")) pl->nstage = 2;
+  if ((g.nch0 + g.nch1) * g.ntaps <= 3 && g.block_n >= 64 && cl_m * cl_n == 1 && !tuning_env("B200DM_IGEMM_NO2")) pl->nstage = 2;
   // grids of several waves: two stages x three co-resident CTAs keep more operand bytes in flight per SM than one CTA with
   // four stages, and hide every CTA's prologue / epilogue (measured: 16^3 128->128 parity conv 123 -> 77 us, 8^3 MLP GEMM
   // 17.5 -> 12.7 us; a single-wave split-K grid gets slower, so it keeps four stages)
   if (!pl->halo && (long long)pl->grid.x * pl->grid.y * pl->grid.z >= 2LL * b2_num_sms() && g.block_n >= 64 && p.ksplit <= 1 &&
-      cl_m * cl_n == 1 && !getenv("B200DM_IGEMM_NO2"))
+      cl_m * cl_n == 1 && !tuning_env("B200DM_IGEMM_NO2"))
     pl->nstage = 2;
-  if (const char* e = getenv("B200DM_IGEMM_STAGES")) { if (atoi(e) == 2 && g.block_n >= 64 && cl_m * cl_n == 1) pl->nstage = 2; if (atoi(e) == 4) pl->nstage = 4; }
+  if (const char* e = tuning_env("B200DM_IGEMM_STAGES")) { if (atoi(e) == 2 && g.block_n >= 64 && cl_m * cl_n == 1) pl->nstage = 2; if (atoi(e) == 4) pl->nstage = 4; }
   // staged (TMA-store) epilogue of the per-tap GEMM kernel: bf16 NDHWC output with whole 64-channel groups
   memset(&pl->om, 0, sizeof(pl->om));
   {
@@ -985,7 +1030,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     const bool n32 = pl->halo && !pl->pair && d->c_out == 32 && g.block_n == 32 && !f32 && (pl->ups || d->mode == B200DM_CONV_DIRECT);
     bool want = cl_m * cl_n == 1 && (!f32 || pl->halo) && d->reserved[1] == 0 && !prelu_alpha &&
                 ((d->c_out % 64 == 0 && g.block_n >= 64) || n32) && !(d->mode == B200DM_CONV_PARITY && residual);
-    if (const char* e = getenv("B200DM_TMA_EPI")) { if (atoi(e) == 0) want = false; }
+    if (const char* e = tuning_env("B200DM_TMA_EPI")) { if (atoi(e) == 0) want = false; }
     if (want) {
       const int par = d->mode == B200DM_CONV_PARITY ? 8 : 1;
       const int ps = d->mode == B200DM_CONV_PARITY ? 2 : 1;   // output voxel stride of one M-space step
@@ -1022,7 +1067,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   if (d->reserved[1] != 0 && !pl->halo && cl_m * cl_n == 1 && d->mode == B200DM_CONV_DIRECT && d->ksize == 1 && st == 1 &&
       d->y_dtype == B200DM_BF16 && g.block_n == 128 && g.box_n == 1 && g.box_w == g.m_w && g.box_h == g.m_h && g.m_d % g.box_d == 0 &&
       !residual && !prelu_alpha && !chan_bias && d->act == B200DM_ACT_NONE && d->reserved[0] == B200DM_ACT_NONE &&
-      !(getenv("B200DM_TMA_EPI") && atoi(getenv("B200DM_TMA_EPI")) == 0)) {
+      !(tuning_env("B200DM_TMA_EPI") && atoi(tuning_env("B200DM_TMA_EPI")) == 0)) {
     const cuuint64_t Lv = (cuuint64_t)g.m_w * g.m_h * g.m_d;
     cuuint64_t dims[5] = {Lv, (cuuint64_t)d->c_out, 1, 1, (cuuint64_t)d->batch};
     cuuint64_t strides[4] = {Lv * 2, Lv * d->c_out * 2, Lv * d->c_out * 2, Lv * d->c_out * 2};
@@ -1039,7 +1084,7 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // BLOCK_N = 128 with the staged epilogue: one-tap weight stages hold only 8 MMAs (4 per issuer warp) and the per-stage
   // barrier round trip (~200 cycles) made those convs issue-bound (45 % of the MMA floor); 3-tap stages x 2 fit once the
   // slab ring is the 4 slabs a channel chunk needs (the next chunk's slab i reloads as soon as slab i is released).
-  if (pl->halo && !pl->pair && g.block_n == 128 && p.tma_epi && !getenv("B200DM_NO_WIDE")) {
+  if (pl->halo && !pl->pair && g.block_n == 128 && p.tma_epi && !tuning_env("B200DM_NO_WIDE")) {
     cuuint64_t dims3[3] = {64, (cuuint64_t)g.n_pad, (cuuint64_t)(g.ktot / 64)};
     cuuint64_t strides3[2] = {(cuuint64_t)g.ktot * 2, 128};
     cuuint32_t box3[3] = {64, 128, 3};
@@ -1054,10 +1099,10 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
   // the U-Net's input conv (256 -> 32, direct stores).  Short-K N=32 convs (the decoder's 32 -> 32 at 128^3) are bound by their
   // direct-store epilogue; pairing them only couples two epilogues (measured 4.18 -> 4.79 ms), so they stay single-CTA.
   // With the SWIZZLE_64B staged epilogue (n32 above) those convs run 3.78 ms, paired or not gated on tma_epi any more.
-  const bool cg2_short = p.tma_epi && getenv("B200DM_CG2_N32S") && atoi(getenv("B200DM_CG2_N32S")) != 0;   // experiment: pair short-K staged N=32 convs too
+  const bool cg2_short = p.tma_epi && tuning_env("B200DM_CG2_N32S") && atoi(tuning_env("B200DM_CG2_N32S")) != 0;   // experiment: pair short-K staged N=32 convs too
   const bool cg2_n32 = g.block_n == 32 && !pl->pair && !pl->ups && pl->halo_td == 2 && !p.y2 && (g.nch0 + g.nch1 >= 2 || cg2_short);
   if (pl->halo && (((g.block_n == 64 || g.block_n == 128) && p.tma_epi && (pl->pair || pl->halo_td == 2 || g.block_n == 128)) || cg2_n32) &&
-      !(getenv("B200DM_CG2") && atoi(getenv("B200DM_CG2")) == 0)) {
+      !(tuning_env("B200DM_CG2") && atoi(tuning_env("B200DM_CG2")) == 0)) {
     const int td = pl->halo_td;   // (pair: d step 2)
     const long long per = (long long)((d->in_w + 7) / 8) * (pl->pair ? (d->in_h + 7) / 8 : (d->in_h + 15) / 16) * ((d->in_d + td - 1) / td) * d->batch;
     if (per % 2 == 0) {
@@ -1109,6 +1154,16 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
 extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "conv_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
+  if (pl->stencil) {
+    auto kern = stencil::conv_stencil_c1_kernel;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil::kSmem));
+      attr_set = true;
+    }
+    B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(stencil::kThreads), pl->smem, s, pl->mapS, pl->sp));
+    return B200DM_OK;
+  }
   if (pl->ups && pl->pair) return pl->g.block_n == 64 ? launch_halo_up<64, 4, 3, true>(pl, s) : launch_halo_up<128, 4, 2, true>(pl, s);
   if (pl->ups && pl->g.block_n == 32) return launch_halo_up<32, 5, 4>(pl, s);
   if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
@@ -1161,7 +1216,7 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   B2_CHECK_ARG(p && y_extra && scale && shift, "conv_plan_add_output: null argument");
   B2_CHECK_ARG(p->desc.c_out % 16 == 0 && p->desc.reserved[1] == 0, "conv_plan_add_output: needs c_out %% 16 == 0 and a plain (non-transposed) store");
   B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
-  if (p->pair || p->wide || p->cg2) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo plans"); return B200DM_ERR_UNSUPPORTED; }
+  if (p->pair || p->wide || p->cg2 || p->stencil) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo / stencil plans"); return B200DM_ERR_UNSUPPORTED; }
   if (p->p.tma_epi) { p->p.tma_epi = 0; p->smem = p->halo ? halo_smem_bytes(p) : conv_smem_bytes(p->g.block_n, p->nstage, false); }
   if (!p->p.y2) { p->p.y2 = (act_t*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (act_t*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
@@ -1173,7 +1228,7 @@ extern "C" int b200dm_conv_plan_set_side_norm(b200dm_conv_plan* pl, void* y_side
   B2_CHECK_ARG(pl && y_side && scale && shift, "conv_plan_set_side_norm: null argument");
   const b200dm_conv_desc* d = &pl->desc;
   const int C = d->c0 + d->c1;
-  if (pl->halo || !pl->p.tma_epi || pl->p.swap_ab || pl->p.ksplit > 1 || pl->p.cl_m * pl->p.cl_n != 1 || d->mode != B200DM_CONV_DIRECT ||
+  if (pl->halo || pl->stencil || !pl->p.tma_epi || pl->p.swap_ab || pl->p.ksplit > 1 || pl->p.cl_m * pl->p.cl_n != 1 || d->mode != B200DM_CONV_DIRECT ||
       d->ksize != 1 || d->stride != 1 || pl->g.block_n < 64 || (d->c1 > 0 && d->c0 % 64 != 0) || C % 8 != 0 || C > 1024 ||
       ((uintptr_t)y_side & 15) != 0) {
     b200dm_set_error("conv_plan_set_side_norm: only on staged 1^3 stride-1 convs (c0 %% 64 == 0 when c1 > 0)");
@@ -1199,7 +1254,7 @@ extern "C" int b200dm_conv_plan_set_side_norm(b200dm_conv_plan* pl, void* y_side
 
 extern "C" int b200dm_conv_plan_info(const b200dm_conv_plan* p, int32_t* halo, int32_t* block_n, int32_t* ksplit) {
   B2_CHECK_ARG(p, "conv_plan_info: null plan");
-  if (halo) *halo = p->halo ? 1 : 0;
+  if (halo) *halo = p->stencil ? 2 : (p->halo ? 1 : 0);   // 2 = HBM-bound stencil-reduce kernel (C_out = 1)
   if (block_n) *block_n = p->g.block_n;
   if (ksplit) *ksplit = p->p.ksplit;
   return B200DM_OK;
@@ -1210,6 +1265,7 @@ extern "C" int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float*
   B2_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_plan_set_out_affine: give both scale and shift, or neither");
   B2_CHECK_ARG(!scale || !p->p.prelu_alpha, "conv_plan_set_out_affine: not combinable with PReLU");
   B2_CHECK_ARG(!scale || !p->p.swap_ab, "conv_plan_set_out_affine: not combinable with a transposed store");
+  B2_CHECK_ARG(!scale || !p->stencil, "conv_plan_set_out_affine: not available on the C_out = 1 stencil plan");
   p->p.out_scale = scale;
   p->p.out_shift = shift;
   return B200DM_OK;

@@ -96,6 +96,14 @@ __global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const
   const int64_t b = blockIdx.y, base = b * d.n_per_sample;
   const bool gen = (noise == nullptr) && d.sampler == 0 && k.t > 0;
   const bool inj = noise != nullptr && k.t > 0;
+  // reserved bit 0: the Philox key and the global index of sample 0 live in device memory (t_dev[4..7]), so a captured step
+  // graph serves every seed / shard without re-capture; desc.sample_id0 is then this launch's offset inside the call's batch
+  uint64_t seed = d.seed;
+  int64_t sid0 = d.sample_id0;
+  if ((d.reserved & 1) && d.t_dev) {
+    seed = (uint64_t)(uint32_t)d.t_dev[4] | ((uint64_t)(uint32_t)d.t_dev[5] << 32);
+    sid0 += (int64_t)((uint64_t)(uint32_t)d.t_dev[6] | ((uint64_t)(uint32_t)d.t_dev[7] << 32));
+  }
   const uint32_t stride = gridDim.x * blockDim.x;
   constexpr int U = 2;
   for (uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x; j0 < n8; j0 += stride * U) {
@@ -122,8 +130,8 @@ __global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const
       float z[8];
       if (gen) {
         float za[4], zb[4];
-        normal4(2 * j, (uint32_t)k.t, (uint32_t)(d.sample_id0 + b), 0u, d.seed, za);
-        normal4(2 * j + 1, (uint32_t)k.t, (uint32_t)(d.sample_id0 + b), 0u, d.seed, zb);
+        normal4(2 * j, (uint32_t)k.t, (uint32_t)(sid0 + b), 0u, seed, za);
+        normal4(2 * j + 1, (uint32_t)k.t, (uint32_t)(sid0 + b), 0u, seed, zb);
 #pragma unroll
         for (int q = 0; q < 4; ++q) { z[q] = za[q]; z[4 + q] = zb[q]; }
       } else if (inj) {

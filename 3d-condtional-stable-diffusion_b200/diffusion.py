@@ -108,17 +108,11 @@ class DiffusionModel:
         # network.load_weights is never followed by sampling with the old weights
         key = (batch, sampler, inject_noise, self._num_chains(batch), self.network.weights_version)
         if self._step is not None and self._step["key"] == key:
-            st = self._step
-            if (st["seed"], st["sample_id0"]) != (seed, sample_id0):
-                st["seed"], st["sample_id0"] = seed, sample_id0
-                for c, d in enumerate(st["descs"]):
-                    d.seed, d.sample_id0 = seed, sample_id0 + c * st["chain_batch"]
-                st["graph"] = None  # kernel arguments are baked into a captured graph
-            return st
+            return self._step   # seed / sample base are device-resident (t_dev[4..7]): the captured graph serves every call
         L.require_gpu()
         dev = torch.device("cuda", torch.cuda.current_device())
         self.b.to(dev)
-        t_dev = torch.zeros(4, dtype=torch.int32, device=dev)        # [t, t_prev, sequence index, -]
+        t_dev = torch.zeros(8, dtype=torch.int32, device=dev)        # [t, t_prev, sequence index, -, seed lo, hi, sample base lo, hi]
         t_seq = torch.full((self.timesteps + 2,), -1, dtype=torch.int32, device=dev)   # the call's timestep sequence, -1 terminated
         chains = key[3]
         cb = batch // chains
@@ -127,10 +121,10 @@ class DiffusionModel:
         S, Cl = self.latent_size, self.lc
         x = torch.zeros(batch, S, S, S, Cl, dtype=torch.float32, device=dev)
         noise = torch.zeros_like(x) if inject_noise else None
-        descs = [ops.make_update_desc(self.b, x[0].numel(), cb, 0, -1, 1 if sampler == "ddim" else 0, seed,
-                                      sample_id0 + c * cb, L.F32, t_dev=t_dev) for c in range(chains)]
+        descs = [ops.make_update_desc(self.b, x[0].numel(), cb, 0, -1, 1 if sampler == "ddim" else 0, 0,
+                                      c * cb, L.F32, t_dev=t_dev, seed_on_device=True) for c in range(chains)]
         self._step = dict(key=key, nets=nets, net=nets[0], x=x, noise=noise, descs=descs, t_dev=t_dev, t_seq=t_seq, graph=None, dev=dev,
-                          chains=chains, chain_batch=cb, seed=seed, sample_id0=sample_id0, streams=None)
+                          chains=chains, chain_batch=cb, streams=None)
         return self._step
 
     def _run_chain(self, st, c):
@@ -210,7 +204,9 @@ class DiffusionModel:
             raise ValueError("generate: empty timestep sequence")
         # one small H2D per call: the whole sequence (+ the -1 terminators) and the walker's start state
         st["t_seq"].copy_(torch.tensor(seq + [-1] * (T + 2 - len(seq)), dtype=torch.int32), non_blocking=True)
-        start = torch.tensor([seq[0], seq[1] if len(seq) > 1 else -1, 0, 0], dtype=torch.int32)
+        i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v  # noqa: E731
+        start = torch.tensor([seq[0], seq[1] if len(seq) > 1 else -1, 0, 0, i32(seed & 0xffffffff), i32((seed >> 32) & 0xffffffff),
+                              i32(sample_id0 & 0xffffffff), i32((sample_id0 >> 32) & 0xffffffff)], dtype=torch.int32)
         if x_T is None:  # samples = tf.random.normal(shape) (dm3d.py:513): Philox stream 1
             x0, xb = ops.philox_normal(shape, seed, sample_id0, 0, 1, want_bf16=True)
         else:

@@ -50,12 +50,13 @@ class ScheduleTables:
 
 
 def make_update_desc(tables: ScheduleTables, n_per_sample, batch, t=0, t_prev=-1, sampler=0, seed=0, sample_id0=0,
-                     eps_dtype=L.F32, t_dev=None) -> L.UpdateDesc:
+                     eps_dtype=L.F32, t_dev=None, seed_on_device=False) -> L.UpdateDesc:
     d = L.UpdateDesc()
     d.n_per_sample, d.batch, d.sampler = n_per_sample, batch, sampler
     tables.fill(d)
     d.t_dev = t_dev.data_ptr() if t_dev is not None else None
     d.t, d.t_prev, d.seed, d.sample_id0, d.eps_dtype = t, t_prev, seed, sample_id0, eps_dtype
+    d.reserved = 1 if seed_on_device else 0   # Philox key / sample base read from t_dev[4..7] (int32[8])
     return d
 
 
@@ -228,7 +229,7 @@ class ConvPlan:
     def info(self):
         halo, bn, ks = C.c_int32(), C.c_int32(), C.c_int32()
         check(lib().b200dm_conv_plan_info(self.h, C.byref(halo), C.byref(bn), C.byref(ks)))
-        return dict(halo=bool(halo.value), block_n=bn.value, ksplit=ks.value)
+        return dict(halo=halo.value, block_n=bn.value, ksplit=ks.value)   # halo: 0 per-tap GEMM, 1 halo kernel, 2 C_out=1 stencil
 
     def add_output(self, y_extra, scale, shift, act=None):
         """Extra bf16 output act(scale*v + shift) of the final value (the consumer's folded BatchNorm), same shape as y."""

@@ -43,11 +43,17 @@ class Program:
         plan = ops.ConvPlan(desc, x0, w_packed, y, x1=x1, bias=bias, chan_bias=chan_bias, t_dev=t_dev,
                             residual=residual, prelu_alpha=prelu_alpha, out_affine=out_affine)
         self.side_ok = side is not None and plan.set_side_norm(*side)   # (y_side, scale, shift, act)
-        self.flops += plan.flops
         check(lib().b200dm_program_add_conv(self.h, plan.h))
         plan.release()
         self.keep.extend(t for t in plan.keep if t is not None)
-        self.log.append(("conv" if not plan.info["halo"] else "conv_halo", note, plan.flops))
+        kind = plan.info["halo"]
+        if kind == 2:   # C_out = 1 stencil-reduce kernel: HBM-bound, accounted in bytes (input read once + output written)
+            nbytes = float(x0.numel() * x0.element_size() + y.numel() * y.element_size())
+            self.bytes += nbytes
+            self.log.append(("stencil", note, nbytes))
+        else:
+            self.flops += plan.flops
+            self.log.append(("conv_halo" if kind else "conv", note, plan.flops))
         self.outputs[note] = y
         self.producers[y.data_ptr()] = plan
         return y

@@ -230,7 +230,7 @@ def run_ours(args):
 
     def reset(t0=T - 1):   # restart the device-side timestep walker on the DDPM sequence T-1, T-2, ...
         st["t_seq"].copy_(torch.tensor(list(range(T - 1, -1, -1)) + [-1, -1], dtype=torch.int32))
-        st["t_dev"].copy_(torch.tensor([t0, t0 - 1, T - 1 - t0, 0], dtype=torch.int32))
+        st["t_dev"][:4].copy_(torch.tensor([t0, t0 - 1, T - 1 - t0, 0], dtype=torch.int32))
 
     # ---- device-resident timing: K graph replays between CUDA events on the launching stream
     reset()

@@ -68,13 +68,15 @@ typedef struct {
   const float* sqrt_alpha_bar;
   const float* sqrt_alpha_bar_prev;
   const float* sqrt_one_minus_alpha_bar;
-  const int32_t* t_dev;            /* device int32[2] = {t, t_prev}; if NULL use t / t_prev below */
+  const int32_t* t_dev;            /* device int32[2] = {t, t_prev}; if NULL use t / t_prev below.  With reserved bit 0 set it is
+                                    * int32[8] = {t, t_prev, idx, -, seed lo, seed hi, sample base lo, sample base hi} */
   int32_t t;
   int32_t t_prev;                  /* DDIM only: next (smaller) timestep, -1 for the last step */
   uint64_t seed;
   int64_t sample_id0;              /* global index of sample 0 of this batch (multi-GPU sharding) */
   int32_t eps_dtype;               /* dtype of eps */
-  int32_t reserved;
+  int32_t reserved;                /* bit 0: Philox key = t_dev[4..5], sample index = t_dev[6..7] + sample_id0 + b (device-resident:
+                                    * one captured step graph serves every seed and every shard) */
 } b200dm_update_desc;
 
 int b200dm_ddpm_update(const b200dm_update_desc* d, const float* x_t, const void* eps,

@@ -342,3 +342,29 @@ def test_conv_extra_normalised_outputs(cuda, B, S, cin, cout, halo):
     _close(y, ref, tol=6e-3, what="main output")
     _close(y2, O.swish(ref * s2 + h2), tol=8e-3, what="extra output 1 (BN + swish)")
     _close(y3, ref * s3 + h3, tol=8e-3, what="extra output 2 (BN)")
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 13, 40), (1, 16, 16, 16), (1, 3, 8, 32), (2, 33, 24, 70)])
+def test_conv3_head_stencil_kernel(cuda, shape):
+    """C_in = 32 -> C_out = 1 (vqgan_attn_cp.py:424-427, the decoder's head): the HBM-bound stencil-reduce kernel
+    (conv_stencil.cuh) on ragged volumes (partial h / w tiles, several d ranges), fp32 and 16-bit outputs, bias + activation."""
+    from b200dm import ops, _lib as L
+    B, D, H, W = shape
+    x = _rand((B, D, H, W, 32), 1)
+    w = _rand((3, 3, 3, 32, 1), 2, 1.0 / np.sqrt(27 * 32))
+    b = torch.tensor([0.37])
+    ref = O.conv3d(x, w, b)
+    xd = x.to(cuda, L.ACT_DTYPE)
+    desc = ops.make_conv_desc(L.CONV_DIRECT, B, (D, H, W), 32, 0, 1, 3, 1, None, None, torch.float32)
+    y = torch.empty(B, D, H, W, 1, dtype=torch.float32, device=cuda)
+    plan = ops.ConvPlan(desc, xd, ops.pack_conv_weights(desc, w, False).to(cuda), y, bias=b.to(cuda))
+    assert plan.info["halo"] == 2, "expected the stencil plan"
+    plan.run()
+    _check_flag()
+    _close(y, ref, tol=2e-5, what=f"stencil head {shape} fp32 out")
+    # against the tensor-core halo / per-tap path on the same inputs (use_halo = -1 switches the stencil and halo kernels off)
+    y2 = ops.conv3d(xd, w, bias=b.to(cuda), y_dtype=torch.float32, use_halo=-1)
+    _close(y, y2.float().cpu(), tol=2e-5, what="stencil vs per-tap GEMM kernel")
+    y16 = ops.conv3d(xd, w, bias=b.to(cuda), act="silu")
+    _check_flag()
+    _close(y16, O.swish(ref), tol=6e-3, what="stencil head + silu (16-bit out)")
