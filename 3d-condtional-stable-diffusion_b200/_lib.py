@@ -128,6 +128,10 @@ _SIGS = {
     "b200dm_conv_plan_add_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b200dm_conv_plan_set_side_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b200dm_conv_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "b200dm_conv_plan_gn_partials_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "b200dm_conv_plan_set_gn_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200dm_gn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
+    "b200dm_program_add_gn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p]),
     "b200dm_attention_plan_create": (C.c_int, [C.POINTER(AttnDesc)] + [C.c_void_p] * 5 + [C.POINTER(C.c_void_p)]),
     "b200dm_attention_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200dm_attention_plan_destroy": (None, [C.c_void_p]),

@@ -36,6 +36,7 @@ static const char* tuning_env(const char* name) {
 #include "conv_halo.cuh"
 #include "conv_halo_up.cuh"
 #include "conv_stencil.cuh"
+#include "conv_sweep.cuh"
 
 namespace {
 
@@ -559,6 +560,8 @@ struct b200dm_conv_plan {
   bool stencil = false;   // C_out = 1, C_in = 32 3^3 conv: HBM-bound stencil-reduce kernel (conv_stencil.cuh)
   stencil::Params sp;
   CUtensorMap mapS;
+  bool sweep = false;     // C_in = C_out = 32 3^3 conv: d-sweeping N = 96 kernel (conv_sweep.cuh); mapS = input, mapB = weights, om.y[0] = output
+  sweep::Params wp;
 };
 
 static int* g_dbg_flag = nullptr;
@@ -863,6 +866,49 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
     *out = pl;
     return B200DM_OK;
   }
+  // C_in = C_out = 32, 3^3 stride 1, 16-bit output (the decoders' 128^3 / 64^3 residual units): d-sweeping kernel with the three
+  // kd taps of an input plane as one N = 96 MMA and the weight set resident in shared memory (conv_sweep.cuh)
+  if (d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->c_out == 32 && d->c0 == 32 && d->c1 == 0 &&
+      d->y_dtype == B200DM_BF16 && !chan_bias && !prelu_alpha && d->reserved[1] == 0 && d->use_halo >= 0 && g.n_pad == 32 &&
+      g.ktot == 27 * 64 && d->in_w >= 8 && d->in_h >= 16 && d->in_d >= 2 && !tuning_env("B200DM_NO_SWEEP")) {
+    const cuuint64_t C = 32;
+    cuuint64_t dims[5] = {C, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->in_d, (cuuint64_t)d->batch};
+    cuuint64_t strides[4] = {C * 2, (cuuint64_t)d->in_w * C * 2, (cuuint64_t)d->in_h * d->in_w * C * 2,
+                             (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t boxx[5] = {32, 10, 18, 2, 1}, boxy[5] = {32, 8, 16, 1, 1};
+    cuuint64_t wdims[3] = {64, 32, 27};
+    cuuint64_t wstrides[2] = {(cuuint64_t)g.ktot * 2, 128};
+    cuuint32_t wbox[3] = {32, 32, 1};
+    const bool okm =
+        enc(&pl->mapS, kTmapAct16, 5, const_cast<void*>(x0), dims, strides, boxx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+        enc(&pl->om.y[0], kTmapAct16, 5, y, dims, strides, boxy, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+        enc(&pl->mapB, kTmapAct16, 3, const_cast<void*>(w_packed), wdims, wstrides, wbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (!okm) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(sweep) failed"); return B200DM_ERR_CUDA; }
+    sweep::Params& wp = pl->wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.D = d->in_d; wp.H = d->in_h; wp.W = d->in_w; wp.batch = d->batch;
+    wp.tiles_w = (d->in_w + 7) / 8; wp.tiles_h = (d->in_h + 15) / 16;
+    const long long cols = (long long)d->batch * wp.tiles_w * wp.tiles_h, ctas = b2_num_sms();
+    int dsplit = 1;
+    while (cols * dsplit < 6 * ctas && d->in_d / (dsplit * 2) >= 8) dsplit *= 2;   // >= ~6 items per CTA, d ranges of >= 8 planes
+    wp.dlen = (d->in_d + dsplit - 1) / dsplit; wp.dsplit = (d->in_d + wp.dlen - 1) / wp.dlen;
+    wp.items = (int)(cols * wp.dsplit);
+    ConvParams& p = pl->p;
+    memset(&p, 0, sizeof(p));
+    p.batch = d->batch; p.in_d = p.out_d = d->in_d; p.in_h = p.out_h = d->in_h; p.in_w = p.out_w = d->in_w;
+    p.c_out = 32; p.n_pad = 32; p.act = d->act; p.post_act = d->reserved[0];
+    p.bias = bias; p.residual = (const act_t*)residual; p.y = y; p.dbg = g_dbg_flag; p.tma_epi = 1;
+    pl->sweep = true; pl->halo = true;
+    pl->grid = dim3((unsigned)(wp.items < ctas ? wp.items : ctas), 1, 1);
+    pl->smem = sweep::kSmem;
+    pl->flops = 2.0 * 27 * 32 * 32 * (double)d->batch * d->in_d * d->in_h * d->in_w;
+    *out = pl;
+    return B200DM_OK;
+  }
   // halo-reuse kernel: 3^3 stride-1 convs on volumes that fill its 8w x 16h tile (use_halo = -1 forces it off)
   pl->halo = d->mode == B200DM_CONV_DIRECT && d->ksize == 3 && d->stride == 1 && d->in_w >= 8 && d->in_h >= 16 &&
              d->reserved[1] == 0 && d->use_halo >= 0;
@@ -1164,6 +1210,16 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
     B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(stencil::kThreads), pl->smem, s, pl->mapS, pl->sp));
     return B200DM_OK;
   }
+  if (pl->sweep) {
+    auto kern = sweep::conv_sweep32_kernel;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep::kSmem));
+      attr_set = true;
+    }
+    B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(sweep::kThreads), pl->smem, s, pl->mapS, pl->mapB, pl->om.y[0], pl->p, pl->wp));
+    return B200DM_OK;
+  }
   if (pl->ups && pl->pair) return pl->g.block_n == 64 ? launch_halo_up<64, 4, 3, true>(pl, s) : launch_halo_up<128, 4, 2, true>(pl, s);
   if (pl->ups && pl->g.block_n == 32) return launch_halo_up<32, 5, 4>(pl, s);
   if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
@@ -1216,7 +1272,7 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   B2_CHECK_ARG(p && y_extra && scale && shift, "conv_plan_add_output: null argument");
   B2_CHECK_ARG(p->desc.c_out % 16 == 0 && p->desc.reserved[1] == 0, "conv_plan_add_output: needs c_out %% 16 == 0 and a plain (non-transposed) store");
   B2_CHECK_ARG(((uintptr_t)y_extra & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0, "conv_plan_add_output: pointers must be 16-byte aligned");
-  if (p->pair || p->wide || p->cg2 || p->stencil) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo / stencil plans"); return B200DM_ERR_UNSUPPORTED; }
+  if (p->pair || p->wide || p->cg2 || p->stencil || p->sweep) { b200dm_set_error("conv_plan_add_output: not available on pair-slab / wide-stage halo / stencil plans"); return B200DM_ERR_UNSUPPORTED; }
   if (p->p.tma_epi) { p->p.tma_epi = 0; p->smem = p->halo ? halo_smem_bytes(p) : conv_smem_bytes(p->g.block_n, p->nstage, false); }
   if (!p->p.y2) { p->p.y2 = (act_t*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (act_t*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
@@ -1254,7 +1310,7 @@ extern "C" int b200dm_conv_plan_set_side_norm(b200dm_conv_plan* pl, void* y_side
 
 extern "C" int b200dm_conv_plan_info(const b200dm_conv_plan* p, int32_t* halo, int32_t* block_n, int32_t* ksplit) {
   B2_CHECK_ARG(p, "conv_plan_info: null plan");
-  if (halo) *halo = p->stencil ? 2 : (p->halo ? 1 : 0);   // 2 = HBM-bound stencil-reduce kernel (C_out = 1)
+  if (halo) *halo = p->stencil ? 2 : (p->sweep ? 3 : (p->halo ? 1 : 0));   // 2 = HBM-bound stencil-reduce kernel (C_out = 1), 3 = d-sweeping N = 96 kernel
   if (block_n) *block_n = p->g.block_n;
   if (ksplit) *ksplit = p->p.ksplit;
   return B200DM_OK;
@@ -1268,5 +1324,33 @@ extern "C" int b200dm_conv_plan_set_out_affine(b200dm_conv_plan* p, const float*
   B2_CHECK_ARG(!scale || !p->stencil, "conv_plan_set_out_affine: not available on the C_out = 1 stencil plan");
   p->p.out_scale = scale;
   p->p.out_shift = shift;
+  return B200DM_OK;
+}
+
+// GroupNorm statistics as a by-product of the producing conv (d-sweeping kernel only): the epilogue accumulates per-(item, channel)
+// partial sums of the STORED values into `workspace` (float [rows][C][2], rows = batch * rows_per_sample); b200dm_gn_finalize
+// turns them into (mean, rstd) in a fixed order.  Returns the workspace size, 0 when the plan cannot produce partials.
+extern "C" size_t b200dm_conv_plan_gn_partials_bytes(const b200dm_conv_plan* p, int32_t* rows_per_sample) {
+  if (!p || !p->sweep) return 0;
+  if (rows_per_sample) *rows_per_sample = p->wp.items / p->wp.batch * 2;
+  return (size_t)p->wp.items * 2 * 32 * 2 * sizeof(float);
+}
+
+extern "C" int b200dm_conv_plan_set_gn_partials(b200dm_conv_plan* p, float* workspace, size_t ws_bytes) {
+  B2_CHECK_ARG(p && workspace, "conv_plan_set_gn_partials: null argument");
+  const size_t need = b200dm_conv_plan_gn_partials_bytes(p, nullptr);
+  if (need == 0) { b200dm_set_error("conv_plan_set_gn_partials: this plan cannot produce GroupNorm partial sums"); return B200DM_ERR_UNSUPPORTED; }
+  B2_CHECK_ARG(ws_bytes >= need, "conv_plan_set_gn_partials: workspace too small (%zu < %zu)", ws_bytes, need);
+  p->wp.gn_part = workspace;
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_gn_finalize(const float* partials, int32_t batch, int32_t rows_per_sample, int32_t c, int32_t groups,
+                                  int64_t voxels_per_sample, float eps, float* mean_rstd, void* stream) {
+  B2_CHECK_ARG(partials && mean_rstd && batch > 0 && rows_per_sample > 0 && c > 0 && groups > 0 && c % groups == 0 && voxels_per_sample > 0,
+               "gn_finalize: bad argument");
+  const double count = (double)voxels_per_sample * (c / groups);
+  B2_CHECK_CUDA(b2_launch(sweep::gn_finalize_kernel, dim3((unsigned)(batch * groups)), dim3(128), 0, (cudaStream_t)stream, partials,
+                          rows_per_sample, 1, c, groups, count, eps, mean_rstd));
   return B200DM_OK;
 }

@@ -12,7 +12,7 @@
 #include "common.cuh"
 
 namespace {
-enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN, OP_NORM_EX, OP_STATS_F32, OP_SYNC };
+enum OpKind { OP_CONV, OP_NORM, OP_GNSTATS, OP_LN, OP_SOFTMAX, OP_UPDATE, OP_ADVANCE, OP_ATTN, OP_NORM_EX, OP_STATS_F32, OP_SYNC, OP_GN_FINAL };
 constexpr int kMaxLanes = 10;
 struct Op {
   OpKind kind;
@@ -108,6 +108,15 @@ extern "C" int b200dm_program_add_gn_stats(b200dm_program* p, const b200dm_norm_
   B2_CHECK_ARG(p && d && x && mean_rstd && workspace, "program_add_gn_stats: null argument");
   Op op; op.kind = OP_GNSTATS; op.nd = *d; op.p0 = x; op.f0 = eps; op.out = mean_rstd; op.out2 = workspace; op.ws = ws_bytes;
   op.launches = 2;
+  p->push(op);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_program_add_gn_finalize(b200dm_program* p, const float* partials, int32_t batch, int32_t rows_per_sample,
+                                              int32_t c, int32_t groups, int64_t voxels_per_sample, float eps, float* mean_rstd) {
+  B2_CHECK_ARG(p && partials && mean_rstd, "program_add_gn_finalize: null argument");
+  Op op; op.kind = OP_GN_FINAL; op.p0 = partials; op.i1 = batch; op.i2 = rows_per_sample; op.nd.c0 = c; op.nd.groups = groups;
+  op.i0 = voxels_per_sample; op.f0 = eps; op.out = mean_rstd;
   p->push(op);
   return B200DM_OK;
 }
@@ -238,6 +247,9 @@ static int run_op(Op& op, void* stream) {
         rc = b200dm_norm_act_ex(&op.ned, op.p0, (const float*)op.p1, (const float*)op.p2, (const float*)op.p3, op.p4, op.p5, op.out, stream);
         break;
       case OP_SYNC: break;
+      case OP_GN_FINAL:
+        rc = b200dm_gn_finalize((const float*)op.p0, op.i1, op.i2, op.nd.c0, op.nd.groups, op.i0, op.f0, (float*)op.out, stream);
+        break;
       case OP_STATS_F32: rc = b200dm_stats_f32((const float*)op.p0, op.i1, op.i0, op.f0, (float*)op.out, op.out2, op.ws, stream); break;
     }
   }

@@ -3,6 +3,7 @@ fixed buffers.  Building happens once; ``run()`` is one ctypes call and is CUDA-
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -85,6 +86,19 @@ class Program:
         return y
 
     def gn_stats(self, x, groups, eps, note=""):
+        """(mean, rstd) per (sample, group) of x -> fp32 (B, groups, 2).  When x is the output of a conv whose kernel can
+        accumulate the sums in its epilogue (d-sweeping 32 -> 32 kernel), only a tiny fixed-order reduction is recorded;
+        otherwise a statistics pass re-reads x."""
+        plan = self.producers.get(x.data_ptr())
+        part = plan.gn_partials() if plan is not None and x.dtype == L.ACT_DTYPE and os.environ.get("B200DM_GN_PASS") != "1" else None
+        if part is not None:
+            ws, rows = part
+            mr = self.buf((x.shape[0], groups, 2), torch.float32)
+            vox = x[0].numel() // x.shape[-1]
+            check(lib().b200dm_program_add_gn_finalize(self.h, ptr(ws), x.shape[0], rows, x.shape[-1], groups, vox, eps, ptr(mr)))
+            self.hold(ws, x)
+            self.log.append(("gn_stats", note + " (from the conv epilogue)", 0.0))
+            return mr
         d = ops.make_norm_desc(x, None, 1, groups)
         ws_bytes = lib().b200dm_gn_stats_workspace(C.byref(d))
         ws = self.buf((ws_bytes // 4,), torch.float32)

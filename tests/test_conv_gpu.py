@@ -368,3 +368,45 @@ def test_conv3_head_stencil_kernel(cuda, shape):
     y16 = ops.conv3d(xd, w, bias=b.to(cuda), act="silu")
     _check_flag()
     _close(y16, O.swish(ref), tol=6e-3, what="stencil head + silu (16-bit out)")
+
+
+@pytest.mark.parametrize("shape,extras", [((2, 20, 16, 8), False), ((1, 35, 24, 12), True), ((3, 9, 48, 40), True)])
+def test_conv3_sweep32_kernel(cuda, shape, extras):
+    """C_in = C_out = 32 (the decoders' residual units, vqgan_attn_cp.py:250-276): the d-sweeping kernel -- three kd taps per
+    N = 96 MMA into a TMEM ring, weights resident, SWIZZLE_64B slabs -- on ragged volumes (partial h / w tiles, several d ranges,
+    ring wrap-around), with bias + output affine + SiLU + residual, and its GroupNorm partial sums against a direct evaluation."""
+    from b200dm import ops, _lib as L
+    B, D, H, W = shape
+    x = _rand((B, D, H, W, 32), 1)
+    w = _rand((3, 3, 3, 32, 32), 2, 1.0 / np.sqrt(27 * 32))
+    b = torch.randn(32, generator=torch.Generator().manual_seed(3))
+    xd = x.to(cuda, L.ACT_DTYPE)
+    desc = ops.make_conv_desc(L.CONV_DIRECT, B, (D, H, W), 32, 0, 32, 3, 1, "silu" if extras else None, None)
+    y = torch.empty(B, D, H, W, 32, dtype=L.ACT_DTYPE, device=cuda)
+    res = _rand((B, D, H, W, 32), 5) if extras else None
+    sc = torch.rand(32, generator=torch.Generator().manual_seed(6)) + 0.5
+    sh = torch.randn(32, generator=torch.Generator().manual_seed(7))
+    plan = ops.ConvPlan(desc, xd, ops.pack_conv_weights(desc, w, False).to(cuda), y, bias=b.to(cuda),
+                        residual=None if res is None else res.to(cuda, L.ACT_DTYPE),
+                        out_affine=(sc.to(cuda), sh.to(cuda)) if extras else None)
+    assert plan.info["halo"] == 3, "expected the d-sweeping plan"
+    ws, rows = plan.gn_partials()
+    plan.run()
+    _check_flag()
+    ref = O.conv3d(x, w, b)
+    if extras:
+        ref = O.swish(ref * sc + sh) + res
+    _close(y, ref, tol=6e-3, what=f"sweep32 {shape}")
+    # the same layer on the halo kernel (tuning switch off -> use_halo = -1 selects the per-tap GEMM): agree to one 16-bit ulp
+    y2 = ops.conv3d(xd, w, bias=b.to(cuda), use_halo=-1, act="silu" if extras else None,
+                    residual=None if res is None else res.to(cuda, L.ACT_DTYPE), out_affine=(sc.to(cuda), sh.to(cuda)) if extras else None)
+    _close(y, y2.float().cpu(), tol=8e-3, what="sweep32 vs per-tap GEMM kernel")
+    # GroupNorm statistics from the epilogue's partial sums (of the stored values) vs a direct evaluation, 8 groups
+    mr = torch.empty(B, 8, 2, dtype=torch.float32, device=cuda)
+    L.check(L.lib().b200dm_gn_finalize(L.ptr(ws), B, rows, 32, 8, D * H * W, 1e-6, L.ptr(mr), L.stream()))
+    torch.cuda.synchronize()
+    yf = y.float().cpu().reshape(B, -1, 8, 4).double()
+    mean = yf.mean(dim=(1, 3))
+    var = yf.var(dim=(1, 3), unbiased=False)
+    assert torch.allclose(mr[..., 0].cpu().double(), mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(mr[..., 1].cpu().double(), 1.0 / torch.sqrt(var + 1e-6), rtol=1e-4)

@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 #include "../3d-condtional-stable-diffusion_b200/csrc/ptx.cuh"
 
-template <int M, int N, int SBO_A, int PATTERN>
+template <int M, int N, int SBO_A, int PATTERN, int LAYOUT = 2, int SBO_B = 1024>
 __global__ void __launch_bounds__(128, 1) probe(long long* out, int iters) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -19,9 +19,9 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int iters) {
   ptx::fence_proxy_async();
   const uint32_t tm = tptr;
   if (threadIdx.x < 32) {
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(M, N);
-    const uint64_t da0 = ptx::make_smem_desc(base, 16, SBO_A, ptx::kLayoutSw128);
-    const uint64_t db0 = ptx::make_smem_desc(base + 48 * 1024, 16, 1024, ptx::kLayoutSw128);
+    constexpr uint32_t idesc = ptx::make_idesc_act(M, N);
+    const uint64_t da0 = ptx::make_smem_desc(base, 16, SBO_A, (uint64_t)LAYOUT);
+    const uint64_t db0 = ptx::make_smem_desc(base + 48 * 1024, 16, SBO_B, (uint64_t)LAYOUT);
     long long t0 = 0, t1 = 0;
     if (ptx::elect_one()) {
       t0 = clock64();
@@ -30,7 +30,10 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int iters) {
         for (int k = 0; k < 8; ++k) {
           // walk different tiles so operands are not trivially cached: 8 A offsets x 128 B rows, 4 k-steps
           const int accsel = PATTERN == 0 ? (k & 1) : (PATTERN == 1 ? 0 : (k >> 2));
-          ptx::tc_mma_f16(tm + accsel * N, da0 + (uint64_t)((k & 3) * 2 + (k >> 2) * 8), db0 + (uint64_t)((k & 3) * 2), idesc, 1u);
+          if (LAYOUT == 4)   // SWIZZLE_64B: 64-byte rows, two K = 16 steps per row; odd k: next tap (+1 row)
+            ptx::tc_mma_f16(tm + accsel * N, da0 + (uint64_t)((k & 1) * 2 + (k >> 1) * 4), db0 + (uint64_t)((k & 1) * 2 + (k >> 1) * 384), idesc, 1u);
+          else
+            ptx::tc_mma_f16(tm + accsel * N, da0 + (uint64_t)((k & 3) * 2 + (k >> 2) * 8), db0 + (uint64_t)((k & 3) * 2), idesc, 1u);
         }
       }
       ptx::tc_commit(ptx::smem_u32(&bar));
@@ -44,10 +47,10 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int iters) {
   if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tm, 512); }
 }
 
-template <int M, int N, int SBO_A, int PATTERN = 0>
+template <int M, int N, int SBO_A, int PATTERN = 0, int LAYOUT = 2, int SBO_B = 1024>
 void run(const char* name, int grid) {
   long long* d; cudaMalloc(&d, 8);
-  auto k = probe<M, N, SBO_A, PATTERN>;
+  auto k = probe<M, N, SBO_A, PATTERN, LAYOUT, SBO_B>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int iters = 2000;
   k<<<grid, 128, 100 * 1024>>>(d, 10);
@@ -61,6 +64,12 @@ void run(const char* name, int grid) {
 
 int main() {
   for (int grid : {148}) {
+    run<128, 96, 640, 1, 4, 512>("M128 N96 SW64 same acc", grid);
+    run<128, 96, 640, 2, 4, 512>("M128 N96 SW64 4+4 acc", grid);
+    run<128, 32, 640, 1, 4, 512>("M128 N32 SW64 same acc", grid);
+    run<128, 64, 640, 1, 4, 512>("M128 N64 SW64 same acc", grid);
+    run<128, 96, 1280, 1, 2, 1024>("M128 N96 SW128 same acc", grid);
+    run<128, 192, 1280, 1, 2, 1024>("M128 N192 SW128 same acc", grid);
     run<64, 8, 1024>("M64 N8 (issue floor?)", grid);
     run<64, 16, 1024>("M64 N16", grid);
     run<64, 32, 1024>("M64 N32", grid);
