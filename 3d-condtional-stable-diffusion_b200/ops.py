@@ -211,6 +211,8 @@ class ConvPlan:
                  out_affine=None):
         _dev()
         self.keep = (x0, x1, w_packed, bias, chan_bias, t_dev, residual, prelu_alpha, y) + tuple(out_affine or ())  # keep buffers alive
+        # algorithmic HBM bytes of one launch: every operand read once, the output written once
+        self.alg_bytes = float(sum(t.numel() * t.element_size() for t in (x0, x1, w_packed, residual, y) if t is not None))
         self.desc = desc
         h = C.c_void_p()
         check(lib().b200dm_conv_plan_create(C.byref(desc), ptr(x0), ptr(x1), ptr(w_packed), ptr(bias), ptr(chan_bias),

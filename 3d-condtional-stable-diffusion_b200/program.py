@@ -25,6 +25,7 @@ class Program:
         self.log = []        # (kind, note) per op, for profiles / debugging
         self.outputs = {}    # note -> output tensor (layer-by-layer parity debugging)
         self.producers = {}  # data_ptr of a conv output -> its ConvPlan (extra normalised outputs are attached there)
+        self.op_bytes = {}   # note -> algorithmic HBM bytes of that conv launch
 
     # -- allocation helper
     def buf(self, shape, dtype=torch.bfloat16):
@@ -48,6 +49,7 @@ class Program:
         plan.release()
         self.keep.extend(t for t in plan.keep if t is not None)
         kind = plan.info["halo"]
+        self.op_bytes[note] = plan.alg_bytes
         if kind == 2:   # C_out = 1 stencil-reduce kernel: HBM-bound, accounted in bytes (input read once + output written)
             nbytes = float(x0.numel() * x0.element_size() + y.numel() * y.element_size())
             self.bytes += nbytes

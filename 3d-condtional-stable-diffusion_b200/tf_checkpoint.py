@@ -276,9 +276,30 @@ def assign_by_creation_order(spec, layer_groups):
     return out
 
 
-def load_keras_checkpoint(prefix, spec, root="network", name_map=None):
+def keras_nested_variables(variables, root):
+    """{(n, 'sub/attr' path): array} for every ``<root>/layer_with_weights-<n>/<...>/<attr>`` key, nested sublayers included
+    (AttentionBlock / CrossAttentionBlock are single Keras layers whose variables sit one or two levels down:
+    ``layer_with_weights-31/query/kernel``, ``.../proj/layer_with_weights-0/kernel``)."""
+    pat = re.compile(re.escape(root.rstrip("/")) + r"/layer_with_weights-(\d+)/(.+)" + re.escape(_SUFFIX) + r"$")
+    out = {}
+    for k, v in variables.items():
+        m = pat.match(k)
+        if m and ".OPTIMIZER_SLOT" not in k:
+            out[(int(m.group(1)), m.group(2))] = v
+    return out
+
+
+def load_keras_checkpoint(prefix, spec, root="network", name_map=None, assume_creation_order=False):
     """{canonical name: float32 array} for a model with ``spec`` from the TF checkpoint ``prefix``.
-    ``name_map``: optional {canonical name: checkpoint key} that overrides the creation-order correspondence."""
+
+    ``name_map`` {canonical name: checkpoint key} is the reliable route (tools/tf_export_npz.py, run where TensorFlow is,
+    pairs tensors by Keras class + construction counter and can also write this map).  Without it the only information in the
+    file is ``layer_with_weights-<n>``, and for a FUNCTIONAL model (the U-Net) n follows Keras' depth-sorted ``model.layers``
+    -- norm1 sorts before the time-embedding Dense, a block's shortcut conv next to its conv2 -- not the order build_model
+    constructs layers in, and attention blocks nest their variables.  Zipping by n is therefore only done on request
+    (``assume_creation_order=True``: Sequential-style checkpoints, this repository's own writer) and is shape-checked; the
+    default refuses instead of guessing.  Not validated against a checkpoint written by TensorFlow (none ships with the
+    reference)."""
     variables = read_checkpoint(prefix)
     if name_map is not None:
         out = {}
@@ -288,6 +309,13 @@ def load_keras_checkpoint(prefix, spec, root="network", name_map=None):
                 raise ValueError(f"{name_map[name]} has shape {tuple(a.shape)}, {name} expects {tuple(shape)}")
             out[name] = a.astype(np.float32)
         return out
+    nested = [k for k in keras_nested_variables(variables, root) if "/" in k[1]]
+    if nested or not assume_creation_order:
+        raise ValueError(
+            f"{prefix}: the U-Net's variables are keyed by Keras' depth-sorted layer index (layer_with_weights-<n>"
+            + (f", {len(nested)} of them nested inside block layers" if nested else "") + "), which does not determine the layer without "
+            "TensorFlow.  Export canonical names with tools/tf_export_npz.py (inside the reference's environment) and load the .npz, "
+            "or pass name_map={canonical name: checkpoint key}; assume_creation_order=True zips flat keys by n (shape-checked).")
     return assign_by_creation_order(spec, keras_layer_variables(variables, root))
 
 

@@ -140,13 +140,16 @@ class UNet:
         self._per_sample = None
         self.weights_version += 1
 
-    def load_weights(self, path, name_map=None):
-        """``path``: a flat .npz of canonical names, or the prefix of a TensorFlow checkpoint written by the reference's
-        ``save_weights`` (``<path>.index`` + ``<path>.data-*``, read without TensorFlow: tf_checkpoint.py)."""
+    def load_weights(self, path, name_map=None, assume_creation_order=False):
+        """``path``: a flat .npz of canonical names (tools/tf_export_npz.py writes one from a reference checkpoint), or the prefix
+        of a TensorFlow checkpoint (``<path>.index`` + ``<path>.data-*``, read without TensorFlow: tf_checkpoint.py) together
+        with ``name_map`` -- a TF checkpoint of the functional U-Net alone does not say which layer each
+        ``layer_with_weights-<n>`` is (see tf_checkpoint.load_keras_checkpoint), so without a map it is refused."""
         import os as _os
         if not str(path).endswith(".npz") and _os.path.exists(str(path) + ".index"):
             from . import tf_checkpoint as T
-            self.set_weights(T.load_keras_checkpoint(str(path), self.spec, root="network", name_map=name_map))
+            self.set_weights(T.load_keras_checkpoint(str(path), self.spec, root="network", name_map=name_map,
+                                                     assume_creation_order=assume_creation_order))
         else:
             self.set_weights(Wt.load_npz(path))
 

@@ -80,17 +80,34 @@ def test_unet_weights_from_object_graph_checkpoint(tmp_path):
     vars_["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"] = np.array(3, dtype=np.int64)
     prefix = str(tmp_path / "dm3d-1")
     T.write_checkpoint(prefix, vars_, checksum_limit=1 << 14)
-    loaded = T.load_keras_checkpoint(prefix, net.spec, root="network")
+    # a bare TF checkpoint of the functional U-Net does not determine the layer of each layer_with_weights-<n> (Keras sorts
+    # model.layers by depth): refused by default, zipped by n only on request (this file was written in creation order)
+    with pytest.raises(ValueError, match="tf_export_npz"):
+        T.load_keras_checkpoint(prefix, net.spec, root="network")
+    loaded = T.load_keras_checkpoint(prefix, net.spec, root="network", assume_creation_order=True)
     assert set(loaded) == set(params)
     for k in params:
         assert np.array_equal(loaded[k], params[k].numpy()), k
     net2 = b200dm.build_model(8, 8, [64, 128, 256], [False, False, True, True])
-    net2.load_weights(prefix)                      # same call the reference makes (dm3d.py:408-414)
+    net2.load_weights(prefix, assume_creation_order=True)
     assert all(np.array_equal(net2.params[k].numpy(), params[k].numpy()) for k in params)
+    # the reliable route: an explicit {canonical name: checkpoint key} map (what the TF-side exporter knows)
+    name_map = {name: f"network/layer_with_weights-{n}/{T._ATTR_OF_LEAF.get(leaf, leaf)}/.ATTRIBUTES/VARIABLE_VALUE"
+                for n, (stem, tensors) in enumerate(layers) for name, leaf in tensors}
+    net4 = b200dm.build_model(8, 8, [64, 128, 256], [False, False, True, True])
+    net4.load_weights(prefix, name_map=name_map)
+    assert all(np.array_equal(net4.params[k].numpy(), params[k].numpy()) for k in params)
+    # nested block variables (AttentionBlock is one Keras layer) are recognised and never zipped by order
+    vars_n = dict(vars_)
+    vars_n["network/layer_with_weights-900/query/kernel/.ATTRIBUTES/VARIABLE_VALUE"] = np.zeros((4, 4), np.float32)
+    T.write_checkpoint(str(tmp_path / "nested"), vars_n, checksum_limit=1 << 14)
+    assert (900, "query/kernel") in T.keras_nested_variables(T.read_checkpoint(str(tmp_path / "nested")), "network")
+    with pytest.raises(ValueError, match="nested"):
+        T.load_keras_checkpoint(str(tmp_path / "nested"), net.spec, assume_creation_order=True)
     # a checkpoint of a different architecture is rejected with the offending shapes
     net3 = b200dm.build_model(8, 16, [64, 128, 256], [False, False, True, True])
     with pytest.raises(ValueError):
-        T.load_keras_checkpoint(prefix, net3.spec)
+        T.load_keras_checkpoint(prefix, net3.spec, assume_creation_order=True)
 
 
 def test_first_stage_weights_from_checkpoint(tmp_path):
@@ -187,3 +204,65 @@ def test_first_stage_npz_roundtrip_includes_encoder(tmp_path):
     for n, _, _ in vq.encoder.spec:
         assert np.array_equal(vq.encoder.params[n].numpy(), flat[f"encoder.{n}"]), n
     assert vq.encoder.weights_missing is None
+
+
+def test_tf_side_exporter_matches_by_class_creation_order_not_by_layer_order():
+    """tools/tf_export_npz.py (runs inside the reference's TensorFlow environment) pairs tensors by Keras class + auto-name
+    counter, so neither the DEPTH-sorted ``model.layers`` of a functional model nor nesting inside custom blocks matters.
+    Mock of the Keras surface it touches: layers named ``<class>_<n>`` in construction order, some nested in container layers,
+    handed over in a shuffled order (zip-by-order exporters silently mispair)."""
+    import importlib.util
+    import random
+    import b200dm
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec_ = importlib.util.spec_from_file_location("tf_export_npz", os.path.join(ROOT, "tools", "tf_export_npz.py"))
+    E = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(E)
+
+    class W:
+        def __init__(self, name, a):
+            self.name, self.a = name, a
+
+        def numpy(self):
+            return self.a
+
+    class Layer:
+        def __init__(self, name, weights=(), children=()):
+            self.name, self.weights, self.children = name, list(weights), list(children)
+
+        def _flatten_layers(self, include_self=False, recursive=True):
+            for c in self.children:
+                yield c
+                if recursive:
+                    yield from c._flatten_layers(False, True)
+
+    net = b200dm.build_model(8, 8, [64, 128, 256], [False, False, True, True], context_dim=1)
+    rng = np.random.default_rng(0)
+    snake = {"Conv3D": "conv3d", "Dense": "dense", "BatchNormalization": "batch_normalization", "LayerNormalization": "layer_normalization",
+             "Embedding": "embedding"}
+    counters, flat, want = {}, [], {}
+    for stem, cls, tensors in E.spec_groups(net.spec):
+        i = counters.get(cls, 0)
+        counters[cls] = i + 1
+        ws = []
+        for name, leaf, shape in tensors:
+            a = rng.standard_normal(shape).astype(np.float32)
+            want[name] = a
+            ws.append(W(f"{snake[cls]}_{i + 7}/{E.LEAF_ATTR[leaf]}:0", a))
+        layer = type(cls, (Layer,), {})(f"{snake[cls]}_{i + 7}", ws)   # counters start at 7: another model was built first
+        flat.append((stem, layer))
+    # nest the sublayers of every attention block inside a container (a custom Keras Layer), then shuffle everything
+    top, blocks = [], {}
+    for stem, layer in flat:
+        if ".attn." in stem and not stem.endswith("ctxmlp"):
+            blocks.setdefault(stem.rsplit(".", 1)[0], []).append(layer)
+        else:
+            top.append(layer)
+    for k, (bname, subs) in enumerate(blocks.items()):
+        random.Random(k).shuffle(subs)
+        top.append(Layer(f"cross_attention_block_{k}", weights=[w for s in subs for w in s.weights], children=subs))
+    random.Random(1).shuffle(top)
+    got = E.export_by_class(Layer("model", children=top), net.spec, "U-Net")
+    assert set(got) == set(want)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k

@@ -13,13 +13,19 @@ ki, vi = h.index("Kernel Name"), h.index("Metric Value")
 L = []
 for r in rows[1:]:
     n = re.sub(r"\(.*$", "", re.sub(r"^void ", "", r[ki]))
-    n = re.sub(r"<unnamed>::|\(anonymous namespace\)::|halo::", "", n)
+    n = re.sub(r"<unnamed>::|\(anonymous namespace\)::|halo::|sweep::|stencil::", "", n)
     L.append((n, float(r[vi].replace(",", "")) / 1000.0))
-marks = [i for i, (n, _) in enumerate(L) if n.startswith("step_advance_kernel")]
-assert len(marks) >= 2, "need two step_advance_kernel launches in the list"
-seq = L[marks[-2]:marks[-1]]
+if what == "decode":   # one quantize + decode pass: from the last vq_kernel launch to the decoder's head (stencil) launch after it
+    a = max(i for i, (n, _) in enumerate(L) if n.startswith("vq_kernel"))
+    b = min(i for i, (n, _) in enumerate(L) if i > a and "conv_stencil" in n)
+    seq = L[a:b + 1]
+else:
+    marks = [i for i, (n, _) in enumerate(L) if n.startswith("step_advance")]
+    assert len(marks) >= 2, "need two step_advance launches in the list"
+    seq = L[marks[-2]:marks[-1]]
 with open(f"profiles/{tag}_launches_{what}.csv", "w") as f:
-    f.write(f"# {tag}: {cmd}\n# one cfg-2 denoise step (graph replay): every launch from step_advance to the fused update; cold-cache, serialised times\n")
+    f.write(f"# {tag}: {cmd}\n# " + ("one cfg-3 quantize + decode pass (B=16): vq_kernel .. the decoder's head" if what == "decode" else
+            "one cfg-2 denoise step (graph replay): every launch from step_advance to the fused update") + "; cold-cache, serialised times\n")
     f.write("index,kernel,us\n")
     for i, (n, u) in enumerate(seq):
         f.write(f'{i},"{n}",{u:.3f}\n')
@@ -28,7 +34,7 @@ agg = collections.OrderedDict()
 for n, u in seq:
     a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += u
 with open(f"profiles/{tag}_launches_{what}_summary.csv", "w") as f:
-    f.write(f"# {tag}: per-kernel totals of one cfg-2 step under ncu (cold-cache, serialised; compare SHARES)\n")
+    f.write(f"# {tag}: per-kernel totals of one " + ("cfg-3 quantize + decode pass" if what == "decode" else "cfg-2 step") + " under ncu (cold-cache, serialised; compare SHARES)\n")
     f.write("# conv_halo_kernel<BLOCK_N, TD, NS, NB, TPS, STAGED, PAIR, CG2>; conv_halo_up_kernel<BLOCK_N, NS, NB, PAIR>; conv_igemm_kernel<BLOCK_N, NSTAGE, CMODE>\n")
     f.write("kernel,launches,total_us,share\n")
     for n, (c, u) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
