@@ -47,6 +47,7 @@ def set_precision(name: str):
     ACT_DTYPE = torch.bfloat16 if name == "bf16" else torch.float16
 
 F32, BF16 = 0, 1
+ERR_UNSUPPORTED = -3
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 CONV_DIRECT, CONV_PARITY, CONV_BATCHED_GEMM = 0, 1, 2
 ACT = {None: ACT_NONE, "none": ACT_NONE, "silu": ACT_SILU, "swish": ACT_SILU, "relu": ACT_RELU}
@@ -128,6 +129,7 @@ _SIGS = {
     "b200dm_conv_plan_add_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b200dm_conv_plan_set_side_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b200dm_conv_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "b200dm_conv_plan_set_input_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "b200dm_conv_plan_gn_partials_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(C.c_int32)]),
     "b200dm_conv_plan_set_gn_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200dm_gn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
@@ -174,6 +176,12 @@ def lib():
             raise B200dmError(f"{_LIB_PATH} stores {got}, expected {_precision}: rebuild (python __graft_entry__.py build)")
         _lib = l
     return _lib
+
+
+def tuning_env(name: str, default: str) -> str:
+    """Experiment switches (B200DM_CHAINS, B200DM_LANES, B200DM_SHADOW, ...) are honoured only when B200DM_TUNING=1 is also set, like
+    the native library's: a production process's environment cannot reconfigure the program by accident."""
+    return os.environ.get(name, default) if os.environ.get("B200DM_TUNING") == "1" else default
 
 
 def check(rc: int):

@@ -1354,3 +1354,14 @@ extern "C" int b200dm_gn_finalize(const float* partials, int32_t batch, int32_t 
                           rows_per_sample, 1, c, groups, count, eps, mean_rstd));
   return B200DM_OK;
 }
+
+// Fold the consumer-side GroupNorm + activation into the conv's operand path (d-sweeping kernel only): the conv then computes
+// conv(act(gamma * (x - mean) * rstd + beta)) from the RAW x, mean / rstd per (sample, group) read from `mean_rstd` at run time.
+extern "C" int b200dm_conv_plan_set_input_norm(b200dm_conv_plan* p, const float* mean_rstd, const float* gamma, const float* beta,
+                                               int32_t groups, int32_t act) {
+  B2_CHECK_ARG(p && mean_rstd && gamma && beta, "conv_plan_set_input_norm: null argument");
+  if (!p->sweep) { b200dm_set_error("conv_plan_set_input_norm: this plan's kernel has no input transform"); return B200DM_ERR_UNSUPPORTED; }
+  B2_CHECK_ARG(groups > 0 && 32 % groups == 0, "conv_plan_set_input_norm: groups must divide 32");
+  p->wp.in_mr = mean_rstd; p->wp.in_gamma = gamma; p->wp.in_beta = beta; p->wp.in_groups = groups; p->wp.in_act = act;
+  return B200DM_OK;
+}

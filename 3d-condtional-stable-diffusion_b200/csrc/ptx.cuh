@@ -53,6 +53,21 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* fl
   }
   return true;
 }
+// The same wait for roles that are NOT on the critical path (producers, epilogue and transform warps): between polls the warp sleeps,
+// so it does not compete for issue slots with the one warp per sub-partition that paces the kernel (a spinning try_wait loop is ~6
+// instructions per poll: four spinners per sub-partition left the MMA-issuing / transforming warp a fifth of the issue slots).
+__device__ __forceinline__ bool mbar_wait_sleep(uint32_t bar, uint32_t parity, int* flag, int code, unsigned ns = 64) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > 2000000000LL) {
+      if (flag) atomicExch(flag, code);
+      return false;
+    }
+  }
+  return true;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -97,7 +97,7 @@ class DiffusionModel:
         # default 1: measured on B200 (cfg-2, B=8) 1 chain 4.98 ms/step, 2 chains 5.22, 4 chains 5.31 -- the persistent
         # 148-CTA conv kernels of one chain leave no SMs for the other chain's small kernels, and smaller sub-batches
         # make the 8^3-level GEMM grids even thinner
-        want = int(os.environ.get("B200DM_CHAINS", "1"))
+        want = int(L.tuning_env("B200DM_CHAINS", "1"))
         c = max(1, min(want, batch))
         while batch % c:
             c -= 1

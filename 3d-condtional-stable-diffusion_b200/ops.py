@@ -253,6 +253,16 @@ class ConvPlan:
         check(lib().b200dm_conv_plan_run(self.h, stream()))
         return self.y
 
+    def set_input_norm(self, mean_rstd, gamma, beta, groups, act=None):
+        """Fold act(GroupNorm(x)) of the conv's INPUT into its operand path (x stays raw in HBM).  False when the plan's kernel has
+        no input transform (the caller then runs a normalisation pass)."""
+        rc = lib().b200dm_conv_plan_set_input_norm(self.h, ptr(mean_rstd), ptr(gamma), ptr(beta), groups, L.ACT[act])
+        if rc == L.ERR_UNSUPPORTED:
+            return False
+        check(rc)
+        self.keep = self.keep + (mean_rstd, gamma, beta)
+        return True
+
     def gn_partials(self):
         """GroupNorm partial sums as a by-product of this conv: -> (workspace fp32 (B * rows, C, 2), rows per sample), or None
         when the plan's kernel cannot produce them (the caller then runs a statistics pass over y)."""

@@ -41,9 +41,13 @@ class Program:
 
     # -- ops
     def conv(self, desc, x0, w_packed, y, x1=None, bias=None, chan_bias=None, t_dev=None, residual=None,
-             prelu_alpha=None, out_affine=None, note="", side=None):
+             prelu_alpha=None, out_affine=None, note="", side=None, in_norm=None):
+        """``in_norm`` = (mean_rstd, gamma, beta, groups, act): the conv reads act(GroupNorm(x0)) with the normalisation folded
+        into its operand path; returns None (nothing recorded) when the plan's kernel cannot do that."""
         plan = ops.ConvPlan(desc, x0, w_packed, y, x1=x1, bias=bias, chan_bias=chan_bias, t_dev=t_dev,
                             residual=residual, prelu_alpha=prelu_alpha, out_affine=out_affine)
+        if in_norm is not None and not plan.set_input_norm(*in_norm):
+            return None
         self.side_ok = side is not None and plan.set_side_norm(*side)   # (y_side, scale, shift, act)
         check(lib().b200dm_program_add_conv(self.h, plan.h))
         plan.release()
@@ -92,7 +96,7 @@ class Program:
         accumulate the sums in its epilogue (d-sweeping 32 -> 32 kernel), only a tiny fixed-order reduction is recorded;
         otherwise a statistics pass re-reads x."""
         plan = self.producers.get(x.data_ptr())
-        part = plan.gn_partials() if plan is not None and x.dtype == L.ACT_DTYPE and os.environ.get("B200DM_GN_PASS") != "1" else None
+        part = plan.gn_partials() if plan is not None and x.dtype == L.ACT_DTYPE and L.tuning_env("B200DM_GN_PASS", "0") != "1" else None
         if part is not None:
             ws, rows = part
             mr = self.buf((x.shape[0], groups, 2), torch.float32)

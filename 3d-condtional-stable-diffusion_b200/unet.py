@@ -174,12 +174,12 @@ class UNet:
         # epilogues, which are on the critical path, by more than the streaming pass costs.  Off unless B200DM_FUSE_NORMS=1.
         self._wcache = {}
         self._lane_base, self._half = 0, (0, batch)
-        self.fuse_norms = os.environ.get("B200DM_FUSE_NORMS", "0") == "1"
+        self.fuse_norms = L.tuning_env("B200DM_FUSE_NORMS", "0") == "1"
         # norm1 as a side output of the 1^3 shortcut conv (b200dm_conv_plan_set_side_norm): measured SLOWER on B200 (cfg-2:
         # 3.35 vs 3.15 ms/step) -- one-tile CTAs serialise load -> transform -> store, while the stand-alone pass is a
         # pipelined HBM stream at 4.9 TB/s.  Off unless B200DM_SIDE_NORM=1 (kept, tested, for a persistent variant).
-        self.side_norm = os.environ.get("B200DM_SIDE_NORM", "0") == "1"
-        self.lanes = os.environ.get("B200DM_LANES", "1") != "0"   # branch-parallel CrossAttentionBlock (program lanes)
+        self.side_norm = L.tuning_env("B200DM_SIDE_NORM", "0") == "1"
+        self.lanes = L.tuning_env("B200DM_LANES", "1") != "0"   # branch-parallel CrossAttentionBlock (program lanes)
         self.t_dev = t_dev if t_dev is not None else torch.zeros(4, dtype=torch.int32, device=dev)   # [t, t_prev, seq idx, -]
         self.per_sample_t, self._temb_rows = bool(per_sample_t), []
         g = lambda n: P[n].to(dev).contiguous()  # noqa: E731
@@ -379,7 +379,7 @@ class UNet:
         # (BN + swish with the CONSUMER block's parameters, dm3d.py:235-236) are therefore run on lane 4 while the 8^3 phase
         # executes on the other lanes, and the up-path passes shrink to the x half.
         self.shadow_norms, self.shadow_joined = {}, False
-        use_shadow = os.environ.get("B200DM_SHADOW", "1") != "0" and len(cfg.widths) >= 2
+        use_shadow = L.tuning_env("B200DM_SHADOW", "1") != "0" and len(cfg.widths) >= 2
         consumer, stack = {}, []          # push index -> the up-path ResidualBlock that pops it
         npush = 0
         for b in self.blocks:
@@ -439,7 +439,7 @@ class UNet:
         blocks = self.blocks
         deep = [i for i, b in enumerate(blocks) if b.get("s") == deepest and b["kind"] in ("res", "attn", "up")]
         i0, i1 = (deep[0], deep[-1] + 1) if deep else (len(blocks), len(blocks))
-        split = (os.environ.get("B200DM_SPLIT_DEEP", "0") == "1" and self.lanes and batch >= 4 and batch % 2 == 0 and deep
+        split = (L.tuning_env("B200DM_SPLIT_DEEP", "0") == "1" and self.lanes and batch >= 4 and batch % 2 == 0 and deep
                  and blocks[i1 - 1]["kind"] == "up")
         i = 0
         while i < len(blocks):

@@ -264,6 +264,11 @@ int b200dm_conv_plan_info(const b200dm_conv_plan* p, int32_t* halo, int32_t* blo
  * accumulate per-(work item, channel) partial sums of the STORED values into `workspace` = float[batch * rows_per_sample][C][2];
  * b200dm_gn_finalize reduces them in a fixed order (bit-reproducible) to (mean, rstd) per (sample, group).
  * _bytes returns 0 when the plan cannot produce partials. */
+/* The consumer-side GroupNorm + activation folded into the conv's operand path (tfa GroupNormalization -> swish -> Conv3D,
+ * vqgan_attn_cp.py:262-270): the plan then reads the RAW tensor and normalises each tile in shared memory with the (mean, rstd)
+ * found in `mean_rstd` (batch, groups, 2) at run time.  B200DM_ERR_UNSUPPORTED when the plan's kernel has no input transform. */
+int b200dm_conv_plan_set_input_norm(b200dm_conv_plan* plan, const float* mean_rstd, const float* gamma, const float* beta,
+                                    int32_t groups, int32_t act);
 size_t b200dm_conv_plan_gn_partials_bytes(const b200dm_conv_plan* plan, int32_t* rows_per_sample);
 int b200dm_conv_plan_set_gn_partials(b200dm_conv_plan* plan, float* workspace, size_t ws_bytes);
 int b200dm_gn_finalize(const float* partials, int32_t batch, int32_t rows_per_sample, int32_t c, int32_t groups,

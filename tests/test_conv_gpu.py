@@ -410,3 +410,38 @@ def test_conv3_sweep32_kernel(cuda, shape, extras):
     var = yf.var(dim=(1, 3), unbiased=False)
     assert torch.allclose(mr[..., 0].cpu().double(), mean, rtol=1e-4, atol=1e-5)
     assert torch.allclose(mr[..., 1].cpu().double(), 1.0 / torch.sqrt(var + 1e-6), rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape,groups", [((2, 20, 16, 8), 32), ((1, 35, 24, 12), 8), ((2, 7, 40, 24), 32)])
+def test_conv3_sweep32_input_groupnorm_fold(cuda, shape, groups):
+    """Conv3D(SiLU(GroupNorm(x))) (vqgan_attn_cp.py:262-270) with the normalisation folded into the conv's operand path: the
+    kernel normalises every landed slab in shared memory, halo voxels outside the volume stay zero ('same' padding pads the
+    NORMALISED tensor).  Reference: the separate GN + SiLU pass (rounded to the 16-bit storage type) followed by the conv."""
+    from b200dm import ops, _lib as L
+    B, D, H, W = shape
+    x = _rand((B, D, H, W, 32), 1) * 1.7 + 0.3
+    x = _r(x)
+    w = _rand((3, 3, 3, 32, 32), 2, 1.0 / np.sqrt(27 * 32))
+    b = torch.randn(32, generator=torch.Generator().manual_seed(3))
+    gamma = torch.rand(32, generator=torch.Generator().manual_seed(8)) + 0.5
+    beta = torch.randn(32, generator=torch.Generator().manual_seed(9)) * 0.2
+    xg = x.reshape(B, -1, groups, 32 // groups).double()
+    mean, var = xg.mean(dim=(1, 3)), xg.var(dim=(1, 3), unbiased=False)
+    mr = torch.stack([mean, 1.0 / torch.sqrt(var + 1e-6)], -1).float()           # (B, groups, 2)
+    a = mr[..., 1].repeat_interleave(32 // groups, 1) * gamma                   # (B, 32)
+    sh = beta - mr[..., 0].repeat_interleave(32 // groups, 1) * a
+    h = O.swish(x * a[:, None, None, None, :] + sh[:, None, None, None, :]).to(L.ACT_DTYPE).float()
+    ref = O.conv3d(h, w, b)
+    xd = x.to(cuda, L.ACT_DTYPE)
+    desc = ops.make_conv_desc(L.CONV_DIRECT, B, (D, H, W), 32, 0, 32, 3, 1, None, None)
+    y = torch.empty(B, D, H, W, 32, dtype=L.ACT_DTYPE, device=cuda)
+    plan = ops.ConvPlan(desc, xd, ops.pack_conv_weights(desc, w, False).to(cuda), y, bias=b.to(cuda))
+    assert plan.set_input_norm(mr.to(cuda), gamma.to(cuda), beta.to(cuda), groups, "silu")
+    plan.run()
+    _check_flag()
+    _close(y, ref, tol=8e-3, what=f"sweep32 with folded GN+SiLU {shape}")
+    # a plan without an input transform says so instead of silently ignoring the request
+    desc2 = ops.make_conv_desc(L.CONV_DIRECT, B, (D, H, W), 32, 0, 64, 3, 1, None, None)
+    w2 = _rand((3, 3, 3, 32, 64), 2, 0.05)
+    plan2 = ops.ConvPlan(desc2, xd, ops.pack_conv_weights(desc2, w2, False).to(cuda), torch.empty(B, D, H, W, 64, dtype=L.ACT_DTYPE, device=cuda))
+    assert not plan2.set_input_norm(mr.to(cuda), gamma.to(cuda), beta.to(cuda), groups, "silu")

@@ -190,3 +190,13 @@ def test_sharded_generate_world2_gloo_matches_single_process(total):
     ctx = [i % 2 for i in range(total)]
     want = _FakeModel().generate((total, 2, 2, 2, 3), seed=5, sample_id0=0, context=ctx).numpy()
     assert np.array_equal(got, want)              # identical regardless of how many ranks produced it
+
+
+def test_tuning_switches_need_the_tuning_gate(monkeypatch):
+    """Experiment switches of the Python layer (and of the native library: conv.cu tuning_env) are ignored unless B200DM_TUNING=1."""
+    from b200dm import _lib as L
+    monkeypatch.delenv("B200DM_TUNING", raising=False)
+    monkeypatch.setenv("B200DM_CHAINS", "4")
+    assert L.tuning_env("B200DM_CHAINS", "1") == "1"
+    monkeypatch.setenv("B200DM_TUNING", "1")
+    assert L.tuning_env("B200DM_CHAINS", "1") == "4"

@@ -106,13 +106,14 @@ def test_unet_cond_forward_split_deep_phase(cuda):
     ctx = torch.tensor([0, 1, 1, 0])
     tt = torch.full((B,), 33)
     os.environ["B200DM_SPLIT_DEEP"] = "1"
+    os.environ["B200DM_TUNING"] = "1"      # experiment switches are read only under B200DM_TUNING=1
     try:
         net, ou, P = _unet_pair(S, C_lat, True)
         net.compile(B, 50)
         assert any(note == "0->5" for kind, note, _ in net.prog.log if kind == "sync"), "deep phase was not split"
         y = net([x.to(cuda), tt, ctx])
     finally:
-        del os.environ["B200DM_SPLIT_DEEP"]
+        del os.environ["B200DM_SPLIT_DEEP"], os.environ["B200DM_TUNING"]
     r_e = rel(y, ou.forward(P, x, tt, ctx=ctx, emu=Emu(True)))
     print(f"cond, split deep phase: rel-L2 vs bf16-emulating oracle {r_e:.3e}")
     assert r_e <= 2.5e-2

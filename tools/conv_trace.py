@@ -16,6 +16,9 @@ x0 = torch.randn(B, D, H, W, c0, device=dev).bfloat16()
 x1 = torch.randn(B, D, H, W, c1, device=dev).bfloat16() if c1 else None
 y = torch.empty(B, D, H, W, cout, device=dev, dtype=torch.bfloat16)
 plan = ops.ConvPlan(desc, x0, wp, y, x1=x1, bias=torch.zeros(cout, device=dev))
+if os.environ.get("XFORM") == "1":   # d-sweeping kernel: folded input GroupNorm + SiLU
+    mr = torch.stack([torch.zeros(B, 32), torch.ones(B, 32)], -1).to(dev)
+    assert plan.set_input_norm(mr, torch.ones(32, device=dev), torch.zeros(32, device=dev), 32, "silu")
 for _ in range(3):
     plan.run()
 tr = torch.zeros(4 * 2048, dtype=torch.int64, device=dev)
@@ -25,7 +28,8 @@ torch.cuda.synchronize()
 t = tr.cpu().view(4, 2048)
 names = {1: "tile:begin", 2: "tile:tmem_empty ok", 3: "kd:slabs ready", 4: "kd:issued", 5: "b?", 6: "b:waited", 7: "b:pre", 10: "epi:wait", 11: "epi:tmem_full ok", 12: "epi:done"}
 t0 = min(int(v) >> 8 for v in t[0] if int(v) != 0)
-for region, label in ((0, "MMA"), (1, "EPI"), (2, "SLAB")):
+names.update({30: "xf:wait", 31: "xf:slab landed", 32: "xf:done", 33: "xf:signalled"})
+for region, label in ((0, "MMA"), (1, "EPI"), (2, "SLAB"), (3, "XFORM")):
     prev = None
     out = []
     for v in t[region]:
