@@ -116,6 +116,9 @@ _SIGS = {
     "b200dm_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "b200dm_vq_argmin_gather": (C.c_int, [C.POINTER(VqDesc)] + [C.c_void_p] * 7),
     "b200dm_vq_prepare": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200dm_vq_tc_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "b200dm_vq_prepare_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200dm_vq_argmin_gather_tc": (C.c_int, [C.POINTER(VqDesc)] + [C.c_void_p] * 9),
     "b200dm_dense_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "b200dm_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "b200dm_conv_packed_weight_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),

@@ -6,6 +6,10 @@
 // products flip near-ties); 128x128 block tile, 8x8 register tile, the (N,K) distance matrix
 // never leaves the SM.
 #include "common.cuh"
+#include "vq_tc.cuh"
+#include <stdlib.h>
+
+int* b200dm_dbg_flag_ptr();
 
 namespace {
 
@@ -295,5 +299,97 @@ extern "C" int b200dm_vq_argmin_gather(const b200dm_vq_desc* d, const void* x, c
   else
     vq_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(*d, x, codebook_kd, code_sqnorm, idx, q, hist);
   B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}
+
+// ---- tensor-core candidate search + exact recheck (vq_tc.cuh): same indices as vq_kernel, bit for bit ----------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn vq_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+size_t vq_tc_smem_bytes(int k, int d) {
+  const int dc = d / 64;
+  return 1024 + (size_t)(2 * dc + vqtc::kNSB) * vqtc::kTile + (size_t)k * 4 + 128 * 4 * 2 + (size_t)128 * vqtc::kCap * 8 + 128 * 4 +
+         (2 * vqtc::kNSB + 4) * 8 + 16;
+}
+bool vq_tc_supported(int k, int d) {
+  return k >= 128 && k % 128 == 0 && d >= 64 && d % 64 == 0 && d <= 256 && vq_tc_smem_bytes(k, d) <= 232448;
+}
+// workspace: [e_hi K*D fp16][e_lo K*D fp16][meta 4 fp32]
+size_t vq_tc_ws_bytes(int k, int d) { return (size_t)k * d * 4 + 16; }
+
+}  // namespace
+
+extern "C" size_t b200dm_vq_tc_workspace_bytes(int32_t k, int32_t d) { return vq_tc_supported(k, d) ? vq_tc_ws_bytes(k, d) : 0; }
+
+extern "C" int b200dm_vq_prepare_tc(const float* codebook_kd, const float* code_sqnorm, int32_t k, int32_t d, void* tc_ws, void* stream) {
+  B2_CHECK_ARG(codebook_kd && code_sqnorm && tc_ws, "vq_prepare_tc: null argument");
+  B2_CHECK_ARG(vq_tc_supported(k, d), "vq_prepare_tc: shape not supported by the tensor-core search (need k %% 128 == 0, d in {64,128,192,256})");
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(tc_ws) & 127) == 0, "vq_prepare_tc: workspace must be 128-byte aligned");
+  __half* ehi = reinterpret_cast<__half*>(tc_ws);
+  __half* elo = ehi + (size_t)k * d;
+  float* meta = reinterpret_cast<float*>(elo + (size_t)k * d);
+  vqtc::vq_tc_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(codebook_kd, code_sqnorm, k, d, ehi, elo, meta);
+  B2_CHECK_LAUNCH();
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_vq_argmin_gather_tc(const b200dm_vq_desc* d, const void* x, const float* codebook_kd, const float* code_sqnorm,
+                                          const void* tc_ws, int64_t* idx, void* q, int32_t* hist, uint64_t* stats, void* stream) {
+  B2_CHECK_ARG(d, "vq_argmin_gather_tc: null desc");
+  if (d->n == 0) return B200DM_OK;
+  B2_CHECK_ARG(x && codebook_kd && code_sqnorm && tc_ws && idx, "vq_argmin_gather_tc: null argument");
+  B2_CHECK_ARG(d->n > 0 && vq_tc_supported(d->k, d->d), "vq_argmin_gather_tc: shape not supported (b200dm_vq_tc_workspace_bytes() == 0): use b200dm_vq_argmin_gather");
+  B2_CHECK_ARG(d->x_dtype == B200DM_F32 || d->x_dtype == B200DM_BF16, "vq_argmin_gather_tc: bad x dtype");
+  B2_CHECK_ARG(d->q_dtype == B200DM_F32 || d->q_dtype == B200DM_BF16, "vq_argmin_gather_tc: bad q dtype");
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "vq_argmin_gather_tc: x must be 16-byte aligned");
+  const int64_t blocks = (d->n + 127) / 128;
+  B2_CHECK_ARG(blocks <= 0x7fffffff, "vq_argmin_gather_tc: too many rows");
+  EncodeTiledFn enc = vq_encode_fn();
+  if (!enc) { b200dm_set_error("vq_argmin_gather_tc: cuTensorMapEncodeTiled unavailable"); return B200DM_ERR_CUDA; }
+  CUtensorMap maps[2];
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)d->d, (cuuint64_t)d->k};
+    cuuint64_t strides[1] = {(cuuint64_t)d->d * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t es[2] = {1, 1};
+    void* base = (char*)const_cast<void*>(tc_ws) + (size_t)i * d->k * d->d * 2;
+    CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200dm_set_error("vq_argmin_gather_tc: cuTensorMapEncodeTiled failed: %d", (int)r); return B200DM_ERR_CUDA; }
+  }
+  vqtc::Params p;
+  p.n = d->n; p.k = d->k; p.d = d->d; p.x = x; p.x_f32 = d->x_dtype == B200DM_F32; p.q_f32 = d->q_dtype == B200DM_F32;
+  p.cb = codebook_kd; p.esq = code_sqnorm;
+  p.meta = reinterpret_cast<const float*>((const char*)tc_ws + (size_t)d->k * d->d * 4);
+  p.idx = idx; p.q = q; p.hist = hist; p.dbg = b200dm_dbg_flag_ptr();
+  p.margin_scale = 1.0f;
+  p.stats = reinterpret_cast<unsigned long long*>(stats);
+  {   // test hook (B200DM_TUNING=1 only): shrink the candidate margin to measure the headroom of the error bound
+    const char* t = getenv("B200DM_TUNING");
+    const char* m = (t && t[0] == '1') ? getenv("B200DM_VQ_MARGIN_SCALE") : nullptr;
+    if (m) p.margin_scale = (float)atof(m);
+  }
+  const size_t smem = vq_tc_smem_bytes(d->k, d->d);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d->x_dtype == B200DM_BF16) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(vqtc::vq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CHECK_CUDA(b2_launch(vqtc::vq_tc_kernel<true>, dim3((unsigned)blocks), dim3(vqtc::kThreads), smem, s, maps[0], maps[1], p));
+  } else {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(vqtc::vq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CHECK_CUDA(b2_launch(vqtc::vq_tc_kernel<false>, dim3((unsigned)blocks), dim3(vqtc::kThreads), smem, s, maps[0], maps[1], p));
+  }
   return B200DM_OK;
 }

@@ -50,7 +50,8 @@ class VectorQuantizer:
             L.require_gpu()
             dev = torch.device("cuda", torch.cuda.current_device())
             kd = (self.embeddings.t() if self.layout == "DK" else self.embeddings).contiguous().to(dev)
-            self._dev = dict(kd=kd, sq=ops.vq_prepare(kd), hist=torch.zeros(self.num_embeddings, dtype=torch.int32, device=dev))
+            sq = ops.vq_prepare(kd)
+            self._dev = dict(kd=kd, sq=sq, tc=ops.vq_prepare_tc(kd, sq), hist=torch.zeros(self.num_embeddings, dtype=torch.int32, device=dev))
         return self._dev
 
     def get_code_indices(self, flattened_inputs, distribution=False):
@@ -64,7 +65,7 @@ class VectorQuantizer:
             dist = torch.empty(x.shape[0], self.num_embeddings, dtype=torch.float32, device=x.device)
             L.check(L.lib().b200dm_vq_distances(d, L.ptr(x), L.ptr(st["kd"]), L.ptr(st["sq"]), L.ptr(dist), L.stream()))
             return dist
-        idx, _ = ops.vq_argmin_gather(flattened_inputs.contiguous(), st["kd"], st["sq"], want_q=False)
+        idx, _ = ops.vq_argmin_gather(flattened_inputs.contiguous(), st["kd"], st["sq"], want_q=False, tc_ws=st["tc"])
         return idx
 
     def quantize(self, x, q_dtype=torch.float32):
@@ -72,7 +73,7 @@ class VectorQuantizer:
         straight-through form x + (q - x) equals q up to 1 ulp."""
         st = self._device_state()
         st["hist"].zero_()
-        idx, q = ops.vq_argmin_gather(x.contiguous(), st["kd"], st["sq"], want_q=True, q_dtype=q_dtype, hist=st["hist"])
+        idx, q = ops.vq_argmin_gather(x.contiguous(), st["kd"], st["sq"], want_q=True, q_dtype=q_dtype, hist=st["hist"], tc_ws=st["tc"])
         counts = st["hist"].cpu()
         self.codebooks_used += counts                       # codebooks_used.assign_add (vqvae3d_monai.py:161)
         p = counts.double() / max(1, idx.numel())

@@ -147,18 +147,39 @@ def vq_prepare(codebook_kd):
     return sq
 
 
-def vq_argmin_gather(x, codebook_kd, code_sqnorm=None, want_q=True, q_dtype=torch.float32, hist=None):
-    """x (..., D) fp32|bf16; codebook (K, D) fp32 -> (idx int64 (N,), q (..., D) | None)."""
+def vq_prepare_tc(codebook_kd, code_sqnorm):
+    """Workspace of the tensor-core search (fp16 hi/lo halves of the codebook + scales), or None when (K, D) is outside its
+    shapes (K % 128, D in {64,128,192,256})."""
+    _dev()
+    k, d = codebook_kd.shape
+    nbytes = lib().b200dm_vq_tc_workspace_bytes(k, d)
+    if nbytes == 0:
+        return None
+    ws = torch.empty((nbytes + 127) // 128 * 128, dtype=torch.uint8, device=codebook_kd.device)   # caching allocator: 512-byte aligned
+    check(lib().b200dm_vq_prepare_tc(ptr(codebook_kd), ptr(code_sqnorm), k, d, ptr(ws), stream()))
+    return ws
+
+
+def vq_argmin_gather(x, codebook_kd, code_sqnorm=None, want_q=True, q_dtype=torch.float32, hist=None, tc_ws="auto", stats=None):
+    """x (..., D) fp32|bf16; codebook (K, D) fp32 -> (idx int64 (N,), q (..., D) | None).  ``tc_ws``: workspace from
+    vq_prepare_tc ('auto' builds it when the shape allows, None forces the fp32 SIMT kernel); both kernels return the same
+    indices bit for bit."""
     _dev()
     D = x.shape[-1]
     n = x.numel() // D
     if code_sqnorm is None:
         code_sqnorm = vq_prepare(codebook_kd)
+    if isinstance(tc_ws, str):
+        tc_ws = vq_prepare_tc(codebook_kd, code_sqnorm)
     d = L.VqDesc()
     d.n, d.d, d.k, d.x_dtype, d.q_dtype = n, D, codebook_kd.shape[0], dt(x), (L.F32 if q_dtype == torch.float32 else L.BF16)
     idx = torch.empty(n, dtype=torch.int64, device=x.device)
     q = torch.empty(x.shape, dtype=L.storage(q_dtype), device=x.device) if want_q else None
-    check(lib().b200dm_vq_argmin_gather(C.byref(d), ptr(x), ptr(codebook_kd), ptr(code_sqnorm), ptr(idx), ptr(q), ptr(hist), stream()))
+    if tc_ws is not None and n > 0:
+        check(lib().b200dm_vq_argmin_gather_tc(C.byref(d), ptr(x), ptr(codebook_kd), ptr(code_sqnorm), ptr(tc_ws), ptr(idx), ptr(q), ptr(hist),
+                                               ptr(stats), stream()))
+    else:
+        check(lib().b200dm_vq_argmin_gather(C.byref(d), ptr(x), ptr(codebook_kd), ptr(code_sqnorm), ptr(idx), ptr(q), ptr(hist), stream()))
     return idx, q
 
 

@@ -175,6 +175,16 @@ int b200dm_vq_argmin_gather(const b200dm_vq_desc* d, const void* x, const float*
                             const float* code_sqnorm /* fp32[K] from b200dm_vq_prepare */,
                             int64_t* idx, void* q_or_null, int32_t* hist_or_null, void* stream);
 int b200dm_vq_prepare(const float* codebook_kd, int32_t k, int32_t d, float* code_sqnorm, void* stream);
+/* The same search with the N x K products on the tensor cores (tcgen05, fp16 hi/lo splits of x and E: candidate codes inside a
+ * proven error margin of the minimum) and the reference's exact fp32 chain re-evaluated for the candidates only: indices, q and
+ * hist are bit-identical to b200dm_vq_argmin_gather.  Shapes: k % 128 == 0, d in {64,128,192,256} (workspace_bytes == 0
+ * otherwise: use the call above).  tc_ws: caller-owned, 128-byte aligned, filled once per codebook by b200dm_vq_prepare_tc.
+ * stats (optional, uint64[3] += rows rechecked, candidates rechecked, rows scanned in full). */
+size_t b200dm_vq_tc_workspace_bytes(int32_t k, int32_t d);
+int b200dm_vq_prepare_tc(const float* codebook_kd, const float* code_sqnorm, int32_t k, int32_t d, void* tc_ws, void* stream);
+int b200dm_vq_argmin_gather_tc(const b200dm_vq_desc* d, const void* x, const float* codebook_kd, const float* code_sqnorm,
+                               const void* tc_ws, int64_t* idx, void* q_or_null, int32_t* hist_or_null, uint64_t* stats_or_null,
+                               void* stream);
 /* get_code_indices(flat, distribution=True) (vqvae3d_monai.py:165-177): the (N,K) fp32 matrix of squared distances, same
  * arithmetic as the argmin kernel (row-wise argmin of it == idx). */
 int b200dm_vq_distances(const b200dm_vq_desc* d, const void* x, const float* codebook_kd, const float* code_sqnorm,

@@ -161,3 +161,75 @@ def test_vq_ties_take_lowest_index_and_empty(cuda):
     assert idx.cpu().tolist() == [0, 2, 0]
     idx, q = ops.vq_argmin_gather(torch.empty(0, 4, device=cuda), cb.to(cuda))
     assert idx.numel() == 0
+
+
+def _vq_both(x, cb_kd, cuda, **kw):
+    """(idx, q, hist) of the fp32 SIMT kernel and of the tensor-core candidate search on the same device inputs."""
+    from b200dm import ops
+    xd, cbd = x.to(cuda), cb_kd.to(cuda)
+    K = cb_kd.shape[0]
+    out = []
+    for tc in (None, "auto"):
+        hist = torch.zeros(K, dtype=torch.int32, device=cuda)
+        stats = torch.zeros(3, dtype=torch.int64, device=cuda)
+        idx, q = ops.vq_argmin_gather(xd, cbd, hist=hist, tc_ws=tc, stats=stats, **kw)
+        out.append((idx.cpu(), q.cpu(), hist.cpu(), stats.cpu()))
+    return out
+
+
+@pytest.mark.parametrize("N,D,K", [(5000, 256, 1024), (777, 64, 128), (4096, 128, 512), (1000, 192, 256), (128 * 300 + 5, 256, 2048)])
+@pytest.mark.parametrize("x16", [False, True])
+def test_vq_tensor_core_search_is_bit_identical(cuda, N, D, K, x16):
+    """vq_tc_kernel (fp16 hi/lo split MMAs -> candidates inside the proven margin -> exact fp32 chain for them) returns the
+    indices, rows and histogram of vq_kernel bit for bit: random rows, rows that ARE codes, duplicated codes (exact ties ->
+    lowest index), codes one ulp apart, tiny and huge row scales, zero rows."""
+    from b200dm import _lib as L
+    g = torch.Generator().manual_seed(N + D + K)
+    cb = (torch.rand(K, D, generator=g) - 0.5) * 0.1
+    cb[K // 2] = cb[3]                                   # exact duplicate: index 3 must win
+    cb[K // 2 + 1] = cb[5]
+    cb[K // 2 + 1, 7] = torch.nextafter(cb[5, 7], torch.tensor(1.0))   # one ulp apart
+    cb[K - 1] = cb[9] * (1 + 2 ** -20)
+    x = torch.randn(N, D, generator=g) * 0.5
+    x[:64] = cb[torch.randint(0, K, (64,), generator=g)]  # rows equal to codes
+    x[64:96] = cb[[3, 5, 9, K // 2 + 1] * 8] + torch.randn(32, D, generator=g) * 1e-6
+    x[96:128] = 0.5 * (cb[3] + cb[11]) + torch.randn(32, D, generator=g) * 1e-7   # equidistant to two codes up to noise
+    x[128:160] *= 1e-9
+    x[160:192] *= 1e9
+    x[192:200] = 0
+    x[200:232] = cb[torch.randint(0, K, (32,), generator=g)] * 40   # large ||x||: fl(||x||^2 + ||e||^2) is coarse, many fp32 ties
+    if x16:
+        x = x.to(L.storage(torch.bfloat16))
+    (i0, q0, h0, _), (i1, q1, h1, st) = _vq_both(x, cb, cuda)
+    assert L.debug_flag() == 0
+    assert torch.equal(i0, i1), f"{(i0 != i1).sum().item()} of {N} indices differ (first rows {torch.nonzero(i0 != i1)[:8].flatten().tolist()})"
+    assert torch.equal(q0, q1) and torch.equal(h0, h1)
+    assert int(st[2]) <= 64 + 8, f"full-scan fallbacks: {st.tolist()}"   # only the out-of-range rows (1e-9 scale is in range)
+    print(f"N={N} D={D} K={K}: rechecked rows {int(st[0])} ({int(st[1])} candidates), full scans {int(st[2])}")
+
+
+def test_vq_tensor_core_search_nonfinite_and_cfg3_margin(cuda):
+    """NaN / inf rows take the full exact scan (code 0 for NaN rows, like vq_kernel); at the cfg-3 shape the candidate margin
+    has headroom: indices stay identical with the margin shrunk 8x (B200DM_TUNING hook), so the error bound of the fp16-split
+    products is not tight."""
+    import os
+    from b200dm import _lib as L
+    g = torch.Generator().manual_seed(5)
+    K, D, N = 1024, 256, 128 * 1024
+    cb = (torch.rand(K, D, generator=g) - 0.5) * 0.1
+    x = torch.randn(N, D, generator=g) * 0.5
+    x[5, 17] = float("nan")
+    x[300, 0] = float("inf")
+    x[301, 3] = -float("inf")
+    (i0, q0, h0, _), (i1, q1, h1, st) = _vq_both(x, cb, cuda)
+    assert torch.equal(i0, i1) and torch.equal(h0, h1) and int(i1[5]) == 0
+    assert 3 <= int(st[2]) <= 8, st.tolist()
+    frac = int(st[0]) / N
+    os.environ["B200DM_TUNING"], os.environ["B200DM_VQ_MARGIN_SCALE"] = "1", "0.125"
+    try:
+        (_, _, _, _), (i2, _, _, st2) = _vq_both(x, cb, cuda)
+    finally:
+        del os.environ["B200DM_TUNING"], os.environ["B200DM_VQ_MARGIN_SCALE"]
+    print(f"cfg-3 rows rechecked: {frac:.4%} at the proven margin, {int(st2[0]) / N:.4%} at 1/8 of it; mismatches at 1/8: {(i2 != i0).sum().item()}")
+    assert torch.equal(i2, i0)
+    assert L.debug_flag() == 0
