@@ -17,7 +17,7 @@
 //   fallback  rows with a non-finite element or more candidates than the list holds: the full exact scan by the row's thread.
 //
 // CTA = 128 rows.  A = [x_hi | x_lo] (128 KB at D = 256) is built once in shared memory by all warps (coalesced fp32 loads, row
-// scale by warp shuffles, SWIZZLE_128B K-major stores); the codebook halves stream through a TMA ring of 16 KB tiles (128 codes x 64
+// scale by shuffles over the 8 lanes of a row, SWIZZLE_128B K-major stores); the codebook halves stream through a TMA ring of 16 KB tiles (128 codes x 64
 // columns), each e_hi tile serving the x_hi and the x_lo pass; the score tile (128 x 128 fp32) is double-buffered in TMEM so the
 // candidate scan of code tile j overlaps the MMAs of tile j + 1.
 // Warps (256 threads): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 4-7 = candidate scan / recheck (thread = row = TMEM lane).
@@ -102,11 +102,26 @@ __device__ __forceinline__ float exact_xsq(const Params& p, int64_t row) {
   return s;
 }
 
+// candidate list of one row (shared memory, ascending k): append (k, g); when full, first drop what the running minimum has left
+// behind.  Returns the new count, or -1 when the list overflows (the row then takes the full exact scan).
+__device__ __noinline__ int cand_push(int* ck, float* cg, int cnt, int k, float g, float thr) {
+  if (cnt == kCap) {
+    int w = 0;
+    for (int i = 0; i < kCap; ++i)
+      if (cg[i] <= thr) { ck[w] = ck[i]; cg[w] = cg[i]; ++w; }
+    cnt = w;
+    if (cnt == kCap) return -1;
+  }
+  ck[cnt] = k;
+  cg[cnt] = g;
+  return cnt + 1;
+}
+
 template <bool kX16>
 __global__ void __launch_bounds__(kThreads, 1)
 vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ CUtensorMap mapLo, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   const int DC = p.d >> 6;                                  // 64-column chunks of the K dimension
   uint8_t* a_hi = smem;                                     // [DC][128 rows][128 B]
   uint8_t* a_lo = a_hi + DC * kTile;
@@ -143,61 +158,82 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
   const bool codebook_bad = __ldg(p.meta + 3) != 0.f;   // non-finite / out-of-range codebook: every row takes the full exact scan
   for (int i = threadIdx.x; i < p.k; i += kThreads) e2_s[i] = __ldg(p.esq + i);
 
-  // ---- A operand: 16 rows per warp; a lane holds 4 consecutive columns of every 128-column group of its row
-  for (int rr = 0; rr < 16; ++rr) {
-    const int r = warp * 16 + rr;
-    const int64_t row = row0 + r;
-    float v[8];   // D <= 256: two groups
-    float amax = 0.f, ssq = 0.f;
-    bool bad = false;
+  // ---- A operand: a warp converts 4 rows at a time (8 lanes per row, each lane 4 consecutive columns of every 32-column group: the
+  // 8 lanes of a row read 128 contiguous bytes per load).  The 4 rows of a trip differ in bit 2 / bit 0 of the row number so that
+  // their swizzled 64-byte store segments fall into different bank halves.  Loads of trip i + 1 are in flight during trip i.
+  {
+    const int sub = lane >> 3, ll = lane & 7;
+    const int ngrp = p.d >> 5;   // 32-column groups (<= 8)
+    auto row_of = [&](int it) { return warp * 16 + (it >> 1) * 8 + (it & 1) * 2 + (sub & 1) * 4 + (sub >> 1); };
+    auto load_row = [&](int it, float4 (&v)[8]) {
+      const int64_t row = row0 + row_of(it);
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int c = g * 128 + lane * 4;
-      float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.n && c < p.d) t4 = load_x4<kX16>(p.x, row * p.d + c);
-      v[g * 4] = t4.x; v[g * 4 + 1] = t4.y; v[g * 4 + 2] = t4.z; v[g * 4 + 3] = t4.w;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float t = v[g * 4 + j];
-        if (!(fabsf(t) <= 3.0e38f)) bad = true;   // NaN / inf
-        amax = fmaxf(amax, fabsf(t));
-        ssq = fmaf(t, t, ssq);
+      for (int j = 0; j < 8; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < ngrp && row < p.n) v[j] = load_x4<kX16>(p.x, row * p.d + j * 32 + ll * 4);
       }
-    }
-    amax = warp_max(amax);
-    ssq = warp_sum(ssq);
-    bad = __any_sync(0xffffffffu, bad) || (amax != 0.f && !(amax >= 9.0e-13f && amax <= 1.0e12f)) || codebook_bad;   // scales stay well inside fp32
-    // row scale 2^sx with max |x| 2^sx in [2^13, 2^14): fp16 hi / lo stay normal for every element within 2^-12 of the row's max
-    int ex = 0;
-    if (amax > 0.f) { (void)frexpf(amax, &ex); }
-    const int sx = amax > 0.f ? 14 - ex : 0;
-    const float sc = ldexpf(1.0f, sx);
+    };
+    float4 cur[8], nxt[8];
+    load_row(0, cur);
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      if (it + 1 < 4) load_row(it + 1, nxt);
+      const int r = row_of(it);
+      const int64_t row = row0 + r;
+      float amax = 0.f, ssq = 0.f;
+      bool bad = false;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int c = g * 128 + lane * 4;
-      if (c < p.d) {
-        __half h[4], l[4];
+      for (int j = 0; j < 8; ++j) {
+        const float t[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float t = bad ? 0.f : v[g * 4 + j] * sc;          // exact (power of two)
-          h[j] = __float2half_rn(t);
-          l[j] = __float2half_rn(t - __half2float(h[j]));         // exact difference, rounded to 11 bits
+        for (int q = 0; q < 4; ++q) {
+          if (!(fabsf(t[q]) <= 3.0e38f)) bad = true;   // NaN / inf
+          amax = fmaxf(amax, fabsf(t[q]));
+          ssq = fmaf(t[q], t[q], ssq);
         }
-        const int chunk = c >> 6, col = c & 63;
-        const uint32_t off = (uint32_t)chunk * kTile + (uint32_t)r * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
-        uint2 hv, lv;
-        memcpy(&hv, h, 8);
-        memcpy(&lv, l, 8);
-        *reinterpret_cast<uint2*>(a_hi + off) = hv;
-        *reinterpret_cast<uint2*>(a_lo + off) = lv;
       }
-    }
-    if (lane == 0) {
-      inv_s[r] = ldexpf(se_inv, -sx);
-      const float xsq_ub = ssq * 1.001f, xn = sqrtf(xsq_ub), en = sqrtf(e2max);
-      const float errS = 2.0f * (float)p.d * 5.9604645e-8f * xn * en + 1.0e-30f + 3.0e-10f * emax * xn * sqrtf((float)p.d);
-      const float U = 4.7683716e-7f * (xsq_ub + e2max);
-      marg_s[r] = (bad || row >= p.n) ? -1.0f : p.margin_scale * 2.0f * (2.0f * errS + U);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {   // over the 8 lanes of the row
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+        const int other_bad = __shfl_xor_sync(0xffffffffu, (int)bad, o);   // unconditional: every lane takes part in the shuffle
+        bad = bad || other_bad != 0;
+      }
+      bad = bad || (amax != 0.f && !(amax >= 9.0e-13f && amax <= 1.0e12f)) || codebook_bad;   // scales stay well inside fp32
+      // row scale 2^sx with max |x| 2^sx in [2^13, 2^14): fp16 hi / lo stay normal for every element within 2^-12 of the row's max
+      int ex = 0;
+      if (amax > 0.f) { (void)frexpf(amax, &ex); }
+      const int sx = (amax > 0.f && !bad) ? 14 - ex : 0;
+      const float sc = bad ? 0.f : ldexpf(1.0f, sx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < ngrp) {
+          const float t[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+          __half h[4], l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float ts = bad ? 0.f : t[q] * sc;                    // exact (power of two)
+            h[q] = __float2half_rn(ts);
+            l[q] = __float2half_rn(ts - __half2float(h[q]));           // exact difference, rounded to 11 bits
+          }
+          const int c = j * 32 + ll * 4, chunk = c >> 6, col = c & 63;
+          const uint32_t off = (uint32_t)chunk * kTile + (uint32_t)r * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
+          uint2 hv, lv;
+          memcpy(&hv, h, 8);
+          memcpy(&lv, l, 8);
+          *reinterpret_cast<uint2*>(a_hi + off) = hv;
+          *reinterpret_cast<uint2*>(a_lo + off) = lv;
+        }
+      }
+      if (ll == 0) {
+        inv_s[r] = ldexpf(se_inv, -sx);
+        const float xsq_ub = ssq * 1.001f, xn = sqrtf(xsq_ub), en = sqrtf(e2max);
+        const float errS = 2.0f * (float)p.d * 5.9604645e-8f * xn * en + 1.0e-30f + 3.0e-10f * emax * xn * sqrtf((float)p.d);
+        const float U = 4.7683716e-7f * (xsq_ub + e2max);
+        marg_s[r] = (bad || row >= p.n) ? -1.0f : p.margin_scale * 2.0f * (2.0f * errS + U);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
     }
   }
   ptx::fence_proxy_async();   // generic-proxy stores of A -> visible to the tensor core's operand reads
@@ -264,31 +300,42 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
     float runmin = INFINITY;
     int cnt = 0;
     bool overflow = false;
+    int* ck = cand_k + r * kCap;
+    float* cg = cand_g + r * kCap;
     for (int t = 0; t < ntile; ++t) {
       const uint32_t b = t & 1;
       if (!ptx::mbar_wait(s_full(b), (t >> 1) & 1, p.dbg, 0x5604)) break;
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t ra[16];
-        ptx::tc_ld_32x32b_x16(tmem_base + ((uint32_t)(qd * 32) << 16) + b * 128 + c * 16, ra);
-        ptx::tc_wait_ld();
+      for (int c = 0; c < 4; ++c) {   // 32 score columns per trip
+        uint32_t ra[16], rb[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + b * 128 + c * 32;
+        ptx::tc_ld_32x32b_x16(ta, ra);
+        ptx::tc_ld_32x32b_x16(ta + 16, rb);
+        const int k0 = t * 128 + c * 32;
+        float e2[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = t * 128 + c * 16 + j;
-          const float g = fmaf(-inv2, __uint_as_float(ra[j]), e2_s[k]);   // ||e||^2 - 2 x.e (approximate)
-          if (g <= runmin + M) {
-            if (cnt == kCap) {   // compact: drop what the running minimum has left behind
-              int w = 0;
-              for (int i = 0; i < kCap; ++i)
-                if (cand_g[r * kCap + i] <= runmin + M) { cand_k[r * kCap + w] = cand_k[r * kCap + i]; cand_g[r * kCap + w] = cand_g[r * kCap + i]; ++w; }
-              cnt = w;
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(&e2[4 * j]) = *reinterpret_cast<const float4*>(&e2_s[k0 + 4 * j]);
+        ptx::tc_wait_ld();
+        float g[32];   // ||e||^2 - 2 x.e (approximate)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { g[j] = fmaf(-inv2, __uint_as_float(ra[j]), e2[j]); g[16 + j] = fmaf(-inv2, __uint_as_float(rb[j]), e2[16 + j]); }
+        float m = g[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fminf(m, g[j]);
+        // candidates of this trip against the running minimum BEFORE it (a superset of the sequential test; the final filter uses the
+        // final minimum).  Taken by few lanes once the minimum has settled: the common trip is 32 FMAs + 31 mins + one compare.
+        const float thr0 = runmin + M;
+        if (m <= thr0) {
+          const float thr = fminf(runmin, m) + M;   // what is above this can never be within M of the final minimum
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (g[j] <= thr && !overflow) {
+              const int n = cand_push(ck, cg, cnt, k0 + j, g[j], thr);
+              if (n < 0) overflow = true; else cnt = n;
             }
-            if (cnt < kCap) { cand_k[r * kCap + cnt] = k; cand_g[r * kCap + cnt] = g; ++cnt; }
-            else overflow = true;
-            runmin = fminf(runmin, g);
-          }
         }
+        runmin = fminf(runmin, m);
       }
       ptx::tc_fence_before();
       __syncwarp();
