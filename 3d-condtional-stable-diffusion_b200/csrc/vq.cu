@@ -321,7 +321,7 @@ EncodeTiledFn vq_encode_fn() {
 
 size_t vq_tc_smem_bytes(int k, int d) {
   const int dc = d / 64;
-  return 1024 + (size_t)(2 * dc + vqtc::kNSB) * vqtc::kTile + (size_t)k * 4 + 128 * 4 * 2 + (size_t)128 * vqtc::kCap * 8 + 128 * 4 +
+  return 1024 + (size_t)(2 * dc + vqtc::kNSB) * vqtc::kTile + (size_t)k * 4 + 128 * 4 * 2 + (size_t)256 * vqtc::kCap * 8 + 256 * 8 + 128 * 4 +
          (2 * vqtc::kNSB + 4) * 8 + 16;
 }
 bool vq_tc_supported(int k, int d) {
@@ -376,6 +376,7 @@ extern "C" int b200dm_vq_argmin_gather_tc(const b200dm_vq_desc* d, const void* x
   p.meta = reinterpret_cast<const float*>((const char*)tc_ws + (size_t)d->k * d->d * 4);
   p.idx = idx; p.q = q; p.hist = hist; p.dbg = b200dm_dbg_flag_ptr();
   p.margin_scale = 1.0f;
+  p.wave_ctas = b2_num_sms();
   p.stats = reinterpret_cast<unsigned long long*>(stats);
   {   // test hook (B200DM_TUNING=1 only): shrink the candidate margin to measure the headroom of the error bound
     const char* t = getenv("B200DM_TUNING");

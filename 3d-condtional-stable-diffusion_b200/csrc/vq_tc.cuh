@@ -20,7 +20,9 @@
 // scale by shuffles over the 8 lanes of a row, SWIZZLE_128B K-major stores); the codebook halves stream through a TMA ring of 16 KB tiles (128 codes x 64
 // columns), each e_hi tile serving the x_hi and the x_lo pass; the score tile (128 x 128 fp32) is double-buffered in TMEM so the
 // candidate scan of code tile j overlaps the MMAs of tile j + 1.
-// Warps (256 threads): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 4-7 = candidate scan / recheck (thread = row = TMEM lane).
+// Warps (384 threads): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 4-11 = candidate scan (thread = row = TMEM lane; two warps per
+// lane quarter, each takes one 64-column half of every score tile and keeps its own running minimum and candidate list; the lists
+// are merged at the end by the warps of half 0, which also run the rechecks).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -29,10 +31,10 @@
 
 namespace vqtc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // 4 role warps + 8 scan warps
 constexpr int kNSB = 4;        // codebook tile ring
 constexpr int kTile = 16384;   // 128 rows x 128 B
-constexpr int kCap = 12;       // candidates kept per row
+constexpr int kCap = 10;       // candidates kept per (row, column half)
 
 struct Params {
   int64_t n;
@@ -46,6 +48,7 @@ struct Params {
   void* q;
   int32_t* hist;
   int* dbg;
+  int wave_ctas;         // CTAs resident at once (1 per SM): block b + wave_ctas runs on an SM after block b
   float margin_scale;    // 1 in production; tests shrink it to measure the headroom of the error bound
   unsigned long long* stats;   // optional [3]: rows rechecked, candidates rechecked, rows that fell back to the full scan
 };
@@ -58,7 +61,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
                "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void scan_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void scan_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 scan warps
 
 template <bool kX16>
 __device__ __forceinline__ float4 load_x4(const void* x, int64_t off) {   // 4 consecutive elements, off % 4 == 0
@@ -129,9 +132,11 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
   float* e2_s = reinterpret_cast<float*>(b_ring + kNSB * kTile);   // [K]
   float* inv_s = e2_s + p.k;                                // [128] 2^-(sx_r + se): score -> x.e
   float* marg_s = inv_s + 128;                              // [128] candidate margin M of the row (< 0: fallback row)
-  int* cand_k = reinterpret_cast<int*>(marg_s + 128);       // [128][kCap]
-  float* cand_g = reinterpret_cast<float*>(cand_k + 128 * kCap);
-  int* final_idx = reinterpret_cast<int*>(cand_g + 128 * kCap);
+  int* cand_k = reinterpret_cast<int*>(marg_s + 128);       // [2 halves][128][kCap]
+  float* cand_g = reinterpret_cast<float*>(cand_k + 256 * kCap);
+  float* half_min = cand_g + 256 * kCap;                    // [2][128] running minimum of each half (overflow: -inf)
+  int* half_cnt = reinterpret_cast<int*>(half_min + 256);   // [2][128]
+  int* final_idx = half_cnt + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(final_idx + 128);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kNSB + 4);
   const uint32_t a_hi_base = ptx::smem_u32(a_hi), a_lo_base = ptx::smem_u32(a_lo), b_base = ptx::smem_u32(b_ring);
@@ -147,7 +152,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNSB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(s_full(b), 1); ptx::mbar_init(s_free(b), 4); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(s_full(b), 1); ptx::mbar_init(s_free(b), 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapHi);
     ptx::prefetch_tmap(&mapLo);
@@ -161,7 +166,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
   // ---- A operand: a warp converts 4 rows at a time (8 lanes per row, each lane 4 consecutive columns of every 32-column group: the
   // 8 lanes of a row read 128 contiguous bytes per load).  The 4 rows of a trip differ in bit 2 / bit 0 of the row number so that
   // their swizzled 64-byte store segments fall into different bank halves.  Loads of trip i + 1 are in flight during trip i.
-  {
+  if (warp < 8) {
     const int sub = lane >> 3, ll = lane & 7;
     const int ngrp = p.d >> 5;   // 32-column groups (<= 8)
     auto row_of = [&](int it) { return warp * 16 + (it >> 1) * 8 + (it & 1) * 2 + (sub & 1) * 4 + (sub >> 1); };
@@ -293,26 +298,32 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== candidate scan: thread = row =====================
-    const int qd = warp & 3, r = qd * 32 + lane;
+    // ===================== candidate scan: thread = row, one 64-column half of every score tile =====================
+    const int qd = warp & 3, r = qd * 32 + lane, half = (warp - 4) >> 2;
     const int64_t row = row0 + r;
     const float inv2 = 2.0f * inv_s[r], M = marg_s[r];
     float runmin = INFINITY;
     int cnt = 0;
     bool overflow = false;
-    int* ck = cand_k + r * kCap;
-    float* cg = cand_g + r * kCap;
+    int* ck = cand_k + (half * 128 + r) * kCap;
+    float* cg = cand_g + (half * 128 + r) * kCap;
+    auto push = [&](int k, float g, float thr) {
+      if (overflow) return;
+      if (cnt < kCap) { ck[cnt] = k; cg[cnt] = g; ++cnt; return; }
+      const int n = cand_push(ck, cg, cnt, k, g, thr);
+      if (n < 0) overflow = true; else cnt = n;
+    };
     for (int t = 0; t < ntile; ++t) {
       const uint32_t b = t & 1;
       if (!ptx::mbar_wait(s_full(b), (t >> 1) & 1, p.dbg, 0x5604)) break;
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {   // 32 score columns per trip
+      for (int c = 0; c < 2; ++c) {   // 32 score columns per trip
         uint32_t ra[16], rb[16];
-        const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + b * 128 + c * 32;
+        const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + b * 128 + half * 64 + c * 32;
         ptx::tc_ld_32x32b_x16(ta, ra);
         ptx::tc_ld_32x32b_x16(ta + 16, rb);
-        const int k0 = t * 128 + c * 32;
+        const int k0 = t * 128 + half * 64 + c * 32;
         float e2[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(&e2[4 * j]) = *reinterpret_cast<const float4*>(&e2_s[k0 + 4 * j]);
@@ -320,19 +331,21 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
         float g[32];   // ||e||^2 - 2 x.e (approximate)
 #pragma unroll
         for (int j = 0; j < 16; ++j) { g[j] = fmaf(-inv2, __uint_as_float(ra[j]), e2[j]); g[16 + j] = fmaf(-inv2, __uint_as_float(rb[j]), e2[16 + j]); }
-        float m = g[0];
+        float q4[8];   // minima of the 8 groups of 4 columns
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = fminf(m, g[j]);
+        for (int i = 0; i < 8; ++i) q4[i] = fminf(fminf(g[4 * i], g[4 * i + 1]), fminf(g[4 * i + 2], g[4 * i + 3]));
+        const float m = fminf(fminf(fminf(q4[0], q4[1]), fminf(q4[2], q4[3])), fminf(fminf(q4[4], q4[5]), fminf(q4[6], q4[7])));
         // candidates of this trip against the running minimum BEFORE it (a superset of the sequential test; the final filter uses the
-        // final minimum).  Taken by few lanes once the minimum has settled: the common trip is 32 FMAs + 31 mins + one compare.
-        const float thr0 = runmin + M;
-        if (m <= thr0) {
+        // final minimum).  Taken by few lanes once the minimum has settled: the common trip is 32 FMAs + the min tree + one compare;
+        // a lane with a hit looks only into the groups of 4 whose minimum passes.
+        if (m <= runmin + M) {
           const float thr = fminf(runmin, m) + M;   // what is above this can never be within M of the final minimum
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (g[j] <= thr && !overflow) {
-              const int n = cand_push(ck, cg, cnt, k0 + j, g[j], thr);
-              if (n < 0) overflow = true; else cnt = n;
+          for (int i = 0; i < 8; ++i)
+            if (q4[i] <= thr) {
+#pragma unroll
+              for (int j = 4 * i; j < 4 * i + 4; ++j)
+                if (g[j] <= thr) push(k0 + j, g[j], thr);
             }
         }
         runmin = fminf(runmin, m);
@@ -341,60 +354,99 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(s_free(b));
     }
-    // ---- decide
-    int best_k = 0;
-    if (row < p.n) {
-      int nlive = 0, only = 0;
-      for (int i = 0; i < cnt; ++i)
-        if (cand_g[r * kCap + i] <= runmin + M) { ++nlive; only = cand_k[r * kCap + i]; }
-      if (M < 0.f || overflow || nlive == 0) {
-        // full exact scan: non-finite / out-of-range row (every comparison false -> code 0, like vq_kernel), candidate overflow
-        const float xsq = exact_xsq<kX16>(p, row);
-        float best = INFINITY;
-        int bi = 0x7fffffff;
-        for (int k = 0; k < p.k; ++k) {
-          const float dist = exact_dist<kX16>(p, row, k, xsq);
-          if (dist < best || (dist == best && k < bi)) { best = dist; bi = k; }
+    half_min[half * 128 + r] = overflow ? -INFINITY : runmin;
+    half_cnt[half * 128 + r] = cnt;
+    scan_bar_sync();
+    // ---- decide (warps of half 0): merge the two halves of the row
+    if (half == 0) {
+      int best_k = 0;
+      if (row < p.n) {
+        const float m0 = half_min[r], m1 = half_min[128 + r];
+        const bool over = m0 == -INFINITY || m1 == -INFINITY;
+        const float thr = fminf(m0, m1) + M;
+        int nlive = 0, only = 0;
+        for (int h = 0; h < 2; ++h) {
+          const int n = half_cnt[h * 128 + r];
+          for (int i = 0; i < n; ++i)
+            if (cand_g[(h * 128 + r) * kCap + i] <= thr) { ++nlive; only = cand_k[(h * 128 + r) * kCap + i]; }
         }
-        best_k = (unsigned)bi >= (unsigned)p.k ? 0 : bi;
-        if (p.stats) atomicAdd(p.stats + 2, 1ull);
-      } else if (nlive == 1) {
-        best_k = only;
-      } else {
-        const float xsq = exact_xsq<kX16>(p, row);
-        float best = INFINITY;
-        int bi = 0x7fffffff;
-        for (int i = 0; i < cnt; ++i) {   // ascending k
-          if (!(cand_g[r * kCap + i] <= runmin + M)) continue;
-          const int k = cand_k[r * kCap + i];
-          const float dist = exact_dist<kX16>(p, row, k, xsq);
-          if (dist < best || (dist == best && k < bi)) { best = dist; bi = k; }
+        if (M < 0.f || over || nlive == 0) {
+          // full exact scan: non-finite / out-of-range row (every comparison false -> code 0, like vq_kernel), candidate overflow
+          const float xsq = exact_xsq<kX16>(p, row);
+          float best = INFINITY;
+          int bi = 0x7fffffff;
+          for (int k = 0; k < p.k; ++k) {
+            const float dist = exact_dist<kX16>(p, row, k, xsq);
+            if (dist < best || (dist == best && k < bi)) { best = dist; bi = k; }
+          }
+          best_k = (unsigned)bi >= (unsigned)p.k ? 0 : bi;
+          if (p.stats) atomicAdd(p.stats + 2, 1ull);
+        } else if (nlive == 1) {
+          best_k = only;
+        } else {
+          const float xsq = exact_xsq<kX16>(p, row);
+          float best = INFINITY;
+          int bi = 0x7fffffff;
+          for (int h = 0; h < 2; ++h) {
+            const int n = half_cnt[h * 128 + r];
+            for (int i = 0; i < n; ++i) {
+              if (!(cand_g[(h * 128 + r) * kCap + i] <= thr)) continue;
+              const int k = cand_k[(h * 128 + r) * kCap + i];
+              const float dist = exact_dist<kX16>(p, row, k, xsq);
+              if (dist < best || (dist == best && k < bi)) { best = dist; bi = k; }   // lowest index on ties, whatever the list order
+            }
+          }
+          best_k = (unsigned)bi >= (unsigned)p.k ? 0 : bi;
+          if (p.stats) { atomicAdd(p.stats, 1ull); atomicAdd(p.stats + 1, (unsigned long long)nlive); }
         }
-        best_k = (unsigned)bi >= (unsigned)p.k ? 0 : bi;
-        if (p.stats) { atomicAdd(p.stats, 1ull); atomicAdd(p.stats + 1, (unsigned long long)nlive); }
+        p.idx[row] = (int64_t)best_k;
+        if (p.hist) atomicAdd(p.hist + best_k, 1);
       }
-      p.idx[row] = (int64_t)best_k;
-      if (p.hist) atomicAdd(p.hist + best_k, 1);
+      final_idx[r] = best_k;
     }
-    final_idx[r] = best_k;
+  } else {
+    // warps 2-3: pull the rows of the CTA that follows on this SM (one wave later) into L2 while this one computes
+    const int64_t nrow0 = row0 + (int64_t)p.wave_ctas * 128;
+    if (nrow0 < p.n) {
+      const int64_t nrows = (p.n - nrow0) < 128 ? (p.n - nrow0) : 128;
+      const int64_t bytes = nrows * p.d * (kX16 ? 2 : 4);
+      const char* base = reinterpret_cast<const char*>(p.x) + nrow0 * p.d * (kX16 ? 2 : 4);
+      for (int64_t off = (int64_t)((warp - 2) * 32 + lane) * 128; off < bytes; off += 64 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
   if (p.q) {
-    // gather: one warp streams one row at a time, 16-byte vectors
-    for (int r = warp; r < 128; r += 8) {
-      const int64_t gr = row0 + r;
-      if (gr >= p.n) break;
-      const float* src = p.cb + (int64_t)final_idx[r] * p.d;
-      for (int d = lane * 4; d < p.d; d += 128) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
-        if (p.q_f32) {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.q) + gr * p.d + d) = v;
-        } else {
-          act2_t* o = reinterpret_cast<act2_t*>(reinterpret_cast<act_t*>(p.q) + gr * p.d + d);
-          o[0] = floats_to_act2(v.x, v.y);
-          o[1] = floats_to_act2(v.z, v.w);
+    // gather: a warp streams rows, 16-byte vectors, all loads of 4 rows in flight before their stores
+    constexpr int kWarps = kThreads / 32;
+    for (int rb = warp * 4; rb < 128; rb += kWarps * 4) {
+      float4 v[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* src = p.cb + (int64_t)final_idx[rb + u] * p.d;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int d = lane * 4 + h * 128;
+          v[u][h] = (row0 + rb + u < p.n && d < p.d) ? __ldg(reinterpret_cast<const float4*>(src + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t gr = row0 + rb + u;
+        if (gr >= p.n) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int d = lane * 4 + h * 128;
+          if (d >= p.d) break;
+          if (p.q_f32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.q) + gr * p.d + d) = v[u][h];
+          } else {
+            act2_t* o = reinterpret_cast<act2_t*>(reinterpret_cast<act_t*>(p.q) + gr * p.d + d);
+            o[0] = floats_to_act2(v[u][h].x, v[u][h].y);
+            o[1] = floats_to_act2(v[u][h].z, v[u][h].w);
+          }
         }
       }
     }
