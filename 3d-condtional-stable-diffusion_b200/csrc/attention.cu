@@ -228,21 +228,27 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       ptx::tc_fence_after();
       const uint32_t s_addr = lane_addr + (uint32_t)sb * BKV;
       const int kvalid = p.lk - j * BKV;                // keys of this tile that exist
-      // ---- pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t ra[16], rb[16];
-        ptx::tc_ld_32x32b_x16(s_addr + c0, ra);
-        ptx::tc_ld_32x32b_x16(s_addr + c0 + 16, rb);
-        ptx::tc_wait_ld();
+      // ---- the whole score row of this tile -> registers in one round trip (BKV loads in flight, one wait): the TMEM buffer is
+      // free for Q K^T (j + 2) before the exponentials start, and the row is read once instead of twice
+      uint32_t sv[BKV];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (c0 + i < kvalid) mx = fmaxf(mx, __uint_as_float(ra[i]));
-          if (c0 + 16 + i < kvalid) mx = fmaxf(mx, __uint_as_float(rb[i]));
-        }
+      for (int c0 = 0; c0 < BKV; c0 += 16) ptx::tc_ld_32x32b_x16(s_addr + c0, *reinterpret_cast<uint32_t(*)[16]>(&sv[c0]));
+      ptx::tc_wait_ld();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_free(sb));
+      if (kvalid < BKV) {   // last tile only (warp-uniform): keys past Lk score -inf, exp2 makes them 0
+#pragma unroll
+        for (int i = 0; i < BKV; ++i)
+          if (i >= kvalid) sv[i] = 0xff800000u;
       }
-      mx *= p.scale_log2e;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < BKV; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(sv[i + u]));
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2e;
       // ---- reference max update + (rare) rescale of the O accumulator
       float factor = 1.f;
       const bool grow = mx > m_ref + 8.f;               // first tile: m_ref = -inf
@@ -265,41 +271,35 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           tc_st_32x32b_x16(lane_addr + kOCol + c0, rr);
         }
         tc_wait_st();
+        ptx::tc_fence_before();
       }
+      // ---- p = exp2(s*c - m_ref) -> bf16 (in place: two per register)
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float nm = -m_ref;
+#pragma unroll
+      for (int i = 0; i < BKV; i += 2) {
+        const float p0 = ex2(fmaf(__uint_as_float(sv[i]), p.scale_log2e, nm));
+        const float p1 = ex2(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2e, nm));
+        ls4[(i >> 1) & 3] += p0 + p1;
+        const act2_t h = floats_to_act2(p0, p1);
+        memcpy(&sv[i >> 1], &h, 4);
+      }
+      l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       // ---- the P buffer must have been consumed by PV(j - NPB)
       if (j >= NPB) {
         ok = ptx::mbar_wait(p_free(pb), ((j / NPB) - 1) & 1, p.dbg, 30);
         if (!ok) break;
       }
-      // ---- pass 2: p = exp2(s*c - m_ref) -> bf16 -> smem (SWIZZLE_128B, K-major: chunk of 64 keys = [128 rows][128 B])
+      // ---- -> smem (SWIZZLE_128B, K-major: chunk of 64 keys = [128 rows][128 B])
       uint8_t* prow = p_ptr + pb * SM::kP + r * 128;
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t ra[16], rb[16];
-        ptx::tc_ld_32x32b_x16(s_addr + c0, ra);
-        ptx::tc_ld_32x32b_x16(s_addr + c0 + 16, rb);
-        ptx::tc_wait_ld();
-        float pv[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          pv[i] = (c0 + i < kvalid) ? ex2(fmaf(__uint_as_float(ra[i]), p.scale_log2e, -m_ref)) : 0.f;
-          pv[16 + i] = (c0 + 16 + i < kvalid) ? ex2(fmaf(__uint_as_float(rb[i]), p.scale_log2e, -m_ref)) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) lsum += pv[i];
-        uint8_t* chunk = prow + (c0 >> 6) * (128 * 128);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                   // four 16-byte units (8 keys each) of this 32-key slice
-          const int unit = ((c0 & 63) >> 3) + u;
-          *reinterpret_cast<bf16x8*>(chunk + ((unit ^ (r & 7)) << 4)) = pack8(*reinterpret_cast<float(*)[8]>(&pv[8 * u]));
-        }
+      for (int u = 0; u < BKV / 8; ++u) {               // 16-byte units of 8 keys
+        uint8_t* chunk = prow + (u >> 3) * (128 * 128);
+        *reinterpret_cast<uint4*>(chunk + (((u & 7) ^ (r & 7)) << 4)) = make_uint4(sv[4 * u], sv[4 * u + 1], sv[4 * u + 2], sv[4 * u + 3]);
       }
-      l += lsum;
-      ptx::tc_fence_before();
       ptx::fence_proxy_async();                         // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(s_free(sb)); ptx::mbar_arrive(p_full(pb)); }
+      if (lane == 0) ptx::mbar_arrive(p_full(pb));
     }
     // ---- epilogue: O / l (+ residual) -> bf16
     if (ok) ok = ptx::mbar_wait(o_done, (ntile - 1) & 1, p.dbg, 31);

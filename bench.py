@@ -423,7 +423,7 @@ def cfg3_line(b200dm, L, dev, pk, tf_peak):
            "quantize_ms": ms_q, "decode_ms": ms_d, "volumes_per_s": Bd / ((ms_q + ms_d) * 1e-3), "decode_volumes_per_s": Bd / (ms_d * 1e-3),
            "vq_rows_per_s": N / (ms_q * 1e-3)}
     vq_fl, vq_by = 2.0 * N * Kc * D, N * D * 4.0 * 2 + N * 8.0 + Kc * D * 4.0
-    out["roofline_vq"] = {"kernel": "vq argmin + gather", "bound": "tensor", "achieved": vq_fl / (ms_q * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+    out["roofline_vq"] = {"kernel": "vq_tc_kernel (tcgen05 fp16 hi/lo candidate search, 3 MMA passes = 3x the algorithmic FLOPs executed, + exact fp32 recheck + gather); indices bit-identical to the fp32 SIMT vq_kernel", "bound": "tensor", "achieved": vq_fl / (ms_q * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                           "frac": vq_fl / (ms_q * 1e-3) / 1e12 / tf_peak, "hbm_gbps": vq_by / (ms_q * 1e-3) / 1e9, "hbm_frac": vq_by / (ms_q * 1e-3) / 1e9 / pk["hbm"],
                           "note": "2*N*K*D FLOP vs the dense bf16 tensor peak and N*D*4*2 + N*8 + K*D*4 bytes vs HBM (SURVEY 8d: compute-bound at K=1024)"}
     tens = [r for r in rows if r[0] in ("conv", "conv_halo")]
