@@ -54,7 +54,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int D, int BKV, int NST, int NPB>
+template <int D, int BKV, int NST, int NPB>   // (shared-memory layout does not depend on the number of score buffers)
 struct Smem {
   static constexpr int kQ = 128 * D * 2;                 // D/64 chunks of [128 rows][128 B]
   static constexpr int kK = BKV * D * 2;                 // D/64 chunks of [BKV rows][128 B]
@@ -62,21 +62,31 @@ struct Smem {
   static constexpr int kP = 128 * BKV * 2;               // BKV/64 chunks of [128 rows][128 B]
   static constexpr int kBars = 1 + 4 * NST + 4 + 2 * NPB + 2;
   static_assert(NST * kK >= kQ, "the residual tile is staged in the (drained) K ring");
-  static constexpr size_t kTotal = 1024 + kQ + (size_t)NST * (kK + kV) + (size_t)NPB * kP + kBars * 8 + 16;
+  static constexpr size_t kBody = kQ + (size_t)NST * (kK + kV) + (size_t)NPB * kP + kBars * 8 + 16;
+  static constexpr size_t kTotal = 1024 + kBody;   // with the alignment slack (one CTA per SM)
 };
 
-template <int D, int BKV, int NST, int NPB>
-__global__ void __launch_bounds__(kThreads, 1)
+// NSB = score buffers in TMEM (2: Q K^T of tile j + 1 overlaps the whole softmax of tile j; 1: it overlaps everything after
+// the softmax warps' load of the row, which is enough when MINB = 2 CTAs share the SM and interleave their phases)
+template <int D, int BKV, int NST, int NPB, int NSB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                   const __grid_constant__ CUtensorMap mapVt, const __grid_constant__ CUtensorMap mapO,
                   const __grid_constant__ CUtensorMap mapR, const AttnParams p) {
   using SM = Smem<D, BKV, NST, NPB>;
   static_assert(D % 64 == 0 && D <= 256 && BKV % 64 == 0 && BKV <= 128, "tile shape");
   constexpr int kDC = D / 64, kKC = BKV / 64;
-  constexpr uint32_t kOCol = 2 * BKV;                               // TMEM: S0 | S1 | O
-  constexpr uint32_t kTmemCols = (2 * BKV + D) <= 128 ? 128 : ((2 * BKV + D) <= 256 ? 256 : 512);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t kOCol = NSB * BKV;                             // TMEM: S0 | (S1 |) O
+  constexpr uint32_t kTmemCols = (NSB * BKV + D) <= 128 ? 128 : ((NSB * BKV + D) <= 256 ? 256 : 512);
+  static_assert(kTmemCols * MINB <= 512, "co-resident CTAs share the SM's 512 TMEM columns");
+  // two CTAs per SM leave no room for 1 KB of alignment slack (2 x (kBody + 1 KB reserved) = 228 KB - 1.7 KB): that variant is
+  // launched with kBody bytes and relies on the 1024-byte alignment of the dynamic window (no static shared memory), checked here
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  if (MINB > 1 && smem != smem_raw) {
+    if (threadIdx.x == 0 && p.dbg) atomicExch(p.dbg, 0x5701);
+    return;
+  }
   const uint32_t q_base = ptx::smem_u32(smem);
   const uint32_t k_base = q_base + SM::kQ;
   const uint32_t v_base = k_base + NST * SM::kK;
@@ -174,11 +184,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     auto issue_qk = [&](int j) {   // S[j&1] = Q K_j^T
       const int s = j % NST;
       ok = ok && ptx::mbar_wait(k_full(s), (j / NST) & 1, p.dbg, 24);
-      if (j >= 2) ok = ok && ptx::mbar_wait(s_free(j & 1), ((j >> 1) - 1) & 1, p.dbg, 25);
+      if (j >= NSB) ok = ok && ptx::mbar_wait(s_free(j % NSB), ((j / NSB) - 1) & 1, p.dbg, 25);
       if (!ok) return;
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t acc = tmem_base + (uint32_t)(j & 1) * BKV;
+        const uint32_t acc = tmem_base + (uint32_t)(j % NSB) * BKV;
 #pragma unroll
         for (int c = 0; c < kDC; ++c) {
           const uint64_t a = dq + (uint64_t)(c * ((128 * 128) >> 4));
@@ -187,7 +197,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           for (int k = 0; k < 4; ++k) ptx::tc_mma_f16(acc, a + 2 * k, b + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
         }
         ptx::tc_commit(k_empty(s));
-        ptx::tc_commit(s_full(j & 1));
+        ptx::tc_commit(s_full(j % NSB));
       }
       __syncwarp();
     };
@@ -222,8 +232,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     float m_ref = -INFINITY, l = 0.f;                   // reference max (log2 units) and running sum
     bool ok = true;
     for (int j = 0; j < ntile && ok; ++j) {
-      const int sb = j & 1, pb = j % NPB;
-      ok = ptx::mbar_wait(s_full(sb), (j >> 1) & 1, p.dbg, 28);
+      const int sb = j % NSB, pb = j % NPB;
+      ok = ptx::mbar_wait(s_full(sb), (j / NSB) & 1, p.dbg, 28);
       if (!ok) break;
       ptx::tc_fence_after();
       const uint32_t s_addr = lane_addr + (uint32_t)sb * BKV;
@@ -397,16 +407,19 @@ struct b200dm_attn_plan {
 
 int* b200dm_dbg_flag_ptr();
 
-template <int D, int BKV, int NST, int NPB>
+template <int D, int BKV, int NST, int NPB, int NSB, int MINB>
 static int launch_attn(const b200dm_attn_plan* pl, cudaStream_t s) {
-  auto kern = flash_attn_kernel<D, BKV, NST, NPB>;
+  auto kern = flash_attn_kernel<D, BKV, NST, NPB, NSB, MINB>;
+  constexpr size_t kSmem = MINB > 1 ? Smem<D, BKV, NST, NPB>::kBody : Smem<D, BKV, NST, NPB>::kTotal;
+  static_assert(MINB * (kSmem + 1024) <= 233472, "co-resident CTAs fit the SM's shared memory");
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<D, BKV, NST, NPB>::kTotal));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    if (MINB > 1) B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   dim3 grid((pl->desc.lq + 127) / 128, pl->desc.batch);
-  B2_CHECK_CUDA(b2_launch(kern, grid, dim3(kThreads), Smem<D, BKV, NST, NPB>::kTotal, s, pl->mapQ, pl->mapK, pl->mapVt, pl->mapO, pl->mapR, pl->p));
+  B2_CHECK_CUDA(b2_launch(kern, grid, dim3(kThreads), kSmem, s, pl->mapQ, pl->mapK, pl->mapVt, pl->mapO, pl->mapR, pl->p));
   return B200DM_OK;
 }
 
@@ -446,9 +459,11 @@ extern "C" int b200dm_attention_plan_run(b200dm_attn_plan* pl, void* stream) {
   B2_CHECK_ARG(pl, "attention_plan_run: null plan");
   cudaStream_t s = (cudaStream_t)stream;
   switch (pl->desc.d) {
-    case 64: return launch_attn<64, 128, 3, 2>(pl, s);
-    case 128: return launch_attn<128, 128, 2, 1>(pl, s);
-    case 256: return launch_attn<256, 64, 2, 1>(pl, s);
+    // d = 64 (cfg-4, L = 32768): the exponentials (MUFU, 1024 cycles per 128 x 128 tile) outweigh the MMAs (640), and one CTA's
+    // softmax -> P V -> next softmax chain leaves both pipes idle half of the time: two CTAs per SM (112 KB, 256 TMEM columns each)
+    case 64: return launch_attn<64, 128, 2, 1, 1, 2>(pl, s);
+    case 128: return launch_attn<128, 128, 2, 1, 2, 1>(pl, s);
+    case 256: return launch_attn<256, 64, 2, 1, 2, 1>(pl, s);
   }
   b200dm_set_error("attention_plan_run: unsupported head dim");
   return B200DM_ERR_UNSUPPORTED;
