@@ -394,6 +394,7 @@ def run_ours(args):
                                                   "algorithmic_bytes_per_launch": big[2], "avg_launch_ms": big[3]}
         if not args.no_cfg3:
             line["cfg3"] = cfg3_line(b200dm, L, dev, pk, tf_peak)
+            line["cfg4"] = cfg4_line(b200dm, L, dev, tf_peak)
         if world == 1 and not args.no_cpu:
             r = oracle_cpu_rate(3, 1, budget_s=25.0)   # 8 volumes per step, like the GPU arm
             line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
@@ -438,6 +439,40 @@ def cfg3_line(b200dm, L, dev, pk, tf_peak):
     out["decoder_whole"] = {"algorithmic_gflop": t_fl / 1e9, "achieved_tflops": t_fl / (ms_d * 1e-3) / 1e12, "frac": t_fl / (ms_d * 1e-3) / 1e12 / tf_peak}
     out["top_ops"] = [{"kind": r[0], "op": r[1], "ms": round(r[3], 4)} for r in sorted(rows, key=lambda r: -r[3])[:8]]
     return out
+
+
+def cfg4_line(b200dm, L, dev, tf_peak):
+    """BASELINE configs[3]: dm3d U-Net with self-attention at the highest latent resolution (has_attention=[T,F,T]: level 0 has
+    L = 32^3 = 32768 tokens, d = 64), 250-step DDIM (eta = 0), batch 1: the public generate(sampler='ddim') path (graph replay,
+    device-resident timestep sequence) timed over a 16-step slice of the 250-step sequence, plus the flash attention kernel's
+    roofline from per-launch events."""
+    import types
+    B, S, C, T, steps, K = 1, 32, 256, 1000, 250, 16
+    dm = b200dm.DiffusionModel(S, 256, C, None, types.SimpleNamespace(timesteps=T, num_gpus=1, kernel_resize=False, bs=B))
+    dm.network = b200dm.build_model(S, C, [64, 128, 256], [True, False, True])
+    shape = (B, S, S, S, C)
+    seq = list(range(T - 1, T - 1 - (T // steps) * K, -(T // steps)))   # the first K entries of the 250-step sequence 999, 995, ...
+    lat = dm.generate(shape, seed=1, sampler="ddim", timestep_seq=seq)    # compile + capture
+    assert torch.isfinite(lat).all() and L.debug_flag() == 0
+    ms = event_time(lambda: dm.generate(shape, seed=1, sampler="ddim", timestep_seq=seq), 2, 1)
+    n_steps = len(seq)
+    rows = dm._step["net"].prog.run_timed()
+    attn = [r for r in rows if r[0] == "attn"]
+    a_ms, a_fl = sum(r[3] for r in attn), sum(r[2] for r in attn)
+    big = max(attn, key=lambda r: r[2])
+    tens = [r for r in rows if r[0] in ("conv", "conv_halo", "attn")]
+    return {"workload": "cfg-4: dm3d U-Net, has_attention=[T,F,T] (level-0 self-attention: L = 32768, d = 64), DDIM 250 of 1000 steps, batch 1",
+            "ms_per_step": ms / n_steps, "steps_timed": n_steps, "volume_steps_per_s": B * n_steps / (ms * 1e-3),
+            "seconds_per_250_step_chain": 250 * ms / n_steps * 1e-3,
+            "call": "DiffusionModel.generate(shape, sampler='ddim', timestep_seq=<first 16 of the 250>) (graph replay; device-generated x_T)",
+            "roofline_flash_attention": {"kernel": "flash_attn_kernel (tcgen05 QK^T / PV, online softmax, no (L, L) tensor)", "bound": "tensor",
+                                         "achieved": a_fl / (a_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                                         "frac": a_fl / (a_ms * 1e-3) / 1e12 / tf_peak, "launches": len(attn), "ms": a_ms,
+                                         "largest_launch": {"op": big[1], "ms": big[3], "tflops": big[2] / (big[3] * 1e-3) / 1e12},
+                                         "share_of_step": a_ms / sum(r[3] for r in rows)},
+            "roofline_step": {"bound": "tensor", "algorithmic_gflop": sum(r[2] for r in tens) / 1e9,
+                              "achieved": sum(r[2] for r in tens) / (ms / n_steps * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                              "frac": sum(r[2] for r in tens) / (ms / n_steps * 1e-3) / 1e12 / tf_peak}}
 
 
 def main():
