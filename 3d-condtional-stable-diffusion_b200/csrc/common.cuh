@@ -106,11 +106,31 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) p.v[i] = floats_to_act2(f[2 * i], f[2 * i + 1]);
   return p;
 }
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x).  ex2.approx.ftz == __expf outside the denormal range, and there 1 + e == 1 either way: same values as
+// __fdividef(x, 1 + __expf(-x)) without the per-element range fix-up (FSETP + two predicated FMULs) of the non-ftz form.
+__device__ __forceinline__ float silu_f(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  return __fdividef(x, 1.0f + e);
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == B200DM_ACT_SILU) return silu_f(x);
   if (act == B200DM_ACT_RELU) return fmaxf(x, 0.0f);
   return x;
+}
+// Runtime activation of a register vector with the kind test OUTSIDE the element loop.  With the test inside, the compiler
+// emitted a branch per element and the N dependent MUFU.EX2 -> FADD -> MUFU.RCP -> FMUL chains ran one after the other
+// (~80 cycles each): the SiLU epilogue of a 64 -> 64 conv tile took 9.3 k cycles against 3.6 k without activation and made
+// the ResidualBlock conv1 launches epilogue-bound (clock64 timeline, tools/conv_trace.py EPI=1).
+template <int N>
+__device__ __forceinline__ void apply_act_vec(float (&v)[N], int act) {
+  if (act == B200DM_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = silu_f(v[j]);
+  } else if (act == B200DM_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -71,8 +71,7 @@ __device__ __forceinline__ void extra_output16(const float (&v)[16], act_t* yo, 
     w[j] = fmaf(a.x, v[j], b.x); w[j + 1] = fmaf(a.y, v[j + 1], b.y); w[j + 2] = fmaf(a.z, v[j + 2], b.z); w[j + 3] = fmaf(a.w, v[j + 3], b.w);
   }
   if (act != B200DM_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) w[j] = apply_act(w[j], act);
+    apply_act_vec(w, act);
   }
   *reinterpret_cast<bf16x8*>(yo) = pack8(*reinterpret_cast<float(*)[8]>(&w[0]));
   *reinterpret_cast<bf16x8*>(yo + 8) = pack8(*reinterpret_cast<float(*)[8]>(&w[8]));
@@ -124,8 +123,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) + a[j] * fminf(v[j], 0.f);
     }
     if (p.act != B200DM_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+      apply_act_vec(v, p.act);
     }
     if (p.residual) {
       float a[16];
@@ -141,8 +139,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, const uint3
       for (int j = 0; j < 16; ++j) v[j] += a[j];
     }
     if (p.post_act != B200DM_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+      apply_act_vec(v, p.post_act);
     }
     if (p.y_f32) {
       float* yo = reinterpret_cast<float*>(p.y) + row_off + col0;
@@ -210,8 +207,7 @@ __device__ __forceinline__ void conv_epilogue16_staged(const ConvParams& p, cons
     }
   }
   if (p.act != B200DM_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+    apply_act_vec(v, p.act);
   }
   // 128-byte rows (64 channels, SWIZZLE_128B: chunk ^ (row & 7)) or 64-byte rows (32 channels, SWIZZLE_64B: chunk ^ ((row >> 1) & 3))
   const int ch = c_local >> 3, sw = row64 ? (r >> 1) & 3 : r & 7;
@@ -231,8 +227,7 @@ __device__ __forceinline__ void conv_epilogue16_staged(const ConvParams& p, cons
     for (int j = 0; j < 16; ++j) v[j] += a[j];
   }
   if (p.post_act != B200DM_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+    apply_act_vec(v, p.post_act);
   }
   *reinterpret_cast<bf16x8*>(stg + o0) = pack8(*reinterpret_cast<float(*)[8]>(&v[0]));
   *reinterpret_cast<bf16x8*>(stg + o1) = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
@@ -261,8 +256,7 @@ __device__ __forceinline__ void conv_epilogue16_staged_f32(const ConvParams& p, 
     }
   }
   if (p.act != B200DM_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+    apply_act_vec(v, p.act);
   }
   if (has_rpre) {
     float a[16];
@@ -272,8 +266,7 @@ __device__ __forceinline__ void conv_epilogue16_staged_f32(const ConvParams& p, 
     for (int j = 0; j < 16; ++j) v[j] += a[j];
   }
   if (p.post_act != B200DM_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+    apply_act_vec(v, p.post_act);
   }
   const int u0 = c_local >> 2, sw = r & 7;
 #pragma unroll

@@ -391,8 +391,7 @@ conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += bs[j];
         if (p.act != B200DM_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+          apply_act_vec(v, p.act);
         }
         if (pre) {
           float a[16];
@@ -402,8 +401,7 @@ conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
           for (int j = 0; j < 16; ++j) v[j] += a[j];
         }
         if (p.post_act != B200DM_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.post_act);
+          apply_act_vec(v, p.post_act);
         }
         const bf16x8 o0 = pack8(*reinterpret_cast<float(*)[8]>(&v[0])), o1 = pack8(*reinterpret_cast<float(*)[8]>(&v[8]));
         if (q.gn_part) {

@@ -219,6 +219,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const act_t* __restrict_
       }
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int k = 0; k < kVecPerLane; ++k) {
+      const int c = (k * 32 + lane) << 3;
+      if (c < C) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[k][i] = (f[k][i] - mean) * rstd;
+      }
+    }
     for (int o = 0; o < n_out; ++o) {
       const float* g = o == 0 ? g0 : (o == 1 ? g1 : g2);
       const float* b = o == 0 ? b0 : (o == 1 ? b1 : b2);
@@ -227,9 +235,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const act_t* __restrict_
       for (int k = 0; k < kVecPerLane; ++k) {
         const int c = (k * 32 + lane) << 3;
         if (c < C) {
+          // affine coefficients as four 16-byte loads (they were 16 scalar loads per output on the row's critical path)
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(g + c)), gb = __ldg(reinterpret_cast<const float4*>(g + c + 4));
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(b + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c + 4));
           float r[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) r[i] = (f[k][i] - mean) * rstd * g[c + i] + b[c + i];
+          r[0] = f[k][0] * ga.x + ba.x; r[1] = f[k][1] * ga.y + ba.y; r[2] = f[k][2] * ga.z + ba.z; r[3] = f[k][3] * ga.w + ba.w;
+          r[4] = f[k][4] * gb.x + bb.x; r[5] = f[k][5] * gb.y + bb.y; r[6] = f[k][6] * gb.z + bb.z; r[7] = f[k][7] * gb.w + bb.w;
           *reinterpret_cast<bf16x8*>(y + row * C + c) = pack8(r);
         }
       }
@@ -432,6 +443,7 @@ extern "C" int b200dm_layernorm_fwd(const void* x, int64_t rows, int32_t c, floa
   for (int i = 0; i < n_out; ++i) {
     g[i] = gammas[i]; b[i] = betas[i]; y[i] = (act_t*)ys[i];
     B2_CHECK_ARG(g[i] && b[i] && y[i], "layernorm_fwd: null affine/output %d", i);
+    B2_CHECK_ARG(((uintptr_t)g[i] & 15) == 0 && ((uintptr_t)b[i] & 15) == 0, "layernorm_fwd: gamma/beta %d must be 16-byte aligned", i);
   }
   const int grid = grid_for(rows * 32, 256, 8);
   cudaStream_t s = (cudaStream_t)stream;

@@ -66,8 +66,7 @@ __global__ void __launch_bounds__(256) norm_ex_vec_kernel(const ExParams p) {
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f) + a[j] * fminf(f[j], 0.f);
     }
     if (p.act != B200DM_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+      apply_act_vec(f, p.act);
     }
     if (rs) {
       float r[8];
@@ -76,8 +75,7 @@ __global__ void __launch_bounds__(256) norm_ex_vec_kernel(const ExParams p) {
       for (int j = 0; j < 8; ++j) f[j] += r[j];
     }
     if (p.post_act != B200DM_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.post_act);
+      apply_act_vec(f, p.post_act);
     }
     *reinterpret_cast<bf16x8*>(yo + vo * p.c + c0) = pack8(f);
   }

@@ -15,7 +15,14 @@ wp = ops.pack_conv_weights(desc, w).to(dev)
 x0 = torch.randn(B, D, H, W, c0, device=dev).bfloat16()
 x1 = torch.randn(B, D, H, W, c1, device=dev).bfloat16() if c1 else None
 y = torch.empty(B, D, H, W, cout, device=dev, dtype=torch.bfloat16)
-plan = ops.ConvPlan(desc, x0, wp, y, x1=x1, bias=torch.zeros(cout, device=dev))
+kw = {}
+if os.environ.get("EPI") == "1":     # the ResidualBlock conv1 form: + temb row (device-side t), folded norm2, swish
+    desc = ops.make_conv_desc(0, B, (D, H, W), c0, c1, cout, 3, 1, "silu", None, torch.bfloat16, chan_bias_rows=1)
+    kw = dict(chan_bias=torch.randn(1000, cout, device=dev), t_dev=torch.tensor([500, 499, 0, 0], dtype=torch.int32, device=dev),
+              out_affine=(torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.1))
+if os.environ.get("RES") == "1":     # the conv2 form: + residual
+    kw = dict(residual=torch.randn(B, D, H, W, cout, device=dev).bfloat16())
+plan = ops.ConvPlan(desc, x0, wp, y, x1=x1, bias=torch.zeros(cout, device=dev), **kw)
 if os.environ.get("XFORM") == "1":   # d-sweeping kernel: folded input GroupNorm + SiLU
     mr = torch.stack([torch.zeros(B, 32), torch.ones(B, 32)], -1).to(dev)
     assert plan.set_input_norm(mr, torch.ones(32, device=dev), torch.zeros(32, device=dev), 32, "silu")
