@@ -557,6 +557,7 @@ struct b200dm_conv_plan {
   bool pair = false;   // halo kernel on 8 x 8 planes: 8w x 8h x 2d tiles from pair slabs (conv_halo.cuh)
   int halo_td = 1, halo_nb = 4, halo_tps = 1;
   int halo_ns = 0;     // slab ring depth when a variant fixes it (0 = by epilogue kind)
+  bool fuse = false;   // CTA-pair N = 128 fp32 conv with the reverse-diffusion update fused into its epilogue (set_fused_update)
   bool stencil = false;   // C_out = 1, C_in = 32 3^3 conv: HBM-bound stencil-reduce kernel (conv_stencil.cuh)
   stencil::Params sp;
   CUtensorMap mapS;
@@ -718,7 +719,7 @@ static int launch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     attr_set = true;
   }
-  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->om.y[1], pl->p));
   return B200DM_OK;
 }
 
@@ -761,7 +762,29 @@ static int launch_halo_cg2(const b200dm_conv_plan* pl, cudaStream_t s) {
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
-  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
+  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->om.y[1], pl->p));
+  return B200DM_OK;
+}
+
+constexpr int kHaloNSFused = 4;   // the 16-bit staging tiles of the fused update take the room of the fifth slab
+
+template <int TD>
+static int launch_halo_cg2_fused(const b200dm_conv_plan* pl, cudaStream_t s) {
+  auto kern = halo::conv_halo_kernel<128, TD, kHaloNSFused, 3, 3, true, false, true, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = pl->grid; cfg.blockDim = dim3(halo::kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = b200dm_pdl_enabled() ? 2 : 1;
+  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->om.y[1], pl->p));
   return B200DM_OK;
 }
 
@@ -773,7 +796,7 @@ static int launch_halo_wide(const b200dm_conv_plan* pl, cudaStream_t s) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     attr_set = true;
   }
-  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->om.y[1], pl->p));
   return B200DM_OK;
 }
 
@@ -784,7 +807,7 @@ static int launch_halo_pair(const b200dm_conv_plan* pl, cudaStream_t s) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     attr_set = true;
   }
-  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->p));
+  B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(halo::kThreads), pl->smem, s, pl->mapA0, pl->mapA1, pl->mapB, pl->om.y[0], pl->om.y[1], pl->p));
   return B200DM_OK;
 }
 
@@ -805,10 +828,10 @@ static int dispatch_halo(const b200dm_conv_plan* pl, cudaStream_t s) {
 
 static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const bool st = pl->p.tma_epi != 0;
-  const int ns = pl->halo_ns ? pl->halo_ns : (pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : halo_ns_for(pl->g.block_n, st)));   // (cg2: 5, or 4 for pair slabs)
+  const int ns = pl->fuse ? kHaloNSFused : pl->halo_ns ? pl->halo_ns : (pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : halo_ns_for(pl->g.block_n, st)));   // (cg2: 5, or 4 for pair slabs)
   return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) +
          (size_t)pl->halo_nb * pl->halo_tps * (pl->cg2 ? pl->g.block_n / 2 : pl->g.block_n) * 128 +
-         (size_t)halo::stage_bytes(pl->g.block_n, st) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
+         (size_t)halo::stage_bytes(pl->g.block_n, st) + (pl->fuse ? halo::kFuseStage16Bytes + 16 : 0) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
 }
 
 extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const void* x1, const void* w_packed,
@@ -1224,6 +1247,7 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
   if (pl->ups && pl->g.block_n == 32) return launch_halo_up<32, 5, 4>(pl, s);
   if (pl->ups) return pl->g.block_n == 64 ? launch_halo_up<64, 5, 3>(pl, s) : launch_halo_up<128, 5, 2>(pl, s);
   if (pl->cg2) {
+    if (pl->fuse) return pl->halo_td == 2 ? launch_halo_cg2_fused<2>(pl, s) : launch_halo_cg2_fused<1>(pl, s);
     if (pl->pair) return launch_halo_cg2<64, 1, kHaloNSPair, 3, true>(pl, s);
     if (pl->g.block_n == 32) return pl->p.tma_epi ? launch_halo_cg2<32, 2, kHaloNS, 4, false, true>(pl, s)
                                                   : launch_halo_cg2<32, 2, kHaloNS, 4, false, false>(pl, s);
@@ -1277,6 +1301,50 @@ extern "C" int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, c
   if (!p->p.y2) { p->p.y2 = (act_t*)y_extra; p->p.scale2 = scale; p->p.shift2 = shift; p->p.act2 = act; }
   else if (!p->p.y3) { p->p.y3 = (act_t*)y_extra; p->p.scale3 = scale; p->p.shift3 = shift; p->p.act3 = act; }
   else { b200dm_set_error("conv_plan_add_output: at most two extra outputs"); return B200DM_ERR_UNSUPPORTED; }
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_conv_plan_set_fused_update(b200dm_conv_plan* pl, const b200dm_update_desc* u, const float* x_t, float* x_prev,
+                                                 void* x_prev_16) {
+  B2_CHECK_ARG(pl && u && x_t && x_prev && x_prev_16, "conv_plan_set_fused_update: null argument");
+  const b200dm_conv_desc* d = &pl->desc;
+  const ConvParams& p = pl->p;
+  // the CTA-pair N = 128 halo kernel with the fp32 staged epilogue, no other epilogue term
+  if (!(pl->halo && pl->cg2 && !pl->pair && !pl->ups && !pl->sweep && !pl->stencil && pl->g.block_n == 128 &&
+        p.y_f32 && p.tma_epi && d->c_out % 128 == 0 && !p.residual && !p.prelu_alpha && !p.y2 && p.act == B200DM_ACT_NONE &&
+        p.post_act == B200DM_ACT_NONE)) {
+    b200dm_set_error("conv_plan_set_fused_update: only on the CTA-pair fp32-output 3^3 conv with C_out %% 128 == 0");
+    return B200DM_ERR_UNSUPPORTED;
+  }
+  B2_CHECK_ARG(u->sampler == 0 || u->sampler == 1, "conv_plan_set_fused_update: sampler must be 0 (ddpm) or 1 (ddim)");
+  B2_CHECK_ARG(u->beta && u->sqrt_alpha && u->alpha_bar && u->alpha_bar_prev && u->sqrt_alpha_bar && u->sqrt_alpha_bar_prev &&
+                   u->sqrt_one_minus_alpha_bar, "conv_plan_set_fused_update: null schedule table");
+  B2_CHECK_ARG(u->batch == d->batch && u->n_per_sample == (int64_t)d->in_d * d->in_h * d->in_w * d->c_out,
+               "conv_plan_set_fused_update: update geometry (%d x %lld) differs from the conv output", u->batch, (long long)u->n_per_sample);
+  B2_CHECK_ARG((u->n_per_sample >> 2) < (1ll << 32), "conv_plan_set_fused_update: sample too large for the 32-bit Philox counter");
+  B2_CHECK_ARG(x_t == x_prev, "conv_plan_set_fused_update: x_prev must alias x_t (the tile is updated in place through one tensor map)");
+  B2_CHECK_ARG(((uintptr_t)x_t & 15) == 0 && ((uintptr_t)x_prev & 15) == 0 && ((uintptr_t)x_prev_16 & 15) == 0,
+               "conv_plan_set_fused_update: pointers must be 16-byte aligned");
+  EncodeTiledFn enc = get_encode_fn();
+  const cuuint64_t C = (cuuint64_t)d->c_out;
+  cuuint64_t dims[5] = {C, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->in_d, (cuuint64_t)d->batch};
+  cuuint32_t box[5] = {16, 8, 16, 1, 1}, es[5] = {1, 1, 1, 1, 1};   // one round of the fused epilogue: 16 columns x one 8 x 16 plane tile
+  cuuint64_t st4[4] = {C * 4, (cuuint64_t)d->in_w * C * 4, (cuuint64_t)d->in_h * d->in_w * C * 4, (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 4};
+  cuuint64_t st2[4] = {C * 2, (cuuint64_t)d->in_w * C * 2, (cuuint64_t)d->in_h * d->in_w * C * 2, (cuuint64_t)d->in_d * d->in_h * d->in_w * C * 2};
+  CUtensorMap my, mz;
+  if (!enc ||
+      enc(&my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, x_prev, dims, st4, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+      enc(&mz, kTmapAct16, 5, x_prev_16, dims, st2, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    b200dm_set_error("conv_plan_set_fused_update: cuTensorMapEncodeTiled failed");
+    return B200DM_ERR_CUDA;
+  }
+  pl->om.y[0] = my; pl->om.y[1] = mz;
+  pl->p.upd = *u; pl->p.upd_x = x_t;
+  pl->fuse = true;
+  pl->smem = halo_smem_bytes(pl);
+  if (pl->smem > 232448) { b200dm_set_error("conv_plan_set_fused_update: shared memory"); return B200DM_ERR_UNSUPPORTED; }
   return B200DM_OK;
 }
 

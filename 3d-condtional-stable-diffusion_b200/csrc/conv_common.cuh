@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
+#include "update_math.cuh"
 
 struct ConvParams {
   int mode, batch;
@@ -42,6 +43,12 @@ struct ConvParams {
   act_t* y3; const float* scale3; const float* shift3; int act3;
   int* dbg;
   long long* trace;                  // optional per-role clock64 timeline of CTA 0 (tuning aid), else nullptr
+  // fused reverse-diffusion update (the U-Net's output conv on the sampling graph, b200dm_conv_plan_set_fused_update): the
+  // epilogue turns its eps tile into x_{t-1} = step(x_t, eps, Philox noise) and stores that (fp32 through the y map + a
+  // 16-bit copy for the next step's input conv) instead of eps -- the fp32 eps round trip through HBM and the update
+  // kernel's launch disappear.  upd_x = x_t (fp32, the output's geometry); nullptr = off.
+  const float* upd_x;
+  b200dm_update_desc upd;
 };
 
 // Output-side tensor maps of the staged (TMA-store) epilogue: y[parity] (parity 0 only outside PARITY mode), r = residual.
@@ -273,6 +280,56 @@ __device__ __forceinline__ void conv_epilogue16_staged_f32(const ConvParams& p, 
   for (int u = 0; u < 4; ++u)
     *reinterpret_cast<float4*>(stg + (uint32_t)r * 128u + (uint32_t)(((u0 + u) ^ sw) << 4)) =
         make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+}
+
+// Fused-update form of the fp32 staged epilogue: the 16 accumulator columns of this thread's row are eps_hat.  x_t of the same
+// 128 rows x 16 columns has been TMA-loaded INTO the fp32 staging tile (64-byte rows, SWIZZLE_64B; completion on mbarrier
+// `xbar`): each thread reads its 16 values from the very chunks it then overwrites with x_{t-1}; a second tile of 32-byte rows
+// (SWIZZLE_32B) takes the copy rounded to the 16-bit storage type.  The noise comes from the Philox stream of the stand-alone
+// update kernel (counter = element / 4 of the sample, step = t, sample = global sample index) and is generated BEFORE the
+// wait on the x_t tile, so the load's latency hides behind it.
+__device__ __forceinline__ bool upd_epilogue16(const ConvParams& p, const uint32_t (&rr)[16], int r, const float* bs, const float* sc,
+                                               const upd::Coef& k, bool gen, uint32_t ctr0, uint32_t sample, uint64_t seed,
+                                               uint8_t* stg, uint8_t* stg16, uint32_t xbar, uint32_t xphase) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+  if (sc) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+      v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+    }
+  }
+  if (bs) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bs + j);
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  float z[16];
+  if (gen) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) upd::normal4(ctr0 + q, (uint32_t)k.t, sample, 0u, seed, *reinterpret_cast<float(*)[4]>(&z[4 * q]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0.0f;
+  }
+  if (!ptx::mbar_wait(xbar, xphase, p.dbg, 17)) return false;
+  const int sw = (r >> 1) & 3;
+  float x[16], y[16];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<float4*>(&x[4 * u]) = *reinterpret_cast<const float4*>(stg + (uint32_t)r * 64u + (uint32_t)((u ^ sw) << 4));
+  upd::step_vec(k, p.upd.sampler, x, v, z, y);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<float4*>(stg + (uint32_t)r * 64u + (uint32_t)((u ^ sw) << 4)) = make_float4(y[4 * u], y[4 * u + 1], y[4 * u + 2], y[4 * u + 3]);
+  const int sw16 = (r >> 2) & 1;
+  *reinterpret_cast<bf16x8*>(stg16 + (uint32_t)r * 32u + (uint32_t)((0 ^ sw16) << 4)) = pack8(*reinterpret_cast<float(*)[8]>(&y[0]));
+  *reinterpret_cast<bf16x8*>(stg16 + (uint32_t)r * 32u + (uint32_t)((1 ^ sw16) << 4)) = pack8(*reinterpret_cast<float(*)[8]>(&y[8]));
+  return true;
 }
 
 // Stage bias[col] (+ chan_bias row `cbrow` when given) for columns [col_base, col_base + ncols) into shared memory.

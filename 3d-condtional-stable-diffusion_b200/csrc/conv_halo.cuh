@@ -55,6 +55,7 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int id) {
 constexpr int stage_bufs(int block_n) { return block_n <= 64 ? 2 : 1; }
 constexpr int stage_groups(int block_n) { return block_n >= 64 ? block_n / 64 : 1; }          // 64-channel groups (one 32-channel group)
 constexpr int stage_group_bytes(int block_n) { return block_n >= 64 ? 16384 : 8192; }         // 128 rows x 128 B | x 64 B
+constexpr int kFuseStage16Bytes = 2 * 8192;
 constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs(block_n) * stage_groups(block_n) * stage_group_bytes(block_n) : 0; }
 
 // PAIR (small planes, 8 x 8: the 8^3 level of the U-Net): the tile is 8 w x 8 h x 2 d.  The activation tensor map lists
@@ -65,10 +66,14 @@ constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs
 // and HALF of every weight stage (BLOCK_N / 2 rows); the leader's issuer warps run M = 256 MMAs over both CTAs' shared memory
 // and TMEM.  Per CTA and MMA that is 4 KB of A + 1 KB of B instead of 4 + 2, and half the weight fill traffic -- the two terms
 // that put the one-CTA main loop on the shared-memory roofline.
-template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED, bool PAIR = false, bool CG2 = false>
+// FUSE_UPD (BLOCK_N = 128, fp32 staged output: the U-Net's eps conv on the sampling graph): the epilogue applies the
+// reverse-diffusion update to its tile -- see ConvParams::upd_x.  mapY then addresses x_{t-1} (fp32) and mapZ its 16-bit copy.
+template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED, bool PAIR = false, bool CG2 = false, bool FUSE_UPD = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY, const ConvParams p) {
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY,
+                 const __grid_constant__ CUtensorMap mapZ, const ConvParams p) {
+  static_assert(!FUSE_UPD || (STAGED && BLOCK_N == 128 && !PAIR), "fused update: fp32 staged epilogue of the N = 128 tiles");
   static_assert(!STAGED || BLOCK_N >= 32, "staged epilogue works on whole 64-channel groups (or one 32-channel group)");
   static_assert(TPS == 1 || TPS == 3, "taps per weight stage: 1 or 3");
   static_assert(!PAIR || (STAGED && TD == 1), "pair-slab tiles: one accumulator, staged epilogue");
@@ -91,8 +96,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_ring = smem + NS * kSlabBytes;
   uint8_t* stg_base = b_ring + NB * kBBytes;   // (1024-aligned: slabs and weight stages are multiples of 1 KB)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + stage_bytes(BLOCK_N, STAGED));
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4);
+  uint8_t* stg16_base = stg_base + stage_bytes(BLOCK_N, STAGED);   // FUSE_UPD: two 8 KB tiles (128 rows x 32 x 16 bit)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg16_base + (FUSE_UPD ? kFuseStage16Bytes : 0));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4 + (FUSE_UPD ? 2 : 0));   // (+1 x_t barrier, +1 pad)
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [2 acc stages][bias | scale][BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,6 +111,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * NS + NB + s); };
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + 2 + s); };
+  const uint32_t x_bar = bar_base + 8u * (2 * NS + 2 * NB + 4);   // FUSE_UPD: the x_t tile of the current round has landed
 
   pdl_launch_dependents();
   const int nch = p.nch0 + p.nch1;
@@ -116,10 +123,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), kIssuers); }
     for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), kIssuers); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), CG2 ? 16 : 8); }
+    if (FUSE_UPD) ptx::mbar_init(x_bar, 4);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
     if (STAGED) ptx::prefetch_tmap(&mapY);
+    if (FUSE_UPD) ptx::prefetch_tmap(&mapZ);
   }
   if (warp == 2) {
     if (CG2) { ptx::tmem_alloc_cg2(ptx::smem_u32(tmem_ptr_smem), kTmemCols); ptx::tmem_relinquish_cg2(); }
@@ -302,6 +311,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     uint32_t it = 0;
     int ti = 0;
     uint32_t nstore = 0;   // staged epilogue: plane stores issued so far (selects the staging buffer)
+    // fused update: the step's coefficients, Philox key and sample base (uniform over the launch)
+    upd::Coef uk = {};
+    uint64_t useed = 0;
+    int64_t usid0 = 0;
+    bool ugen = false;
+    uint32_t xround = 0;   // rounds so far: parity of the x_t barrier
+    if constexpr (FUSE_UPD) {
+      uk = upd::load_coef(p.upd);
+      useed = p.upd.seed; usid0 = p.upd.sample_id0;
+      if ((p.upd.reserved & 1) && p.upd.t_dev) {
+        useed = (uint64_t)(uint32_t)p.upd.t_dev[4] | ((uint64_t)(uint32_t)p.upd.t_dev[5] << 32);
+        usid0 += (int64_t)((uint64_t)(uint32_t)p.upd.t_dev[6] | ((uint64_t)(uint32_t)p.upd.t_dev[7] << 32));
+      }
+      ugen = p.upd.sampler == 0 && uk.t > 0;
+    }
     for (int id = first_tile; id < p.halo_total_tiles; id += tile_step, ++it) {
       const Tile t = decode_tile<PAIR>(p, id);
       const uint32_t as = it & 1;
@@ -309,7 +333,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int colt = t.n_tile * BLOCK_N + cbase;       // first output channel of this warp
       // residual rows of this thread -> registers while the MMAs of this tile are still running
       bf16x8 rpre[TD][kChunks][2];
-      const bool pre = p.residual != nullptr && active && colt + kHalfCols <= p.c_out;
+      const bool pre = !FUSE_UPD && p.residual != nullptr && active && colt + kHalfCols <= p.c_out;
       if (pre) {
 #pragma unroll
         for (int pl = 0; pl < TD; ++pl) {
@@ -322,12 +346,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
         }
       }
-      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 10);
-      const bool ok = ptx::mbar_wait(tmem_full(as), (it >> 1) & 1, p.dbg, 16);
-      ptx::tc_fence_after();
-      if (!ok) break;
-      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 11);
-      // bias + temb row of this tile's sample -> smem once per tile (double-buffered by accumulator stage)
+      if constexpr (FUSE_UPD) {
+        // x_t of this thread's rows (two 128-byte lines per plane and column half) -> L2 while the tile's MMAs run: without
+        // it every other round's TMA load of the x_t tile was a DRAM miss that the round's noise generation could not cover
+        // (4.2 k instead of 2.3 k cycles)
+        if (ow < p.out_w && oh < p.out_h) {
+#pragma unroll
+          for (int pl = 0; pl < TD; ++pl) {
+            const int od = t.d0 + pl;
+            if (od < p.out_d) {
+              const float* xr = p.upd_x + ((int64_t)t.n * vox_per + ((int64_t)od * p.out_h + oh) * p.out_w + ow) * p.c_out + colt;
+#pragma unroll
+              for (int c = 0; c < kHalfCols / 32; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + c * 32));
+            }
+          }
+        }
+      }
+      // bias + temb row of this tile's sample -> smem once per tile (double-buffered by accumulator stage), BEFORE the
+      // accumulator is ready: the two dependent global round trips (t_dev, then the table rows: ~1.5 k cycles) overlap the
+      // tile's MMAs instead of heading its epilogue.  The buffer was last read in tile it - 2; every epilogue thread has
+      // passed a bar.sync of tile it - 1 since.
       float* bs = bias_s + as * 2 * BLOCK_N;
       float* scs = bs + BLOCK_N;
       const bool has_bs = p.bias != nullptr || p.chan_bias != nullptr || p.out_scale != nullptr;
@@ -341,7 +379,69 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         stage_bias(p, bs, scs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128, 256);
         epilogue_bar_sync256();
       }
-      if (STAGED && p.y_f32) {
+      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 10);
+      const bool ok = ptx::mbar_wait(tmem_full(as), (it >> 1) & 1, p.dbg, 16);
+      ptx::tc_fence_after();
+      if (!ok) break;
+      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 11);
+      if constexpr (FUSE_UPD) {
+        // eps tile -> x_{t-1}: rounds of 32 columns per thread (one 128-byte line of x_t, fetched one round ahead into
+        // registers), fp32 result + 16-bit copy staged in shared memory, two TMA stores per column half and round
+        // Rounds of 16 columns per thread; the staging is two SETS of tiles (per column half: 128 rows x 16 fp32 = 8 KB and
+        // x 16 bit = 4 KB), used alternately: round q writes set q & 1 while the TMA stores of round q - 1 still read the other
+        // one, so no round waits for its predecessor's stores (with one set of 32-column tiles that wait was 2.5 k of a
+        // 7.6 k-cycle round).
+        constexpr int kRounds = kHalfCols / 16, kQ = TD * kRounds;
+        const uint32_t sample = (uint32_t)(usid0 + t.n);
+        bool xok = true;
+        // (not unrolled: one round is ~1 k instructions -- Philox, Box-Muller, the posterior -- and eight copies of it would
+        // not fit the instruction cache next to the issuer / producer loops)
+#pragma unroll 1
+        for (int q = 0; q < kQ && xok; ++q, ++xround) {
+          const int pl = q / kRounds, rd = q % kRounds;
+          const int od = t.d0 + pl;
+          if (od >= p.out_d) break;   // CTA-uniform
+          const uint32_t set = xround & 1;
+          uint8_t* stg = stg_base + set * 16384 + half * 8192;
+          uint8_t* stg16 = stg16_base + set * 8192 + half * 4096;
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N + cbase;
+          // Four issuing threads, each with its own bulk-group bookkeeping, so that no single thread serialises six TMA
+          // instructions per round (~1.2 k cycles measured): lane 0 of warps 4 / 8 = the fp32 tile of column half 0 / 1 (x_t load +
+          // x_{t-1} store), lane 0 of warps 5 / 9 = its 16-bit tile.  x_bar (4 arrivals) completes when both x_t tiles have landed
+          // AND both 16-bit tiles of this set have been read by the stores of two rounds ago.  No bar.sync here: every thread
+          // passed the previous round's bar.sync, i.e. finished round q - 1, before any leader can get this far.
+          if (lane == 0 && (warp & 3) == 0) {
+            const int h = (warp - 4) >> 2;
+            ptx::bulk_wait_read_1();   // this thread's store of two rounds ago (same set) has read its tile
+            ptx::mbar_expect_tx(x_bar, 8192u);
+            ptx::tma_load_5d(ptx::smem_u32(stg_base + set * 16384 + h * 8192), &mapY, x_bar, t.n_tile * BLOCK_N + h * kHalfCols + rd * 16, t.w0,
+                             t.h0, od, t.n);
+          } else if (lane == 0 && (warp & 3) == 1) {
+            ptx::bulk_wait_read_1();
+            ptx::mbar_arrive(x_bar);
+          }
+          if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 13);
+          uint32_t ra[16];
+          ptx::tc_ld_32x32b_x16(taddr + rd * 16, ra);
+          ptx::tc_wait_ld();
+          const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;
+          const uint32_t ctr0 = (uint32_t)((vox * p.c_out + colt + rd * 16) >> 2);   // Philox counter = element / 4 of the sample
+          xok = upd_epilogue16(p, ra, r, has_bs ? bs + cbase + rd * 16 : nullptr, has_sc ? scs + cbase + rd * 16 : nullptr, uk, ugen, ctr0,
+                               sample, useed, stg, stg16, x_bar, xround & 1);
+          if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 14);
+          ptx::fence_proxy_async();
+          epilogue_bar_sync256();
+          if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 15);
+          if (lane == 0 && (warp & 3) < 2) {
+            const int h = (warp - 4) >> 2, col = t.n_tile * BLOCK_N + h * kHalfCols + rd * 16;
+            if ((warp & 3) == 0) ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + set * 16384 + h * 8192), col, t.w0, t.h0, od, t.n);
+            else ptx::tma_store_5d(&mapZ, ptx::smem_u32(stg16_base + set * 8192 + h * 4096), col, t.w0, t.h0, od, t.n);
+            ptx::bulk_commit_group();
+          }
+        }
+        if (!xok) break;
+        nstore = 0;
+      } else if (STAGED && p.y_f32) {
         // fp32 output (eps of the U-Net): 32-column groups of 128-byte rows; the staging area (two 16 KB slots) holds one
         // group per column half, so BLOCK_N = 128 takes two rounds per plane
         constexpr int kRounds = kHalfCols / 32;
@@ -390,6 +490,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             if (kBufs == 2) ptx::bulk_wait_read_1(); else ptx::bulk_wait_read_all();
           }
           epilogue_bar_sync256();
+          if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 13);
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N + cbase;
 #pragma unroll
           for (int c = 0; c < kChunks; c += 2) {
@@ -404,8 +505,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               conv_epilogue16_staged(p, rb, r, cl0 + c * 16 + 16, col0 + 16, has_bs ? bs + cbase + c * 16 + 16 : nullptr, nullptr,
                                      has_sc ? scs + cbase + c * 16 + 16 : nullptr, nullptr, stg, pre, rpre[pl][c + 1 < kChunks ? c + 1 : c], kRow64);
           }
+          if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 14);
           ptx::fence_proxy_async();
           epilogue_bar_sync256();
+          if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 15);
           if (warp == 4 && lane == 0) {
             for (int g = 0; g < kNG; ++g)
               if (t.n_tile * BLOCK_N + g * 64 < p.c_out) {
@@ -454,7 +557,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         else ptx::mbar_arrive(tmem_empty(as));
       }
     }
-    if (STAGED && warp == 4 && lane == 0) ptx::bulk_wait_read_all();   // smem must outlive the last store's reads
+    if (STAGED && lane == 0 && (warp == 4 || (FUSE_UPD && (warp & 3) < 2))) ptx::bulk_wait_read_all();   // smem must outlive the last store's reads
   }
   ptx::tc_fence_before();
   __syncthreads();

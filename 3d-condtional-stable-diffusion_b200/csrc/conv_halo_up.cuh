@@ -224,9 +224,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const UTile t = decode(id);
       const uint32_t as = it & 1;
       const int colt = t.nt * BLOCK_N + cbase;
-      const bool ok = ptx::mbar_wait(tmem_full(as), (it >> 1) & 1, p.dbg, 46);
-      ptx::tc_fence_after();
-      if (!ok) break;
+      // bias staging before the accumulator is ready (see conv_halo.cuh): its global round trips overlap the tile's MMAs
       float* bs = bias_s + as * 2 * BLOCK_N;
       float* scs = bs + BLOCK_N;
       const bool has_bs = p.bias != nullptr || p.chan_bias != nullptr || p.out_scale != nullptr;
@@ -240,6 +238,9 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         stage_bias(p, bs, scs, t.nt * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128, 256);
         epilogue_bar_sync256();
       }
+      const bool ok = ptx::mbar_wait(tmem_full(as), (it >> 1) & 1, p.dbg, 46);
+      ptx::tc_fence_after();
+      if (!ok) break;
 #pragma unroll
       for (int pl = 0; pl < TD; ++pl) {
         const int od = t.d0 + pl;            // low-resolution (M-space) plane; the parity map places it at 2 * od + pd

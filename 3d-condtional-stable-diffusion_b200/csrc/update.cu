@@ -4,89 +4,16 @@
 // (networks/dm3d.py:477-508, 516-530).  Arithmetic follows the reference op by op in fp32
 // (__fmul_rn/__fadd_rn/__fdiv_rn forbid FMA contraction so the result matches separate TF ops).
 #include "common.cuh"
+#include "update_math.cuh"
 
 namespace {
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t (&out)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-// Box-Muller on the SFU paths: lg2/sin/cos/sqrt approximations (abs error of z < 4e-6, checked against the numpy oracle
-// at 2e-5); the angle is folded to [-pi, pi) where sin.approx / cos.approx are at their best:
-// cos(2 pi u) = -cos(2 pi (u - 1/2)), same for sin.  (The libm forms cost ~70 instructions per pair and made the update
-// pass instruction-bound: 4.5 TB/s.)
-__device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
-  const float u1 = __fadd_rn(__fmul_rn((float)(ra >> 8), 5.9604644775390625e-8f), 2.98023223876953125e-8f);
-  const float u2 = __fmul_rn((float)(rb >> 8), 5.9604644775390625e-8f);
-  float rad;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
-  const float a = 6.283185307179586f * (u2 - 0.5f);
-  z0 = -rad * __cosf(a);
-  z1 = -rad * __sinf(a);
-}
-
-__device__ __forceinline__ void normal4(uint32_t ctr, uint32_t step, uint32_t sample, uint32_t stream, uint64_t seed,
-                                        float (&z)[4]) {
-  uint32_t r[4];
-  philox4x32_10(ctr, step, sample, stream, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  box_muller(r[0], r[1], z[0], z[1]);
-  box_muller(r[2], r[3], z[2], z[3]);
-}
-
-struct Coef {
-  float sq1ab, sqab, c1, c2, sigma, sqab_p, sq1ab_p;
-  int t, t_prev;
-};
-
-__device__ __forceinline__ Coef load_coef(const b200dm_update_desc& d) {
-  Coef k;
-  k.t = d.t_dev ? d.t_dev[0] : d.t;
-  k.t_prev = d.t_dev ? d.t_dev[1] : d.t_prev;
-  const int t = k.t;
-  const float b = d.beta[t], sqa = d.sqrt_alpha[t], ab = d.alpha_bar[t], abp = d.alpha_bar_prev[t];
-  const float sqabp = d.sqrt_alpha_bar_prev[t];
-  k.sqab = d.sqrt_alpha_bar[t];
-  k.sq1ab = d.sqrt_one_minus_alpha_bar[t];
-  const float om = __fsub_rn(1.0f, ab);
-  k.c1 = __fdiv_rn(__fmul_rn(b, sqabp), om);                     // b*sqab_prev/(1-ab)
-  k.c2 = __fdiv_rn(__fmul_rn(__fsub_rn(1.0f, abp), sqa), om);     // (1-ab_prev)*sqa/(1-ab)
-  const float var = __fdiv_rn(__fmul_rn(__fsub_rn(1.0f, abp), b), om);
-  k.sigma = expf(0.5f * logf(fmaxf(var, 1e-20f)));                // exp(0.5*log(max(var,1e-20)))
-  if (d.sampler == 1 && k.t_prev >= 0) {
-    k.sqab_p = d.sqrt_alpha_bar[k.t_prev];
-    k.sq1ab_p = d.sqrt_one_minus_alpha_bar[k.t_prev];
-  } else {
-    k.sqab_p = 1.0f; k.sq1ab_p = 0.0f;
-  }
-  return k;
-}
-
-__device__ __forceinline__ float step_one(const Coef& k, int sampler, float x, float e, float z) {
-  const float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sq1ab, e)), k.sqab);
-  if (sampler == 0) {
-    float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, x));
-    mean = fminf(fmaxf(mean, -1.0f), 1.0f);
-    return (k.t > 0) ? __fadd_rn(mean, __fmul_rn(k.sigma, z)) : mean;
-  }
-  const float x0c = fminf(fmaxf(x0, -1.0f), 1.0f);
-  if (k.t_prev < 0) return x0c;
-  return __fadd_rn(__fmul_rn(k.sqab_p, x0c), __fmul_rn(k.sq1ab_p, e));
-}
+using namespace upd;
 
 // 8 elements per thread per trip (two Philox counters), two trips in flight: 4x LDG.128 x_t, 2-4x LDG.128 eps issued before
 // any use; grid = (blocks, batch) so the loop has no index division.
 template <bool kEpsBf16>
-__global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const float* __restrict__ x_t,
+__global__ void __launch_bounds__(256, 4) update_kernel(b200dm_update_desc d, const float* __restrict__ x_t,
                                                      const void* __restrict__ eps, const float* __restrict__ noise,
                                                      float* __restrict__ x_prev, act_t* __restrict__ x_bf16) {
   pdl_launch_dependents();
@@ -142,8 +69,7 @@ __global__ void __launch_bounds__(256) update_kernel(b200dm_update_desc d, const
         for (int q = 0; q < 8; ++q) z[q] = 0.0f;
       }
       float y[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) y[q] = step_one(k, d.sampler, x[u][q], e[u][q], z[q]);
+      step_vec(k, d.sampler, x[u], e[u], z, y);
       *reinterpret_cast<float4*>(x_prev + off) = *reinterpret_cast<float4*>(&y[0]);
       *reinterpret_cast<float4*>(x_prev + off + 4) = *reinterpret_cast<float4*>(&y[4]);
       if (x_bf16) *reinterpret_cast<bf16x8*>(x_bf16 + off) = pack8(y);

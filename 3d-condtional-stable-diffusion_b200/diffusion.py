@@ -103,10 +103,10 @@ class DiffusionModel:
             c -= 1
         return c
 
-    def _compile(self, batch, sampler, inject_noise, seed, sample_id0):
+    def _compile(self, batch, sampler, inject_noise, seed, sample_id0, fuse_update=False):
         # the compiled copies hold PACKED weights: key on the network's weights version so that network.set_weights /
         # network.load_weights is never followed by sampling with the old weights
-        key = (batch, sampler, inject_noise, self._num_chains(batch), self.network.weights_version)
+        key = (batch, sampler, inject_noise, self._num_chains(batch), self.network.weights_version, bool(fuse_update))
         if self._step is not None and self._step["key"] == key:
             return self._step   # seed / sample base are device-resident (t_dev[4..7]): the captured graph serves every call
         L.require_gpu()
@@ -123,14 +123,29 @@ class DiffusionModel:
         noise = torch.zeros_like(x) if inject_noise else None
         descs = [ops.make_update_desc(self.b, x[0].numel(), cb, 0, -1, 1 if sampler == "ddim" else 0, 0,
                                       c * cb, L.F32, t_dev=t_dev, seed_on_device=True) for c in range(chains)]
+        # Fused update: the output conv's epilogue turns its eps tile straight into x_{t-1} (+ the 16-bit copy that is the next
+        # step's network input) -- no fp32 eps round trip through HBM, no update launch.  Same arithmetic and noise stream as
+        # the update kernel (bit-identical latents); needs the Philox path (no injected noise) and an output conv on the
+        # CTA-pair fp32 kernel (C_lat % 128 == 0, planes >= 8 x 16), else the two-kernel form stays.
+        fused = False
+        if fuse_update and not inject_noise:
+            oks = []
+            for c, net in enumerate(nets):
+                plan = net.prog.producers.get(net.eps.data_ptr())
+                xs = x[c * cb:(c + 1) * cb]
+                oks.append(plan is not None and plan.set_fused_update(descs[c], xs, xs, net.x_in))
+            fused = all(oks)
+            assert fused or not any(oks), "fused update: the chains' output convs differ"
         self._step = dict(key=key, nets=nets, net=nets[0], x=x, noise=noise, descs=descs, t_dev=t_dev, t_seq=t_seq, graph=None, dev=dev,
-                          chains=chains, chain_batch=cb, streams=None)
+                          chains=chains, chain_batch=cb, streams=None, fused=fused)
         return self._step
 
     def _run_chain(self, st, c):
         """U-Net forward of chain c -> fused update of its samples (x in place, bf16 copy into the U-Net input)."""
         cb, net = st["chain_batch"], st["nets"][c]
         net.prog.run()
+        if st["fused"]:   # the output conv has already written x_{t-1} and the next network input
+            return
         xs = st["x"][c * cb:(c + 1) * cb]
         nz = st["noise"][c * cb:(c + 1) * cb] if st["noise"] is not None else None
         L.check(L.lib().b200dm_ddpm_update(ctypes.byref(st["descs"][c]), L.ptr(xs), L.ptr(net.eps), L.ptr(nz), L.ptr(xs),
@@ -169,11 +184,13 @@ class DiffusionModel:
         return g
 
     def generate(self, shape=(1, 16, 16, 16, 16), last_step=0, context_value=None, *, x_T=None, noise=None, seed=None,
-                 sample_id0=0, sampler="ddpm", steps=None, context=None, use_graph=True, on_step=None, timestep_seq=None):
+                 sample_id0=0, sampler="ddpm", steps=None, context=None, use_graph=True, on_step=None, timestep_seq=None,
+                 fuse_update=None):
         """Reverse diffusion from t=T-1 down to ``last_step`` (dm3d.py:510-532).  ``noise``: callable i -> tensor or
         dict/sequence indexed by timestep, injected instead of the Philox stream (parity tests).  ``seed=None`` draws a fresh
         seed per call (the reference draws fresh tf.random.normal noise on every call); it is kept in ``self.last_seed``.
         ``sampler="ddim"`` with ``steps=n`` (or an explicit descending ``timestep_seq``) walks a sub-sequence of the schedule.
+        ``fuse_update`` (default: on when possible) runs the update inside the output conv's epilogue (see _compile).
         The timestep sequence lives in device memory and the captured step graph indexes it, so every sequence -- DDPM ranges,
         strided or non-uniform DDIM -- replays the same graph with no host work between steps.  Returns fp32 latents."""
         shape = tuple(shape)
@@ -182,7 +199,10 @@ class DiffusionModel:
         if seed is None:
             seed = int.from_bytes(os.urandom(7), "little")
         self.last_seed = seed
-        st = self._compile(B, sampler, noise is not None, seed, sample_id0)
+        if fuse_update is None:   # default: on whenever nothing needs eps_hat in HBM (B200DM_FUSE_UPDATE=0 under B200DM_TUNING=1: off)
+            fuse_update = noise is None and on_step is None and L.tuning_env("B200DM_FUSE_UPDATE", "1") != "0"
+        assert not (fuse_update and (noise is not None or on_step is not None)), "fuse_update: no injected noise / eps callback"
+        st = self._compile(B, sampler, noise is not None, seed, sample_id0, fuse_update)
         dev, nets, cb = st["dev"], st["nets"], st["chain_batch"]
         if self.conditional:
             ctx = context if context is not None else (0 if context_value is None else context_value)

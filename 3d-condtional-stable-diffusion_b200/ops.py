@@ -270,6 +270,17 @@ class ConvPlan:
         self.keep = self.keep + (y_side, scale, shift)
         return True
 
+    def set_fused_update(self, upd_desc, x_t, x_prev, x_prev_16):
+        """Output conv of the U-Net only: the epilogue applies the reverse-diffusion update to its eps tile and stores
+        x_{t-1} (fp32 -> ``x_prev`` = ``x_t``, in place; 16-bit copy -> ``x_prev_16``) instead of eps.  False when the plan's
+        kernel cannot (the caller then runs the stand-alone update kernel on the conv's eps output)."""
+        rc = lib().b200dm_conv_plan_set_fused_update(self.h, C.byref(upd_desc), ptr(x_t), ptr(x_prev), ptr(x_prev_16))
+        if rc == L.ERR_UNSUPPORTED:
+            return False
+        check(rc)
+        self.keep = self.keep + (x_t, x_prev, x_prev_16, upd_desc)
+        return True
+
     def run(self):
         check(lib().b200dm_conv_plan_run(self.h, stream()))
         return self.y

@@ -267,6 +267,13 @@ int b200dm_conv_plan_add_output(b200dm_conv_plan* p, void* y_extra, const float*
  * in shared memory -- the block's norm1 + swish (dm3d.py:235-236) without a second pass over x / skip.  Returns
  * B200DM_ERR_UNSUPPORTED when the plan cannot do it (the caller then runs b200dm_norm_act_fwd). */
 int b200dm_conv_plan_set_side_norm(b200dm_conv_plan* p, void* y_side, const float* scale, const float* shift, int32_t act);
+/* Fuse the reverse-diffusion update (b200dm_ddpm_update: DiffusionModel.sample + the loop body of generate, networks/dm3d.py:
+ * 477-508, 516-530) into the epilogue of the U-Net's output conv (dm3d.py:373-374, the fp32 eps_hat): the conv then stores
+ * x_{t-1} = step(x_t, eps_hat, Philox noise) to x_prev (fp32; must alias x_t: updated in place) and a copy in the 16-bit storage type to x_prev_16
+ * (the next step's network input) INSTEAD of eps_hat -- same arithmetic, same noise stream, no fp32 eps round trip through
+ * HBM and no separate update launch.  `u` is read as by b200dm_ddpm_update (tables, t_dev, seed, sample_id0, sampler; no injected
+ * noise).  Returns B200DM_ERR_UNSUPPORTED unless the plan is the CTA-pair 3^3 conv with fp32 output and C_out % 128 == 0. */
+int b200dm_conv_plan_set_fused_update(b200dm_conv_plan* p, const b200dm_update_desc* u, const float* x_t, float* x_prev, void* x_prev_16);
 /* which kernel / tile configuration the plan launches (profiling): halo 1 = persistent halo-reuse kernel */
 int b200dm_conv_plan_info(const b200dm_conv_plan* p, int32_t* halo, int32_t* block_n, int32_t* ksplit);
 /* GroupNorm statistics as a by-product of the producing conv (replaces a second read of the conv output by

@@ -250,3 +250,42 @@ def test_vqgan_family_decoders(cuda, variant, channels):
     r_e, r_x = rel(y, od.forward(P, z, Emu(True))), rel(y, od.forward(P, z))
     print(f"{variant} {channels} decoder: rel-L2 vs emu {r_e:.3e}, vs fp32 {r_x:.3e}")
     assert r_e <= 1e-2 and r_x <= 3e-2
+
+
+@pytest.mark.parametrize("sampler,cond,S,C_lat,B", [("ddpm", False, 16, 128, 2), ("ddim", False, 16, 128, 2), ("ddpm", True, 32, 256, 2)])
+def test_fused_update_equals_update_kernel(cuda, sampler, cond, S, C_lat, B):
+    """The reverse-diffusion update fused into the output conv's epilogue (b200dm_conv_plan_set_fused_update) against the
+    stand-alone update kernel on the conv's eps output: same arithmetic, same Philox stream -> bit-identical latents, for the
+    DDPM chain down to t = 0 (the noise-free last step) and for a strided DDIM sequence; sharding offset included."""
+    import b200dm
+    T = 20
+    args = types.SimpleNamespace(timesteps=T, num_gpus=1, kernel_resize=False, bs=B)
+    cls = b200dm.ConditionalDiffusionModel if cond else b200dm.DiffusionModel
+    dm = cls(S, 256, C_lat, None, args)
+    F = 32 if cond else 64
+    ou = OUNet(S, C_lat, [64, 128, 256], [False, False, True, True], first_conv_channels=F, conditional=cond)
+    P = OI.make_params(ou.spec(), 0, "stress")
+    # contraction-scaled output conv: a random-init eps_hat of 10-30x its input would saturate the clip (DDPM) or blow up (DDIM)
+    P["out.conv.kernel"] = P["out.conv.kernel"] * 0.05
+    dm.network.set_weights(P)
+    shape = (B, S, S, S, C_lat)
+    x_T = OI.normal(shape, 4321)
+    kw = dict(x_T=x_T, seed=99, sample_id0=3, sampler=sampler, last_step=T - 6)
+    if sampler == "ddim":
+        kw.update(steps=5, last_step=0)
+    if cond:
+        kw.update(context=torch.arange(B) % 2)
+    a = dm.generate(shape, fuse_update=False, **kw)
+    assert dm._step["fused"] is False
+    b = dm.generate(shape, fuse_update=True, **kw)
+    assert dm._step["fused"] is True, "the output conv of this configuration must take the fused update"
+    assert torch.isfinite(a).all() and a.abs().max() > 0.1
+    assert torch.equal(a, b), (a - b).abs().max().item()
+    if sampler == "ddpm":   # down to t = 0: the last step adds no noise
+        a0 = dm.generate(shape, fuse_update=False, **{**kw, "last_step": 0})
+        b0 = dm.generate(shape, **{**kw, "last_step": 0})     # default: fused whenever possible
+        assert dm._step["fused"] is True
+        assert torch.equal(a0, b0)
+        assert not torch.equal(a0, a)
+    from b200dm import _lib
+    assert _lib.debug_flag() == 0
