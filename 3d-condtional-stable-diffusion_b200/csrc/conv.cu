@@ -557,6 +557,7 @@ struct b200dm_conv_plan {
   bool pair = false;   // halo kernel on 8 x 8 planes: 8w x 8h x 2d tiles from pair slabs (conv_halo.cuh)
   int halo_td = 1, halo_nb = 4, halo_tps = 1;
   int halo_ns = 0;     // slab ring depth when a variant fixes it (0 = by epilogue kind)
+  const CUtensorMap& residual_map() const { return p.residual ? om.r : om.y[0]; }   // (a valid map either way: unused without a residual)
   bool fuse = false;   // CTA-pair N = 128 fp32 conv with the reverse-diffusion update fused into its epilogue (set_fused_update)
   bool stencil = false;   // C_out = 1, C_in = 32 3^3 conv: HBM-bound stencil-reduce kernel (conv_stencil.cuh)
   stencil::Params sp;
@@ -910,7 +911,9 @@ extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
         enc(&pl->mapB, kTmapAct16, 3, const_cast<void*>(w_packed), wdims, wstrides, wbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    if (!okm) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(sweep) failed"); return B200DM_ERR_CUDA; }
+    const bool okr = !residual || enc(&pl->om.r, kTmapAct16, 5, const_cast<void*>(residual), dims, strides, boxy, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (!okm || !okr) { delete pl; b200dm_set_error("cuTensorMapEncodeTiled(sweep) failed"); return B200DM_ERR_CUDA; }
     sweep::Params& wp = pl->wp;
     memset(&wp, 0, sizeof(wp));
     wp.D = d->in_d; wp.H = d->in_h; wp.W = d->in_w; wp.batch = d->batch;
@@ -1240,7 +1243,7 @@ extern "C" int b200dm_conv_plan_run(b200dm_conv_plan* pl, void* stream) {
       B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep::kSmem));
       attr_set = true;
     }
-    B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(sweep::kThreads), pl->smem, s, pl->mapS, pl->mapB, pl->om.y[0], pl->p, pl->wp));
+    B2_CHECK_CUDA(b2_launch(kern, pl->grid, dim3(sweep::kThreads), pl->smem, s, pl->mapS, pl->mapB, pl->om.y[0], pl->residual_map(), pl->p, pl->wp));
     return B200DM_OK;
   }
   if (pl->ups && pl->pair) return pl->g.block_n == 64 ? launch_halo_up<64, 4, 3, true>(pl, s) : launch_halo_up<128, 4, 2, true>(pl, s);

@@ -34,7 +34,7 @@ constexpr int kNS = 3;                      // slab ring
 constexpr int kR = 16;                      // TMEM ring: 16 slots x 32 columns = 512 columns
 constexpr int kWBytes = 27 * 2048;          // [kh*3+kw][kd][32 co][32 ci] bf16, one 2 KB SWIZZLE_64B tile per tap
 constexpr int kStgBytes = 8192;             // one plane tile: 128 rows x 64 B
-constexpr size_t kSmem = 1024 + (size_t)kNS * kSlabBytes + kWBytes + 4 * kStgBytes + (3 * kNS + 1 + 2 * kR) * 8 + 16 + 2 * 32 * 4 +
+constexpr size_t kSmem = 1024 + (size_t)kNS * kSlabBytes + kWBytes + 4 * kStgBytes + (3 * kNS + 1 + 2 * kR + 2) * 8 + 16 + 2 * 32 * 4 +
                          2 * 4 * 2 * 32 * 4;
 
 struct Params {
@@ -126,13 +126,13 @@ __device__ __forceinline__ void issue_plane(uint32_t tmem_base, uint32_t s0, uin
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
-                    const __grid_constant__ CUtensorMap mapY, const ConvParams p, const Params q) {
+                    const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapR, const ConvParams p, const Params q) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem + kNS * kSlabBytes;
   uint8_t* stg_base = w_s + kWBytes;                     // [group][2 buffers][8 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + 4 * kStgBytes);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * kNS + 1 + 2 * kR);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * kNS + 1 + 2 * kR + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [bias | scale][32]
   float* red_s = bias_s + 64;                                     // [group][quarter][half][16 columns][2]
 
@@ -144,6 +144,7 @@ conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   auto acc_full = [&](int s) { return bar_base + 8u * (2 * kNS + 1 + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kNS + 1 + kR + s); };
   auto slab_ready = [&](int s) { return bar_base + 8u * (2 * kNS + 1 + 2 * kR + s); };   // input transform done (6 warps)
+  auto res_bar = [&](int g) { return bar_base + 8u * (3 * kNS + 1 + 2 * kR + g); };   // residual tile of epilogue group g has landed
   const bool xform = q.in_mr != nullptr;
 
   pdl_launch_dependents();
@@ -152,10 +153,12 @@ conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     ptx::mbar_init(w_full, 1);
     for (int s = 0; s < kR; ++s) { ptx::mbar_init(acc_full(s), 1); ptx::mbar_init(acc_empty(s), 8); }
     for (int s = 0; s < kNS; ++s) ptx::mbar_init(slab_ready(s), 6);
+    ptx::mbar_init(res_bar(0), 1); ptx::mbar_init(res_bar(1), 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapX);
     ptx::prefetch_tmap(&mapW);
     ptx::prefetch_tmap(&mapY);
+    if (p.residual) ptx::prefetch_tmap(&mapR);
   }
   if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 32 * kR); ptx::tmem_relinquish(); }
   if (threadIdx.x >= 128 && threadIdx.x < 128 + 32) {   // bias / output affine of the 32 channels: constant for the whole launch
@@ -364,11 +367,16 @@ conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         if ((int)(G & 1) != e) continue;
         const int od = it.d0 + pq;
         const uint32_t sl = kR - 1 - G % kR;
-        bf16x8 rpre[2];
-        const bool pre = p.residual != nullptr && inb;
-        if (pre) {
-          const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + ((((int64_t)it.n * q.D + od) * q.H + oh) * q.W + ow) * kC + 16 * half);
-          rpre[0] = ldg_bf16x8(rp); rpre[1] = ldg_bf16x8(rp + 1);
+        // residual tile (the output tile's own box) -> TMA-loaded INTO this plane's staging buffer while the accumulator is
+        // still in flight; each thread later reads its 32 bytes from the chunks it overwrites with the result.  (Row-per-thread
+        // global loads of the residual cost the LSU ~16 lines per instruction: the conv2 launches ran 2.44 ms against 1.81 ms
+        // for the same conv without a residual.)
+        const bool res = p.residual != nullptr;
+        uint8_t* stg = stg_g + (nstore & 1) * kStgBytes;
+        if (res && gtid == 0) {
+          ptx::bulk_wait_read_1();   // the store that last used this buffer has finished reading it
+          ptx::mbar_expect_tx(res_bar(e), kStgBytes);
+          ptx::tma_load_5d(ptx::smem_u32(stg), &mapR, res_bar(e), 0, it.w0, it.h0, od, it.n);
         }
         if (trw) trace_ev(p, 1, ti, 10);
         ok = ptx::mbar_wait_sleep(acc_full(sl), (G / kR) & 1, p.dbg, 0x5305);
@@ -393,10 +401,13 @@ conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         if (p.act != B200DM_ACT_NONE) {
           apply_act_vec(v, p.act);
         }
-        if (pre) {
+        const int ch = 2 * half, sw = (r >> 1) & 3;   // 64-byte rows, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+        if (res) {
+          ok = ptx::mbar_wait_sleep(res_bar(e), nstore & 1, p.dbg, 0x5306, 32);
+          if (!ok) break;
           float a[16];
-          unpack8(rpre[0], *reinterpret_cast<float(*)[8]>(&a[0]));
-          unpack8(rpre[1], *reinterpret_cast<float(*)[8]>(&a[8]));
+          unpack8(*reinterpret_cast<const bf16x8*>(stg + r * 64 + (((ch) ^ sw) << 4)), *reinterpret_cast<float(*)[8]>(&a[0]));
+          unpack8(*reinterpret_cast<const bf16x8*>(stg + r * 64 + (((ch + 1) ^ sw) << 4)), *reinterpret_cast<float(*)[8]>(&a[8]));
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += a[j];
         }
@@ -424,14 +435,12 @@ conv_sweep32_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
           }
           sacc += w[0];
         }
-        uint8_t* stg = stg_g + (nstore & 1) * kStgBytes;
-        if (gtid == 0) ptx::bulk_wait_read_1();   // the store that last used this buffer has finished reading it
-        group_bar_sync(e);
-        {
-          const int ch = 2 * half, sw = (r >> 1) & 3;   // 64-byte rows, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
-          *reinterpret_cast<bf16x8*>(stg + r * 64 + (((ch) ^ sw) << 4)) = o0;
-          *reinterpret_cast<bf16x8*>(stg + r * 64 + (((ch + 1) ^ sw) << 4)) = o1;
+        if (!res) {   // (with a residual the buffer was claimed before its tile was loaded, and every thread has seen that load land)
+          if (gtid == 0) ptx::bulk_wait_read_1();   // the store that last used this buffer has finished reading it
+          group_bar_sync(e);
         }
+        *reinterpret_cast<bf16x8*>(stg + r * 64 + (((ch) ^ sw) << 4)) = o0;
+        *reinterpret_cast<bf16x8*>(stg + r * 64 + (((ch + 1) ^ sw) << 4)) = o1;
         ptx::fence_proxy_async();
         group_bar_sync(e);
         if (gtid == 0) {

@@ -25,7 +25,7 @@ else:
     seq = L[marks[-2]:marks[-1]]
 with open(f"profiles/{tag}_launches_{what}.csv", "w") as f:
     f.write(f"# {tag}: {cmd}\n# " + ("one cfg-3 quantize + decode pass (B=16): vq_kernel .. the decoder's head" if what == "decode" else
-            "one cfg-2 denoise step (graph replay): every launch from step_advance to the fused update") + "; cold-cache, serialised times\n")
+            "one cfg-2 denoise step (graph replay): every launch from one step_advance to the next (the update runs in out.conv's epilogue)") + "; cold-cache, serialised times\n")
     f.write("index,kernel,us\n")
     for i, (n, u) in enumerate(seq):
         f.write(f'{i},"{n}",{u:.3f}\n')
