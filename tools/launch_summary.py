@@ -13,16 +13,18 @@ ki, vi = h.index("Kernel Name"), h.index("Metric Value")
 L = []
 for r in rows[1:]:
     n = re.sub(r"\(.*$", "", re.sub(r"^void ", "", r[ki]))
-    n = re.sub(r"<unnamed>::|\(anonymous namespace\)::|halo::|sweep::|stencil::", "", n)
+    n = re.sub(r"<unnamed>::|\(anonymous namespace\)::|halo::|sweep::|stencil::|vqtc::", "", n)
     L.append((n, float(r[vi].replace(",", "")) / 1000.0))
 if what == "decode":   # one quantize + decode pass: from the last vq_kernel launch to the decoder's head (stencil) launch after it
-    a = max(i for i, (n, _) in enumerate(L) if n.startswith("vq_kernel"))
+    a = max(i for i, (n, _) in enumerate(L) if n.startswith("vq_kernel") or n.startswith("vq_tc_kernel"))
     b = min(i for i, (n, _) in enumerate(L) if i > a and "conv_stencil" in n)
     seq = L[a:b + 1]
 else:
     marks = [i for i, (n, _) in enumerate(L) if n.startswith("step_advance")]
     assert len(marks) >= 2, "need two step_advance launches in the list"
-    seq = L[marks[-2]:marks[-1]]
+    # the last cfg-2 step: bench.py also replays cfg-4 steps (level-0 self-attention: flash_attn_kernel<64, ...>) later in the run
+    segs = [L[a:b] for a, b in zip(marks, marks[1:]) if not any(n.startswith("flash_attn_kernel<64") for n, _ in L[a:b]) and b - a > 100]
+    seq = segs[-1]
 with open(f"profiles/{tag}_launches_{what}.csv", "w") as f:
     f.write(f"# {tag}: {cmd}\n# " + ("one cfg-3 quantize + decode pass (B=16): vq_kernel .. the decoder's head" if what == "decode" else
             "one cfg-2 denoise step (graph replay): every launch from one step_advance to the next (the update runs in out.conv's epilogue)") + "; cold-cache, serialised times\n")
