@@ -778,7 +778,7 @@ static int launch_halo_cg2_fused(const b200dm_conv_plan* pl, cudaStream_t s) {
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = pl->grid; cfg.blockDim = dim3(halo::kThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+  cfg.gridDim = pl->grid; cfg.blockDim = dim3(halo::kThreadsFused); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -832,7 +832,7 @@ static size_t halo_smem_bytes(const b200dm_conv_plan* pl) {
   const int ns = pl->fuse ? kHaloNSFused : pl->halo_ns ? pl->halo_ns : (pl->pair ? kHaloNSPair : (pl->wide ? kHaloNSWide : halo_ns_for(pl->g.block_n, st)));   // (cg2: 5, or 4 for pair slabs)
   return 1024 + (size_t)ns * (pl->pair ? 25 * 1024 : halo::kSlabBytes) +
          (size_t)pl->halo_nb * pl->halo_tps * (pl->cg2 ? pl->g.block_n / 2 : pl->g.block_n) * 128 +
-         (size_t)halo::stage_bytes(pl->g.block_n, st) + (pl->fuse ? halo::kFuseStage16Bytes + 16 : 0) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
+         (size_t)halo::stage_bytes(pl->g.block_n, st) + (pl->fuse ? halo::kFuseStage16Bytes + 32 : 0) + (2 * ns + 2 * pl->halo_nb + 4) * 8 + 16 + 4 * pl->g.block_n * 4;
 }
 
 extern "C" int b200dm_conv_plan_create(const b200dm_conv_desc* d, const void* x0, const void* x1, const void* w_packed,

@@ -25,6 +25,7 @@
 namespace halo {
 
 constexpr int kThreads = 384;
+constexpr int kThreadsFused = 416;         // FUSE_UPD: + one warp that owns the epilogue's TMA traffic (see the kernel)
 constexpr int kSlabBytes = 23 * 1024;      // 180 voxels x 128 B = 23040, rounded up to the 1024-B swizzle period
 constexpr int kSlabTx = 180 * 128;
 
@@ -69,7 +70,7 @@ constexpr int stage_bytes(int block_n, bool staged) { return staged ? stage_bufs
 // FUSE_UPD (BLOCK_N = 128, fp32 staged output: the U-Net's eps conv on the sampling graph): the epilogue applies the
 // reverse-diffusion update to its tile -- see ConvParams::upd_x.  mapY then addresses x_{t-1} (fp32) and mapZ its 16-bit copy.
 template <int BLOCK_N, int TD, int NS, int NB, int TPS, bool STAGED, bool PAIR = false, bool CG2 = false, bool FUSE_UPD = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(FUSE_UPD ? kThreadsFused : kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapY,
                  const __grid_constant__ CUtensorMap mapZ, const ConvParams p) {
@@ -98,7 +99,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint8_t* stg_base = b_ring + NB * kBBytes;   // (1024-aligned: slabs and weight stages are multiples of 1 KB)
   uint8_t* stg16_base = stg_base + stage_bytes(BLOCK_N, STAGED);   // FUSE_UPD: two 8 KB tiles (128 rows x 32 x 16 bit)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg16_base + (FUSE_UPD ? kFuseStage16Bytes : 0));
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4 + (FUSE_UPD ? 2 : 0));   // (+1 x_t barrier, +1 pad)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4 + (FUSE_UPD ? 4 : 0));   // (+2 x_t barriers, +1 written, +1 pad)
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [2 acc stages][bias | scale][BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,7 +112,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * NS + NB + s); };
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + 2 + s); };
-  const uint32_t x_bar = bar_base + 8u * (2 * NS + 2 * NB + 4);   // FUSE_UPD: the x_t tile of the current round has landed
+  auto x_bar = [&](uint32_t set) { return bar_base + 8u * (2 * NS + 2 * NB + 4 + 2 * set); };   // FUSE_UPD: the x_t tiles of staging set `set` have landed
+  const uint32_t w_bar = bar_base + 8u * (2 * NS + 2 * NB + 5);   // FUSE_UPD: the 256 epilogue threads have written the round's tiles
 
   pdl_launch_dependents();
   const int nch = p.nch0 + p.nch1;
@@ -123,7 +125,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), kIssuers); }
     for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), kIssuers); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), CG2 ? 16 : 8); }
-    if (FUSE_UPD) ptx::mbar_init(x_bar, 4);
+    if (FUSE_UPD) { ptx::mbar_init(x_bar(0), 4); ptx::mbar_init(x_bar(1), 4); ptx::mbar_init(w_bar, 256); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
@@ -294,7 +296,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     }   // elected lane
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 =====================
     // Measured on B200 (64->64 @ 32^3): with 4 warps the epilogue of a tile took as long as the tile's MMA phase and any
     // extra work (residual read, SiLU) made the kernel epilogue-bound; two warps per lane quarter split the columns, and
@@ -346,22 +348,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
         }
       }
-      if constexpr (FUSE_UPD) {
-        // x_t of this thread's rows (two 128-byte lines per plane and column half) -> L2 while the tile's MMAs run: without
-        // it every other round's TMA load of the x_t tile was a DRAM miss that the round's noise generation could not cover
-        // (4.2 k instead of 2.3 k cycles)
-        if (ow < p.out_w && oh < p.out_h) {
-#pragma unroll
-          for (int pl = 0; pl < TD; ++pl) {
-            const int od = t.d0 + pl;
-            if (od < p.out_d) {
-              const float* xr = p.upd_x + ((int64_t)t.n * vox_per + ((int64_t)od * p.out_h + oh) * p.out_w + ow) * p.c_out + colt;
-#pragma unroll
-              for (int c = 0; c < kHalfCols / 32; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + c * 32));
-            }
-          }
-        }
-      }
       // bias + temb row of this tile's sample -> smem once per tile (double-buffered by accumulator stage), BEFORE the
       // accumulator is ready: the two dependent global round trips (t_dev, then the table rows: ~1.5 k cycles) overlap the
       // tile's MMAs instead of heading its epilogue.  The buffer was last read in tile it - 2; every epilogue thread has
@@ -405,21 +391,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           uint8_t* stg = stg_base + set * 16384 + half * 8192;
           uint8_t* stg16 = stg16_base + set * 8192 + half * 4096;
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + as * kAccCols + pl * BLOCK_N + cbase;
-          // Four issuing threads, each with its own bulk-group bookkeeping, so that no single thread serialises six TMA
-          // instructions per round (~1.2 k cycles measured): lane 0 of warps 4 / 8 = the fp32 tile of column half 0 / 1 (x_t load +
-          // x_{t-1} store), lane 0 of warps 5 / 9 = its 16-bit tile.  x_bar (4 arrivals) completes when both x_t tiles have landed
-          // AND both 16-bit tiles of this set have been read by the stores of two rounds ago.  No bar.sync here: every thread
-          // passed the previous round's bar.sync, i.e. finished round q - 1, before any leader can get this far.
-          if (lane == 0 && (warp & 3) == 0) {
-            const int h = (warp - 4) >> 2;
-            ptx::bulk_wait_read_1();   // this thread's store of two rounds ago (same set) has read its tile
-            ptx::mbar_expect_tx(x_bar, 8192u);
-            ptx::tma_load_5d(ptx::smem_u32(stg_base + set * 16384 + h * 8192), &mapY, x_bar, t.n_tile * BLOCK_N + h * kHalfCols + rd * 16, t.w0,
-                             t.h0, od, t.n);
-          } else if (lane == 0 && (warp & 3) == 1) {
-            ptx::bulk_wait_read_1();
-            ptx::mbar_arrive(x_bar);
-          }
+          // All TMA traffic of the round -- the x_t tiles in, x_{t-1} fp32 + 16-bit out -- is issued by the agent warp (warp 12,
+          // below): these threads only wait for the x_t tile (x_bar), and signal their writes (w_bar) without waiting for anyone.
           if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 13);
           uint32_t ra[16];
           ptx::tc_ld_32x32b_x16(taddr + rd * 16, ra);
@@ -427,17 +400,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           const int64_t vox = ((int64_t)od * p.out_h + oh) * p.out_w + ow;
           const uint32_t ctr0 = (uint32_t)((vox * p.c_out + colt + rd * 16) >> 2);   // Philox counter = element / 4 of the sample
           xok = upd_epilogue16(p, ra, r, has_bs ? bs + cbase + rd * 16 : nullptr, has_sc ? scs + cbase + rd * 16 : nullptr, uk, ugen, ctr0,
-                               sample, useed, stg, stg16, x_bar, xround & 1);
+                               sample, useed, stg, stg16, x_bar(set), (xround >> 1) & 1);
           if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 14);
-          ptx::fence_proxy_async();
-          epilogue_bar_sync256();
-          if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 15);
-          if (lane == 0 && (warp & 3) < 2) {
-            const int h = (warp - 4) >> 2, col = t.n_tile * BLOCK_N + h * kHalfCols + rd * 16;
-            if ((warp & 3) == 0) ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + set * 16384 + h * 8192), col, t.w0, t.h0, od, t.n);
-            else ptx::tma_store_5d(&mapZ, ptx::smem_u32(stg16_base + set * 8192 + h * 4096), col, t.w0, t.h0, od, t.n);
-            ptx::bulk_commit_group();
-          }
+          ptx::fence_proxy_async();      // this thread's tile writes -> visible to the TMA unit
+          ptx::mbar_arrive(w_bar);
         }
         if (!xok) break;
         nstore = 0;
@@ -557,7 +523,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         else ptx::mbar_arrive(tmem_empty(as));
       }
     }
-    if (STAGED && lane == 0 && (warp == 4 || (FUSE_UPD && (warp & 3) < 2))) ptx::bulk_wait_read_all();   // smem must outlive the last store's reads
+    if (STAGED && !FUSE_UPD && warp == 4 && lane == 0) ptx::bulk_wait_read_all();   // smem must outlive the last store's reads
+  }
+  if constexpr (FUSE_UPD) {
+    if (warp == 12 && lane < 4) {
+      // ===================== TMA agent of the fused update (4 lanes, each with its own bulk-group bookkeeping) =====================
+      // lane 0 / 2: the fp32 tile of column half 0 / 1 (x_t load, x_{t-1} store); lane 1 / 3: its 16-bit tile (store).  Per round:
+      // wait until the 256 epilogue threads have written the tiles of set r & 1 (w_bar), store them, wait until that store has
+      // read its tile, and request the x_t tiles of round r + 2 into the same set (x_bar[set]: 2 loads + 2 plain arrivals) -- a
+      // whole round before they are needed.  With the TMA instructions on epilogue lanes every round paid ~750 cycles of issue
+      // latency inside the warps that do the arithmetic, and the x_t tile of a round was requested only at its start.
+      constexpr int kHalfColsA = BLOCK_N / 2, kRoundsA = kHalfColsA / 16;
+      const int h = lane >> 1;
+      const bool f32 = (lane & 1) == 0;
+      auto rounds_of = [&](const Tile& t) { const int pls = p.out_d - t.d0 < TD ? p.out_d - t.d0 : TD; return pls * kRoundsA; };
+      auto request_x = [&](const Tile& t, int q, uint32_t rnd) {
+        if (f32) {
+          ptx::mbar_expect_tx(x_bar(rnd & 1), 8192u);
+          ptx::tma_load_5d(ptx::smem_u32(stg_base + (rnd & 1) * 16384 + h * 8192), &mapY, x_bar(rnd & 1),
+                           t.n_tile * BLOCK_N + h * kHalfColsA + (q % kRoundsA) * 16, t.w0, t.h0, t.d0 + q / kRoundsA, t.n);
+        } else {
+          ptx::mbar_arrive(x_bar(rnd & 1));
+        }
+      };
+      // look-ahead cursor: (tile id, round within the tile) of round `rnd + 2`
+      int id2 = first_tile, q2 = 0;
+      Tile t2 = decode_tile<PAIR>(p, id2 < p.halo_total_tiles ? id2 : 0);
+      auto advance2 = [&]() {
+        if (++q2 >= rounds_of(t2)) { q2 = 0; id2 += tile_step; if (id2 < p.halo_total_tiles) t2 = decode_tile<PAIR>(p, id2); }
+      };
+      for (uint32_t r0 = 0; r0 < 2 && id2 < p.halo_total_tiles; ++r0) { request_x(t2, q2, r0); advance2(); }   // both sets are free at the start
+      uint32_t rnd = 0;
+      bool ok = true;
+      for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step) {
+        const Tile t = decode_tile<PAIR>(p, id);
+        const int nq = rounds_of(t);
+        for (int q = 0; q < nq; ++q, ++rnd) {
+          ok = ptx::mbar_wait(w_bar, rnd & 1, p.dbg, 18);
+          if (!ok) break;
+          const int col = t.n_tile * BLOCK_N + h * kHalfColsA + (q % kRoundsA) * 16, od = t.d0 + q / kRoundsA;
+          if (f32) ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + (rnd & 1) * 16384 + h * 8192), col, t.w0, t.h0, od, t.n);
+          else ptx::tma_store_5d(&mapZ, ptx::smem_u32(stg16_base + (rnd & 1) * 8192 + h * 4096), col, t.w0, t.h0, od, t.n);
+          ptx::bulk_commit_group();
+          if (id2 < p.halo_total_tiles) {
+            ptx::bulk_wait_read_all();   // this lane's store has read its tile: the set may be refilled
+            request_x(t2, q2, rnd + 2);
+            advance2();
+          }
+        }
+      }
+      ptx::bulk_wait_read_all();   // smem must outlive the last stores' reads
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
