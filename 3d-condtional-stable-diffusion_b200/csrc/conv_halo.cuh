@@ -574,6 +574,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
       ptx::bulk_wait_read_all();   // smem must outlive the last stores' reads
     }
+    if (warp == 12) __syncwarp();   // the agent's four lanes rejoin their warp before the block-wide barrier
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -41,12 +41,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: false (and *flag = code) after ~2e9 cycles.
+// Bounded wait: false (and *flag = code) after ~8e9 cycles (~4 s: longer than any stall a healthy launch can see; a real deadlock still surfaces as an error code instead of a hang).
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* flag, int code) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) {
+    if (clock64() - t0 > 8000000000LL) {
       if (flag) atomicExch(flag, code);
       return false;
     }
@@ -61,7 +61,7 @@ __device__ __forceinline__ bool mbar_wait_sleep(uint32_t bar, uint32_t parity, i
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(ns);
-    if (clock64() - t0 > 2000000000LL) {
+    if (clock64() - t0 > 8000000000LL) {
       if (flag) atomicExch(flag, code);
       return false;
     }
