@@ -4,9 +4,9 @@
         -c 190 --csv --log-file gpurun_out/r2_halo_dram.csv python bench.py --steps 2 --warmup 3 --no-sustained --no-cfg3 --no-cpu
     python tools/ncu_traffic.py gpurun_out/r2_halo_dram.csv 38 "<command>"     ->  profiles/r2_traffic.json (read by bench.py)
 
-38 = halo launches of one cfg-2 step; the average is taken over whole steps only.  A 4th argument "drop-last" leaves the last
-halo launch of every step out of the average: out.conv, whose epilogue carries the fused posterior update (x_t read, x_{t-1}
-fp32 + 16-bit written) and is reported on its own by bench.py; its traffic goes to "fused_out_conv_bytes_per_launch"."""
+38 = halo launches of one cfg-2 step; the average is taken over whole steps only.  A 4th argument "drop-last" also reports the last
+halo launch of every step on its own: out.conv, whose epilogue carries the fused posterior update (x_t read, x_{t-1} fp32 +
+16-bit written): "fused_out_conv_bytes_per_launch", and the family average without it."""
 import collections, csv, json, os, re, sys
 
 src, per_step, cmd = sys.argv[1], int(sys.argv[2]), sys.argv[3]
@@ -23,16 +23,14 @@ launches = list(L.values())
 n = len(launches) // per_step * per_step
 sel = launches[len(launches) - n:]   # the last whole steps (the first launches of a process include cold weights / JIT effects)
 fused = [d for i, d in enumerate(sel) if i % per_step == per_step - 1] if drop_last else []
-if drop_last:
-    sel = [d for i, d in enumerate(sel) if i % per_step != per_step - 1]
-    n = len(sel)
-    per_step -= 1
+plain = [d for i, d in enumerate(sel) if i % per_step != per_step - 1] if drop_last else sel
 tot = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in sel)
 us = sum(d["gpu__time_duration.sum"] for d in sel)
 out = {"halo_bytes_per_launch": tot / n, "halo_launches_averaged": n, "halo_avg_us_under_ncu": us / n,
        "halo_read_bytes_per_launch": sum(d["dram__bytes_read.sum"] for d in sel) / n,
        "halo_write_bytes_per_launch": sum(d["dram__bytes_write.sum"] for d in sel) / n,
-       **({"fused_out_conv_bytes_per_launch": sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in fused) / len(fused),
+       **({"halo_bytes_per_launch_without_fused_out_conv": sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in plain) / len(plain),
+           "fused_out_conv_bytes_per_launch": sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in fused) / len(fused),
            "fused_out_conv_avg_us_under_ncu": sum(d["gpu__time_duration.sum"] for d in fused) / len(fused)} if fused else {}),
        "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over {n} conv_halo*_kernel launches ({n // per_step} cfg-2 steps) of: {cmd}"}
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
