@@ -99,7 +99,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint8_t* stg_base = b_ring + NB * kBBytes;   // (1024-aligned: slabs and weight stages are multiples of 1 KB)
   uint8_t* stg16_base = stg_base + stage_bytes(BLOCK_N, STAGED);   // FUSE_UPD: two 8 KB tiles (128 rows x 32 x 16 bit)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg16_base + (FUSE_UPD ? kFuseStage16Bytes : 0));
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4 + (FUSE_UPD ? 4 : 0));   // (+2 x_t barriers, +1 written, +1 pad)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NB + 4 + (FUSE_UPD ? 4 : 0));   // (+2 x_t barriers, +2 written barriers)
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [2 acc stages][bias | scale][BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,7 +113,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * NS + 2 * NB + 2 + s); };
   auto x_bar = [&](uint32_t set) { return bar_base + 8u * (2 * NS + 2 * NB + 4 + 2 * set); };   // FUSE_UPD: the x_t tiles of staging set `set` have landed
-  const uint32_t w_bar = bar_base + 8u * (2 * NS + 2 * NB + 5);   // FUSE_UPD: the 256 epilogue threads have written the round's tiles
+  // FUSE_UPD: the 256 epilogue threads have written the tiles of staging set `set`.  One barrier PER SET: the writers only arrive
+  // (they never wait on it), so a fast warp may arrive for round r + 1 before a slow warp has arrived for round r -- on a single
+  // barrier that second arrival would be counted into round r's phase (seen as x_bar time-outs at batch 1: phases slipped).
+  // Round r + 2 reuses round r's barrier, but nobody gets there before the agent has seen round r complete (x_bar[set]).
+  auto w_bar = [&](uint32_t set) { return bar_base + 8u * (2 * NS + 2 * NB + 5 + 2 * set); };
 
   pdl_launch_dependents();
   const int nch = p.nch0 + p.nch1;
@@ -125,7 +129,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), kIssuers); }
     for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), kIssuers); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), CG2 ? 16 : 8); }
-    if (FUSE_UPD) { ptx::mbar_init(x_bar(0), 4); ptx::mbar_init(x_bar(1), 4); ptx::mbar_init(w_bar, 256); }
+    if (FUSE_UPD) { ptx::mbar_init(x_bar(0), 4); ptx::mbar_init(x_bar(1), 4); ptx::mbar_init(w_bar(0), 256); ptx::mbar_init(w_bar(1), 256); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
@@ -403,7 +407,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                                sample, useed, stg, stg16, x_bar(set), (xround >> 1) & 1);
           if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 14);
           ptx::fence_proxy_async();      // this thread's tile writes -> visible to the TMA unit
-          ptx::mbar_arrive(w_bar);
+          ptx::mbar_arrive(w_bar(set));
         }
         if (!xok) break;
         nstore = 0;
@@ -559,7 +563,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const Tile t = decode_tile<PAIR>(p, id);
         const int nq = rounds_of(t);
         for (int q = 0; q < nq; ++q, ++rnd) {
-          ok = ptx::mbar_wait(w_bar, rnd & 1, p.dbg, 18);
+          ok = ptx::mbar_wait(w_bar(rnd & 1), (rnd >> 1) & 1, p.dbg, 18);
           if (!ok) break;
           const int col = t.n_tile * BLOCK_N + h * kHalfColsA + (q % kRoundsA) * 16, od = t.d0 + q / kRoundsA;
           if (f32) ptx::tma_store_5d(&mapY, ptx::smem_u32(stg_base + (rnd & 1) * 16384 + h * 8192), col, t.w0, t.h0, od, t.n);

@@ -252,11 +252,14 @@ def test_vqgan_family_decoders(cuda, variant, channels):
     assert r_e <= 1e-2 and r_x <= 3e-2
 
 
-@pytest.mark.parametrize("sampler,cond,S,C_lat,B", [("ddpm", False, 16, 128, 2), ("ddim", False, 16, 128, 2), ("ddpm", True, 32, 256, 2)])
+@pytest.mark.parametrize("sampler,cond,S,C_lat,B", [("ddpm", False, 16, 128, 2), ("ddim", False, 16, 128, 2), ("ddpm", True, 32, 256, 2),
+                                                     ("ddim", False, 32, 256, 1), ("ddpm", False, 32, 256, 1)])
 def test_fused_update_equals_update_kernel(cuda, sampler, cond, S, C_lat, B):
     """The reverse-diffusion update fused into the output conv's epilogue (b200dm_conv_plan_set_fused_update) against the
     stand-alone update kernel on the conv's eps output: same arithmetic, same Philox stream -> bit-identical latents, for the
-    DDPM chain down to t = 0 (the noise-free last step) and for a strided DDIM sequence; sharding offset included."""
+    DDPM chain down to t = 0 (the noise-free last step) and for a strided DDIM sequence; sharding offset included.  The batch-1
+    32^3 x 256 cases are the cfg-4 geometry (one or two tiles per CTA), where unevenly paced epilogue warps exposed a phase slip
+    of the fused epilogue's arrive-only barrier; they are repeated to give a rare interleaving a chance."""
     import b200dm
     T = 20
     args = types.SimpleNamespace(timesteps=T, num_gpus=1, kernel_resize=False, bs=B)
@@ -277,10 +280,13 @@ def test_fused_update_equals_update_kernel(cuda, sampler, cond, S, C_lat, B):
         kw.update(context=torch.arange(B) % 2)
     a = dm.generate(shape, fuse_update=False, **kw)
     assert dm._step["fused"] is False
-    b = dm.generate(shape, fuse_update=True, **kw)
-    assert dm._step["fused"] is True, "the output conv of this configuration must take the fused update"
+    from b200dm import _lib
+    for _ in range(8 if B == 1 else 1):
+        b = dm.generate(shape, fuse_update=True, **kw)
+        assert dm._step["fused"] is True, "the output conv of this configuration must take the fused update"
+        assert _lib.debug_flag() == 0, "tcgen05 / TMA watchdog"
+        assert torch.equal(a, b), (a - b).abs().max().item()
     assert torch.isfinite(a).all() and a.abs().max() > 0.1
-    assert torch.equal(a, b), (a - b).abs().max().item()
     if sampler == "ddpm":   # down to t = 0: the last step adds no noise
         a0 = dm.generate(shape, fuse_update=False, **{**kw, "last_step": 0})
         b0 = dm.generate(shape, **{**kw, "last_step": 0})     # default: fused whenever possible
