@@ -372,3 +372,7 @@ def test_fp16_build_meets_chain_tolerances(cuda):
     print("\n".join(lines))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert any("fp16" in ln for ln in lines)
+    # ... and the fused-update epilogue (16-bit copy tile, TMA agent) against the update kernel in that build
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_model_gpu.py"), "-m", "gpu",
+                        "-x", "-q", "-k", "fused_update"], env=env, cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
