@@ -55,8 +55,8 @@ class VectorQuantizer:
         return self._dev
 
     def get_code_indices(self, flattened_inputs, distribution=False):
-        """(N, D) -> (N,) int64; lowest index on ties.  ``distribution=True`` (the (N,K) distance matrix) is a
-        training-time diagnostic of the reference and is not part of this path."""
+        """(N, D) -> (N,) int64; lowest index on ties.  ``distribution=True`` returns the (N, K) fp32 squared-distance matrix
+        instead (the reference's training-time diagnostic, vqvae3d_monai.py:172-175)."""
         st = self._device_state()
         if distribution:   # the (N, K) squared-distance matrix itself (vqvae3d_monai.py:172-175), same fp32 arithmetic as the argmin
             x = flattened_inputs.contiguous()

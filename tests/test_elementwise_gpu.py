@@ -233,3 +233,23 @@ def test_vq_tensor_core_search_nonfinite_and_cfg3_margin(cuda):
     print(f"cfg-3 rows rechecked: {frac:.4%} at the proven margin, {int(st2[0]) / N:.4%} at 1/8 of it; mismatches at 1/8: {(i2 != i0).sum().item()}")
     assert torch.equal(i2, i0)
     assert L.debug_flag() == 0
+
+
+@pytest.mark.parametrize("layout", ["DK", "KD"])
+def test_vq_distribution_matrix(cuda, layout):
+    """VectorQuantizer.get_code_indices(x, distribution=True) (vqvae3d_monai.py:165-177): the (N, K) squared-distance matrix
+    ||x||^2 + ||e||^2 - 2 x.e itself, in the argmin's own fp32 arithmetic -- its row argmin IS get_code_indices(x), and it
+    matches the oracle's fp32 matrix to rounding (different summation order of the D-term dot products)."""
+    import b200dm
+    N, D, K = 333, 64, 96
+    vq = b200dm.VectorQuantizer(K, D, layout=layout)
+    cb = OI.codebook(K, D, layout, seed=3)
+    vq.set_embeddings(cb)
+    x = OI.normal((N, D), 7, 0.5 if layout == "KD" else 0.05)
+    dist = vq.get_code_indices(x.to(cuda), distribution=True)
+    assert tuple(dist.shape) == (N, K) and dist.dtype == torch.float32
+    ref = OF.code_distances(x, cb, layout)
+    scale = ref.abs().max().item()
+    assert (dist.cpu() - ref).abs().max().item() <= 2e-6 * max(scale, 1.0)
+    idx = vq.get_code_indices(x.to(cuda))
+    assert torch.equal(dist.argmin(1).cpu(), idx.cpu())      # torch.argmin: first minimum, like tf.argmin

@@ -200,3 +200,26 @@ def test_tuning_switches_need_the_tuning_gate(monkeypatch):
     assert L.tuning_env("B200DM_CHAINS", "1") == "1"
     monkeypatch.setenv("B200DM_TUNING", "1")
     assert L.tuning_env("B200DM_CHAINS", "1") == "4"
+
+
+def test_test_dm_script_flags():
+    """tools/test_dm.py mirrors the --test_dm invocation of main.py:428-448 / main_conditional_dm.py:195-215: the reference's flag
+    names parse with the reference's defaults, the modes outside the sampling path are accepted by the parser and refused at run
+    time (no GPU needed for either)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("test_dm_tool", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "test_dm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    a = mod.build_parser().parse_args(["--test_dm", "--suffix", "exp7", "--test_epoch", "100", "--timesteps", "300", "--vqvae_load_ckpt", "vq.ckpt"])
+    assert a.test_dm and a.suffix == "exp7" and a.test_epoch == 100 and a.timesteps == 300 and a.vqvae_load_ckpt == "vq.ckpt"
+    assert a.latent_size == 16 and a.num_embed == 256 and a.latent_channels == 64 and a.num_volumes == 10   # main.py:432-438, dm3d.py:539
+    assert a.lbs == 5 and a.num_gpus == 2 and not a.kernel_resize                                            # main.py:451-505 defaults
+    b = mod.build_parser().parse_args(["--train_dm", "--suffix", "x"])
+    with pytest.raises(SystemExit, match="--test_dm only"):
+        mod.run(b)
+    img = np.arange(12, dtype=np.float32).reshape(3, 4)
+    path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "b200dm_slice_test.pgm")
+    mod.write_pgm(path, img)
+    raw = open(path, "rb").read()
+    assert raw.startswith(b"P5\n4 3\n255\n") and len(raw) == len(b"P5\n4 3\n255\n") + 12 and raw[-1] == 255 and raw[len(b"P5\n4 3\n255\n")] == 0
+    os.remove(path)

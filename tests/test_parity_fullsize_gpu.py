@@ -345,6 +345,30 @@ def test_diffusion_model_test_writes_decoded_volumes(cuda, tmp_path):
     assert torch.equal(dm.generate((1, S, S, S, C), seed=9), dm.generate((1, S, S, S, C), seed=9))
 
 
+def test_slice_export_of_the_image_callback(cuda, tmp_path):
+    """tools/test_dm.py::export_slices = WandbImageCallback.on_epoch_end without wandb (conditional_dm3d.py:32-58): for context 0 and 1
+    generate one volume over all timesteps, decode, write images[:, :, :, slice_index, 0] of the first volume (.npy + 8-bit .pgm)."""
+    import importlib.util
+    import b200dm
+    spec = importlib.util.spec_from_file_location("test_dm_tool", os.path.join(ROOT, "tools", "test_dm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    S, C, T = 8, 8, 4
+    fs = b200dm.VQVAE(1, 1, (32, 64), 1, (32, 64), num_embeddings=16, embedding_dim=C, latent_size=S)
+    dm = b200dm.ConditionalDiffusionModel(S, 16, C, None, types.SimpleNamespace(timesteps=T, num_gpus=1, kernel_resize=False, bs=1), first_stage=fs)
+    paths = mod.export_slices(dm, str(tmp_path), "unit", seed=3)
+    flag_ok()
+    assert [os.path.basename(p) for p in paths] == ["unit-slice-ctx0", "unit-slice-ctx1"]
+    sl = [np.load(p + ".npy") for p in paths]
+    assert all(a.shape == (1, 32, 32) and np.isfinite(a).all() for a in sl)
+    # (with Keras-initialised weights the blocks' last convs are ~zero: the two contexts give the same volume; per-sample
+    # context parity is test_unet_cond_forward's job)
+    ref = dm.vqvae_trainer.decoder(dm.generate((1, S, S, S, C), last_step=0, seed=3, context_value=1))[:, :, :, 16, 0].float().cpu().numpy()
+    assert np.array_equal(sl[1], ref)
+    raw = open(paths[0] + ".pgm", "rb").read()
+    assert raw.startswith(b"P5\n32 32\n255\n") and len(raw) == len(b"P5\n32 32\n255\n") + 32 * 32
+
+
 def test_set_weights_invalidates_compiled_step(cuda):
     """network.set_weights after a generate() must not sample with the previously packed weights."""
     import b200dm
