@@ -128,7 +128,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(slab_full(s), 1); ptx::mbar_init(slab_empty(s), kIssuers); }
     for (int s = 0; s < NB; ++s) { ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), kIssuers); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), CG2 ? 16 : 8); }
+    // accumulator-stage release: one arrival per epilogue warp (both CTAs of a pair); FUSE_UPD: one per CTA, by the TMA agent
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tmem_full(s), kIssuers); ptx::mbar_init(tmem_empty(s), FUSE_UPD ? (CG2 ? 2 : 1) : (CG2 ? 16 : 8)); }
     if (FUSE_UPD) { ptx::mbar_init(x_bar(0), 4); ptx::mbar_init(x_bar(1), 4); ptx::mbar_init(w_bar(0), 256); ptx::mbar_init(w_bar(1), 256); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&mapA0);
@@ -333,10 +334,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       ugen = p.upd.sampler == 0 && uk.t > 0;
     }
     for (int id = first_tile; id < p.halo_total_tiles; id += tile_step, ++it) {
+      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 18);
       const Tile t = decode_tile<PAIR>(p, id);
       const uint32_t as = it & 1;
       const int ow = t.w0 + iw, oh = t.h0 + ih;
       const int colt = t.n_tile * BLOCK_N + cbase;       // first output channel of this warp
+      if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 19);
       // residual rows of this thread -> registers while the MMAs of this tile are still running
       bf16x8 rpre[TD][kChunks][2];
       const bool pre = !FUSE_UPD && p.residual != nullptr && active && colt + kHalfCols <= p.c_out;
@@ -367,6 +370,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           cbrow = p.chan_bias + ((int64_t)tt * p.chan_bias_rows + (p.chan_bias_rows > 1 ? t.n : 0)) * p.c_out;
         }
         stage_bias(p, bs, scs, t.n_tile * BLOCK_N, BLOCK_N, cbrow, threadIdx.x - 128, 256);
+        if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 20);
         epilogue_bar_sync256();
       }
       if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 10);
@@ -407,6 +411,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                                sample, useed, stg, stg16, x_bar(set), (xround >> 1) & 1);
           if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 14);
           ptx::fence_proxy_async();      // this thread's tile writes -> visible to the TMA unit
+          ptx::tc_fence_before();        // ... and its TMEM reads ordered before the arrival (the agent releases the stage on it)
           ptx::mbar_arrive(w_bar(set));
         }
         if (!xok) break;
@@ -522,7 +527,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       ptx::tc_fence_before();
       __syncwarp();
       if (warp == 4 && lane == 0) trace_ev(p, 1, ti, 12);
-      if (lane == 0) {
+      // (FUSE_UPD: the agent warp releases the accumulator stage once the tile's last round is complete -- the cluster-scope
+      // arrive costs the arriving warp ~2.5 k cycles, which these warps would pay at every tile boundary)
+      // Only a tile that has a successor two tiles on hands its accumulator stage back: nobody ever waits for the arrivals of a
+      // CTA's last two tiles, and the cluster-scope arrive costs the arriving warp 2-2.5 k cycles (clock64 timeline) -- on the
+      // one-tile CTAs of the 16^3 / 8^3 levels that was the tail of a fully exposed epilogue.
+      if (lane == 0 && !FUSE_UPD && id + 2 * tile_step < p.halo_total_tiles) {
         if (CG2) ptx::mbar_arrive_cluster(ptx::mapa_shared(tmem_empty(as), 0));   // the leader's issuers own the accumulators
         else ptx::mbar_arrive(tmem_empty(as));
       }
@@ -557,7 +567,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         if (++q2 >= rounds_of(t2)) { q2 = 0; id2 += tile_step; if (id2 < p.halo_total_tiles) t2 = decode_tile<PAIR>(p, id2); }
       };
       for (uint32_t r0 = 0; r0 < 2 && id2 < p.halo_total_tiles; ++r0) { request_x(t2, q2, r0); advance2(); }   // both sets are free at the start
-      uint32_t rnd = 0;
+      uint32_t rnd = 0, atile = 0;   // rounds / tiles so far
       bool ok = true;
       for (int id = first_tile; id < p.halo_total_tiles && ok; id += tile_step) {
         const Tile t = decode_tile<PAIR>(p, id);
@@ -574,7 +584,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             request_x(t2, q2, rnd + 2);
             advance2();
           }
+          if (q == nq - 1 && lane == 1 && id + 2 * tile_step < p.halo_total_tiles) {   // (nobody waits for the last two tiles' release)
+            // the tile's last round is complete: every epilogue thread has read its accumulators (tcgen05.ld -> fence -> w_bar):
+            // hand the TMEM stage back to the (leader's) MMA issuers
+            ptx::tc_fence_after();
+            ptx::tc_fence_before();
+            if (CG2) ptx::mbar_arrive_cluster(ptx::mapa_shared(tmem_empty(atile & 1), 0)); else ptx::mbar_arrive(tmem_empty(atile & 1));
+          }
         }
+        ++atile;
       }
       ptx::bulk_wait_read_all();   // smem must outlive the last stores' reads
     }
