@@ -143,7 +143,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG2) ptx::cluster_sync_all();   // the peer's barriers exist before anything signals them
+  if (CG2) ptx::cluster_sync_exit();   // the peer's barriers exist (fence_barrier_init above) before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();   // set-up above overlaps the previous kernel's tail
@@ -598,9 +598,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     if (warp == 12) __syncwarp();   // the agent's four lanes rejoin their warp before the block-wide barrier
   }
+  int tx = 0;   // (timeline region 3: kernel tail)
+  if (threadIdx.x == 128) trace_ev(p, 3, tx, 30);
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory / write its TMEM until here
+  if (threadIdx.x == 128) trace_ev(p, 3, tx, 31);
+  if (CG2) ptx::cluster_sync_exit();   // the leader's MMAs read the peer's shared memory / write its TMEM until here
+  if (threadIdx.x == 128) trace_ev(p, 3, tx, 32);
   if (warp == 2) {
     ptx::tc_fence_after();
     if (CG2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);

@@ -90,7 +90,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   if (warp == 2) { ptx::tmem_alloc_cg2(ptx::smem_u32(tmem_ptr_smem), kTmemCols); ptx::tmem_relinquish_cg2(); }
   ptx::tc_fence_before();
   __syncthreads();
-  ptx::cluster_sync_all();
+  ptx::cluster_sync_exit();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
@@ -286,7 +286,7 @@ conv_halo_up_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  ptx::cluster_sync_all();
+  ptx::cluster_sync_exit();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);

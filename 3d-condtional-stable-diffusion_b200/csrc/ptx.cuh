@@ -108,6 +108,13 @@ __device__ __forceinline__ uint32_t cluster_ctaid_y() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// The cluster barrier at a kernel's tail orders EXECUTION only (no CTA exits / frees TMEM while its peer may still touch it): every
+// memory effect that matters has been waited for before (tcgen05.wait::ld, mbarrier phases, bulk-group reads), so the arrival needs no
+// release fence.
+// (The same form after barrier initialisation: fence.mbarrier_init.release.cluster has already published the barriers.)
+__device__ __forceinline__ void cluster_sync_exit() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 // distributed shared memory: address of `local_smem_addr` in CTA `rank` of the cluster, and a 4-byte load from it
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t r;

@@ -44,8 +44,8 @@ torch.cuda.synchronize()
 t = tr.cpu().view(4, 2048)
 names = {1: "tile:begin", 2: "tile:tmem_empty ok", 3: "kd:slabs ready", 4: "kd:issued", 5: "b?", 6: "b:waited", 7: "b:pre", 10: "epi:wait", 11: "epi:tmem_full ok", 12: "epi:done", 13: "epi:buf free", 14: "epi:tile written", 15: "epi:synced", 16: "epi:acc in regs", 17: "epi:half done", 18: "epi:loop top", 19: "epi:tile decoded", 20: "epi:bias staged"}
 t0 = min(int(v) >> 8 for v in t[0] if int(v) != 0)
-names.update({30: "xf:wait", 31: "xf:slab landed", 32: "xf:done", 33: "xf:signalled"})
-for region, label in ((0, "MMA"), (1, "EPI"), (2, "SLAB"), (3, "XFORM")):
+names.update({30: "tail:roles done", 31: "tail:block synced", 32: "tail:cluster synced", 33: "xf:signalled"})
+for region, label in ((0, "MMA"), (1, "EPI"), (2, "SLAB"), (3, "TAIL")):
     prev = None
     out = []
     for v in t[region]:
